@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the shifted prox hot path on B200 (contract: see DESIGN.md §Measurement).
+
+Workload = BASELINE.json configs[1] ("C2"): ShiftedNormL0Box prox!, ShiftedRootNormLhalfBox prox! (vector
+l/u bounds) and ShiftedNormL0Box iprox! (diagonal d), n = 2^28 Float64 per GPU.  One step = those three
+launches over the batch.  `value` = elements/s over all ranks (3·n prox evaluations per step and rank) with
+operands resident in HBM; `e2e` = the same through the host-buffer C-ABI entry point (pinned host vectors,
+H2D and D2H inside the timed region); `roofline` = the dominant kernel against the measured HBM peak;
+`cpu_baseline` = the oracle port (one thread: the reference is single-threaded) on a bounded sample.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "shiftedproximaloperators.jl_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+SEED = 20261018
+LAMBDA, SIGMA = 1.0, 0.1
+# algorithmic bytes per element: Box prox! with vector bounds 6R, Box iprox! 7R
+ALG_BYTES = {"prox_l0box": 48, "prox_lhalfbox": 48, "iprox_l0box": 56}
+OPS = ("prox_l0box", "prox_lhalfbox", "iprox_l0box")
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--log2n", type=int, default=28)
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------ CPU reference arm ---
+def cpu_sample(n: int):
+    """The C2 step on n elements through the oracle port (one thread).  Returns seconds per op."""
+    import numpy as np
+
+    from oracle import oracle as orc
+
+    xk = orc.uniform(n, 0, np.float64, 4.0, -2.0)
+    sj = orc.uniform(n, 1, np.float64, 1.0, -0.5)
+    q = orc.uniform(n, 2, np.float64, 4.0, -2.0)
+    l = -(0.25 + orc.uniform(n, 3))
+    u = 0.25 + orc.uniform(n, 4)
+    b = orc.uniform(n, 6)
+    d = 0.5 + orc.uniform(n, 5)
+    d = np.where(b < 0.1, -d, d)
+    d = np.where((b >= 0.1) & (b < 0.2), 0.0, d)
+    t = {}
+    t0 = time.perf_counter(); orc.prox_box("l0", xk, sj, q, l, u, LAMBDA, SIGMA); t["prox_l0box"] = time.perf_counter() - t0
+    t0 = time.perf_counter(); orc.prox_box("lhalf", xk, sj, q, l, u, LAMBDA, SIGMA); t["prox_lhalfbox"] = time.perf_counter() - t0
+    t0 = time.perf_counter(); orc.iprox_box("l0", xk, sj, q, d, l, u, LAMBDA); t["iprox_l0box"] = time.perf_counter() - t0
+    return t
+
+
+def cpu_baseline(budget_s: float):
+    n = 1 << 20
+    t = cpu_sample(n)  # calibration (also warms the oracle build)
+    per_elt = sum(t.values()) / n
+    n2 = int(min(1 << 26, max(1 << 20, budget_s / max(per_elt, 1e-12))))
+    n2 = 1 << (n2.bit_length() - 1)
+    t = cpu_sample(n2)
+    total = sum(t.values())
+    return {
+        "value": 3 * n2 / total, "unit": "elements/s", "cores": 1, "kind": "port",
+        "sample": f"C2 step (L0Box prox!, LhalfBox prox!, L0Box iprox!) on n=2^{n2.bit_length() - 1} Float64, "
+                  f"oracle port g++ -O2 -ffp-contract=off, 1 thread (the reference is single-threaded Julia; "
+                  f"`julia` is not in the image), host has {os.cpu_count()} logical cores",
+        "seconds": total,
+        "per_op_elements_per_s": {k: n2 / v for k, v in t.items()},
+    }, total, n2
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    steps, warm = max(1, args.steps), args.warmup
+    # each step = a bounded sample of the workload; keep the whole run within a few minutes
+    n = 1 << 20
+    t = cpu_sample(n)
+    per_elt = sum(t.values()) / n
+    budget = 120.0 / (steps + warm)
+    n2 = int(min(1 << 26, max(1 << 18, budget / max(per_elt, 1e-12))))
+    n2 = 1 << (n2.bit_length() - 1)
+    for _ in range(warm):
+        cpu_sample(n2)
+    # cpu_sample regenerates its inputs each step; only the three operator calls are timed
+    t0 = time.perf_counter()
+    tot = 0.0
+    for _ in range(steps):
+        tot += sum(cpu_sample(n2).values())
+    wall = time.perf_counter() - t0
+    value = 3 * n2 * steps / tot
+    line = {
+        "impl": "reference", "metric": "prox_elements_per_s", "value": value, "unit": "elements/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": 1e3 * tot / steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(28, sample_log2n=n2.bit_length() - 1),
+        "cpu_baseline": {"value": value, "unit": "elements/s", "cores": 1, "kind": "port",
+                         "sample": f"each step = the C2 step on n=2^{n2.bit_length() - 1} Float64 (bounded sample), "
+                                   f"oracle port, 1 thread; host has {os.cpu_count()} logical cores"},
+        "e2e": {"value": value, "unit": "elements/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": wall,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(log2n, **extra):
+    cfg = {
+        "workload": f"C2 (BASELINE.json configs[1]): ShiftedNormL0Box prox! + ShiftedRootNormLhalfBox prox! "
+                    f"(vector l/u) + ShiftedNormL0Box iprox! (diagonal d), n=2^{log2n} Float64 per GPU, "
+                    f"lambda={LAMBDA}, sigma={SIGMA}",
+        "n_per_gpu": 1 << log2n,
+        "launches_per_step": 3,
+        "alg_bytes_per_element": ALG_BYTES,
+        "l2_policy": "operands larger than L2: each of the 7 streamed vectors is n*8 B (2 GiB at 2^28) vs 126 MB L2",
+        "sharding": "contiguous shards, one process per GPU, no data-path collective",
+    }
+    cfg.update(extra)
+    return cfg
+
+
+# -------------------------------------------------------------------- clocks ---
+class ClockSampler(threading.Thread):
+    def __init__(self, index: int, period=0.02):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    NAMES = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+             0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+             0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def run(self):
+        if self.nv is None:
+            return
+        while not self._stop.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in self.NAMES.items():
+                    if r & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ------------------------------------------------------------------- GPU arm ---
+def run_ours(args, rank, local_rank, world):
+    import torch
+
+    import shiftedprox as sp
+    from shiftedprox import _lib as L
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=dev)
+    n = 1 << args.log2n
+    ctx = sp.context(dev)
+    f64 = torch.float64
+
+    def uniform(stream, scale=1.0, shift=0.0, i0=rank * n):
+        t = torch.empty(n, dtype=f64, device=dev)
+        L.call("spx_fill_uniform_f64", sp.context(dev), C.c_void_p(t.data_ptr()), C.c_int64(n), C.c_int64(i0),
+               C.c_uint64(SEED), C.c_uint64(stream), C.c_double(scale), C.c_double(shift))
+        return t
+
+    # the shard of rank r is elements [r n, (r+1) n) of the global synthetic vectors
+    xk, sj, q = uniform(0, 4.0, -2.0), uniform(1, 1.0, -0.5), uniform(2, 4.0, -2.0)
+    l = uniform(3).add_(0.25).neg_()
+    u = uniform(4).add_(0.25)
+    d = uniform(5).add_(0.5)
+    b = uniform(6)
+    d = torch.where(b < 0.1, -d, d)
+    d = torch.where((b >= 0.1) & (b < 0.2), torch.zeros_like(d), d)
+    del b
+    y = torch.empty(n, dtype=f64, device=dev)
+    psi_l0 = sp.shifted(sp.shifted(sp.NormL0(LAMBDA), xk, l, u), sj)
+    psi_lh = sp.shifted(sp.shifted(sp.RootNormLhalf(LAMBDA), xk, l, u), sj)
+
+    def step(ev=None):
+        if ev is not None:
+            ev[0].record()
+        sp.prox_(y, psi_l0, q, SIGMA)
+        if ev is not None:
+            ev[1].record()
+        sp.prox_(y, psi_lh, q, SIGMA)
+        if ev is not None:
+            ev[2].record()
+        sp.iprox_(y, psi_l0, q, d)
+        if ev is not None:
+            ev[3].record()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    K, W = max(1, args.steps), max(3, args.warmup)
+    for _ in range(W):
+        step()
+    barrier()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(K)]
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = sp.launch_count(dev)
+    barrier()
+    t_start = torch.cuda.Event(enable_timing=True)
+    t_end = torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    for k in range(K):
+        step(evs[k])
+    t_end.record()
+    barrier()
+    launches = sp.launch_count(dev) - launches0
+    clocks = sampler.stop()
+    ms_total = t_start.elapsed_time(t_end)
+    per_op_ms = {op: sum(evs[k][i].elapsed_time(evs[k][i + 1]) for k in range(K)) / K for i, op in enumerate(OPS)}
+    if dist is not None:
+        tt = torch.tensor([ms_total], dtype=f64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_total = float(tt.item())
+    ms_step = ms_total / K
+    value = world * 3 * n / (ms_step * 1e-3)
+    step_bytes = sum(ALG_BYTES[o] for o in OPS) * n
+
+    # roofline of the dominant kernel
+    peak, peak_src = measured_peak()
+    dom = max(per_op_ms, key=per_op_ms.get)
+    achieved = ALG_BYTES[dom] * n / (per_op_ms[dom] * 1e-3) / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            tj = json.load(f)
+        if dom in tj and tj[dom].get("log2n") == args.log2n:
+            traffic = tj[dom]["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "frac_of_nominal_8000": achieved / 8000.0,
+                "per_kernel": {o: {"ms": per_op_ms[o], "GBps": ALG_BYTES[o] * n / (per_op_ms[o] * 1e-3) / 1e9,
+                                   "frac": ALG_BYTES[o] * n / (per_op_ms[o] * 1e-3) / 1e9 / peak} for o in OPS}}
+
+    # end-to-end: host (pinned) buffers through spx_box_host_f64
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(args, sp, L, dev, dist, world, n, (xk, sj, q, d, l, u))
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu, _, _ = cpu_baseline(args.cpu_seconds)
+
+    if rank == 0:
+        line = {
+            "metric": "prox_elements_per_s", "value": value, "unit": "elements/s", "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": workload_config(args.log2n),
+            "hbm_gbs": world * step_bytes / (ms_step * 1e-3) / 1e9,
+            "hbm_frac_of_measured_peak": step_bytes / (ms_step * 1e-3) / 1e9 / peak,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "host_cores": os.cpu_count(),
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_e2e(args, sp, L, dev, dist, world, n, dev_inputs):
+    import torch
+
+    f64 = torch.float64
+    xk, sj, q, d, l, u = dev_inputs
+    try:
+        host = [torch.empty(n, dtype=f64, pin_memory=True) for _ in range(7)]
+    except Exception as e:  # not enough lockable host memory
+        return {"value": None, "unit": "elements/s", "error": f"pinned allocation failed: {e}"}
+    hxk, hsj, hq, hd, hl, hu, hy = host
+    for h, t in zip((hxk, hsj, hq, hd, hl, hu), (xk, sj, q, d, l, u)):
+        h.copy_(t)
+    torch.cuda.synchronize()
+    ctx = sp.context(dev)
+    P = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+
+    def host_step():
+        for op, dd in ((L.BOX_L0, None), (L.BOX_LHALF, None), (L.BOX_L0, hd)):
+            L.call("spx_box_host_f64", ctx, C.c_int32(op), C.c_int64(n), P(hy), P(hxk), P(hsj), P(hq),
+                   P(dd) if dd is not None else None, P(hl), C.c_double(0.0), P(hu), C.c_double(0.0),
+                   C.c_double(LAMBDA), C.c_double(SIGMA), C.c_int64(1 << 22), None)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    host_step()  # warm-up (allocates the staging ring)
+    K = max(1, args.e2e_steps)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        host_step()
+    barrier()
+    dt = time.perf_counter() - t0
+    if dist is not None:
+        tt = torch.tensor([dt], dtype=f64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+    h2d = (5 + 5 + 6) * n * 8
+    d2h = 3 * n * 8
+    return {"value": world * 3 * n * K / dt, "unit": "elements/s", "h2d_bytes_per_step": h2d,
+            "d2h_bytes_per_step": d2h, "steps": K, "ms_per_step": 1e3 * dt / K,
+            "pcie_gbs": (h2d + d2h) * K / dt / 1e9,
+            "api": "spx_box_host_f64 (pinned host vectors, 4 Mi-element chunks, 3-stream H2D/kernel/D2H pipeline)"}
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

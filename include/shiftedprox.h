@@ -1,0 +1,271 @@
+/* ============================================================================
+ * shiftedprox.h -- C ABI of libshiftedprox.so (hand-written sm_100a CUDA).
+ *
+ * Drop-in boundary for the shifted prox hot path of ShiftedProximalOperators.jl
+ * v0.2.2.  The reference is pure Julia with no FFI on this path; the entry
+ * points below are what a Julia glue package binds with
+ *   ccall((:spx_..., libshiftedprox), Int32, (...), ...)
+ * in place of the method bodies cited at each declaration (file:line relative
+ * to the reference tree).  The in-tree FFI precedent the style follows is
+ * src/psvd.jl:99-137 (status out of the callee + a `chk...error` on the Julia
+ * side).  INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *  - every function returns int32 status: 0 = ok, <0 = SPX_E_* below,
+ *    >0 = a cudaError_t; spx_last_error() returns a thread-local message.
+ *  - `R*` arguments are DEVICE pointers on the context's device unless the
+ *    name ends in `_host`.  The library never frees or retains caller
+ *    pointers beyond a call.
+ *  - calls are enqueued on the context's stream and are asynchronous unless
+ *    they return a scalar to the host (`psi_out`, `*_out`), in which case
+ *    they synchronise that stream before returning.
+ *  - scalars (lambda, sigma, delta, bounds) are passed as double and rounded
+ *    to the element type R inside (the reference constrains them to R).
+ *  - indices are 0-based; `n` is the vector length.
+ *  - arithmetic follows the reference operation by operation (no FMA
+ *    contraction, Julia min/max/sign semantics); see DESIGN.md.
+ *  - a ψ must not be used from two host threads at once (the reference is
+ *    not re-entrant per ψ either: scratch lives in the struct).
+ * ========================================================================== */
+#ifndef SHIFTEDPROX_H
+#define SHIFTEDPROX_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPX_OK 0
+#define SPX_E_INVALID (-1)    /* bad argument (null pointer, n < 0, unknown kind ...) */
+#define SPX_E_ASSERT_D (-2)   /* `@assert d[i] > 0` failed: shiftedNormL1.jl:70, shiftedNormL0.jl:70 */
+#define SPX_E_BOUNDS (-3)     /* some l[i] > u[i]: shiftedNormL0Box.jl:33-35, shiftedNormL1Box.jl:33-35 */
+#define SPX_E_NOROOT (-4)     /* trust-region root finder did not bracket a root */
+#define SPX_E_UNSUPPORTED (-5)
+
+typedef struct spx_ctx spx_ctx; /* one device, one stream, reduction scratch */
+
+/* `l` / `u` of the Box types are "scalar or vector" (untyped struct parameters
+ * V3, V4: shiftedNormL1Box.jl:3-19).  vec == NULL -> the scalar `val`. */
+typedef struct spx_bound {
+  const void* vec; /* device pointer to n elements of R, or NULL */
+  double val;
+} spx_bound;
+
+/* `selected::AbstractArray{<:Integer}` (shiftedNormL1Box.jl:10,19,106,71).
+ *  SPX_SEL_ALL   every index (the default `1:length(xk)`)
+ *  SPX_SEL_RANGE start:step:stop, 0-based inclusive (e.g. Julia `1:2:n` -> 0,2,n-1)
+ *  SPX_SEL_MASK  bit i of mask[i/32] set <=> i selected (built by spx_build_mask from
+ *                any index list; membership is what prox!/iprox! need, :106)
+ *  For ψ(y) of a list with duplicates (the gather `x[selected]` counts them
+ *  twice, :71) pass the list as well: `list`/`nlist` (device, int64, 0-based). */
+#define SPX_SEL_ALL 0
+#define SPX_SEL_RANGE 1
+#define SPX_SEL_MASK 2
+typedef struct spx_sel {
+  int32_t kind;
+  int64_t start, step, stop;
+  const uint32_t* mask; /* device, ceil(n/32) words */
+  const int64_t* list;  /* device, optional (values only) */
+  int64_t nlist;
+} spx_sel;
+
+/* Sum all-reduce supplied by the host when one vector is sharded over several
+ * GPUs (one process per GPU): must replace vals[0..count) by their sum over all
+ * ranks, identically on every rank (e.g. ncclAllReduce / torch.distributed
+ * all_reduce on a Float64 buffer).  Return 0 on success. */
+typedef int32_t (*spx_allreduce_sum_fn)(void* user, double* vals, int32_t count);
+
+/* h kinds for the value entry points */
+#define SPX_H_L1 0        /* NormL1(λ):        λ‖v‖₁            (ProximalOperators 0.15) */
+#define SPX_H_L0 1        /* NormL0(λ):        λ·count(v≠0)                              */
+#define SPX_H_LHALF 2     /* RootNormLhalf(λ): λ Σ√|v|          (rootNormLhalf.jl:27-29) */
+#define SPX_H_INDBALLL0 3 /* IndBallL0(r):     count(v≠0) ≤ r ? 0 : Inf                  */
+#define SPX_H_GROUPL2 4   /* GroupNormL2:      Σ_g λ_g‖v_g‖₂    (groupNormL2.jl:33-39)   */
+
+/* ------------------------------------------------------------- context --- */
+int32_t spx_version(void);
+const char* spx_last_error(void);
+/* stream: a cudaStream_t to enqueue on (e.g. the host framework's current
+ * stream), or NULL to let the context create its own non-blocking stream. */
+int32_t spx_ctx_create(spx_ctx** out, int32_t device, void* stream);
+int32_t spx_ctx_destroy(spx_ctx* ctx);
+int32_t spx_ctx_set_stream(spx_ctx* ctx, void* stream);
+int32_t spx_ctx_synchronize(spx_ctx* ctx);
+int32_t spx_ctx_sm_count(spx_ctx* ctx, int32_t* out);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+int32_t spx_ctx_launch_count(spx_ctx* ctx, int64_t* out);
+
+/* ----------------------------------------- device buffers (Julia owns) --- */
+/* replaces `similar(xk)` / `zero(xk)` in the constructors, e.g. shiftedNormL1.jl:16-29 */
+int32_t spx_malloc(spx_ctx* ctx, size_t bytes, void** out);
+int32_t spx_free(spx_ctx* ctx, void* p);
+int32_t spx_malloc_host(size_t bytes, void** out); /* pinned host memory */
+int32_t spx_free_host(void* p);
+int32_t spx_memcpy_h2d(spx_ctx* ctx, void* dst, const void* src_host, size_t bytes);
+int32_t spx_memcpy_d2h(spx_ctx* ctx, void* dst_host, const void* src, size_t bytes); /* synchronises */
+/* `shift!`: ψ.xk .= v / ψ.sj .= v   (ShiftedProximalOperators.jl:72-79) and
+ * vector `set_bounds!` (ShiftedProximalOperators.jl:107-111) */
+int32_t spx_memcpy_d2d(spx_ctx* ctx, void* dst, const void* src, size_t bytes);
+int32_t spx_fill_f64(spx_ctx* ctx, double* p, int64_t n, double v);
+int32_t spx_fill_f32(spx_ctx* ctx, float* p, int64_t n, float v);
+/* ctor validation `any(l .> u)` (shiftedNormL1Box.jl:33, shiftedNormL0Box.jl:33); *out = 1 if any */
+int32_t spx_any_gt_f64(spx_ctx* ctx, int64_t n, const spx_bound* l, const spx_bound* u, int32_t* out);
+int32_t spx_any_gt_f32(spx_ctx* ctx, int64_t n, const spx_bound* l, const spx_bound* u, int32_t* out);
+/* membership bitmask of an arbitrary index list (device int64, 0-based, any
+ * order, duplicates allowed); mask has ceil(n/32) words and is zeroed first */
+int32_t spx_build_mask(spx_ctx* ctx, int64_t n, const int64_t* list, int64_t nlist, uint32_t* mask);
+/* synthetic inputs of SURVEY.md §8d, bit-identical to the oracle's generator:
+ * out[i] = scale * u(i0 + i, stream) + shift,  u = (splitmix64(...) >> 11) * 2^-53 */
+int32_t spx_fill_uniform_f64(spx_ctx* ctx, double* out, int64_t n, int64_t i0, uint64_t seed,
+                             uint64_t stream, double scale, double shift);
+int32_t spx_fill_uniform_f32(spx_ctx* ctx, float* out, int64_t n, int64_t i0, uint64_t seed,
+                             uint64_t stream, float scale, float shift);
+/* order-independent 64-bit checksum of a buffer's bits (Σ mix(word_i, i) mod 2^64),
+ * identical to oracle.checksum(); used for full-size parity */
+int32_t spx_checksum(spx_ctx* ctx, const void* p, int64_t nwords64, uint64_t* out);
+
+/* ------------------------------------------------ separable prox (a2-a6) ---
+ * psi_out (host, may be NULL): if given, ψ(y) at the freshly computed y is
+ * accumulated in the same pass (ShiftedProximalOperators.jl:51-54 fused) and
+ * the call synchronises. */
+#define SPX_DECL_SEPARABLE(SUF, R)                                                               \
+  /* ShiftedNormL1.prox!  shiftedNormL1.jl:40-54 */                                              \
+  int32_t spx_prox_l1_##SUF(spx_ctx* ctx, int64_t n, R* y, const R* xk, const R* sj, const R* q, \
+                            double lambda, double sigma, double* psi_out);                       \
+  /* ShiftedNormL1.iprox! shiftedNormL1.jl:60-75; first_bad_d (host, may be NULL): index of  */ \
+  /* the first d[i] <= 0 or -1; when given the call synchronises and returns SPX_E_ASSERT_D */  \
+  int32_t spx_iprox_l1_##SUF(spx_ctx* ctx, int64_t n, R* y, const R* xk, const R* sj,            \
+                             const R* g, const R* d, double lambda, int64_t* first_bad_d,        \
+                             double* psi_out);                                                   \
+  /* ShiftedNormL0.prox!  shiftedNormL0.jl:38-55 */                                              \
+  int32_t spx_prox_l0_##SUF(spx_ctx* ctx, int64_t n, R* y, const R* xk, const R* sj, const R* q, \
+                            double lambda, double sigma, double* psi_out);                       \
+  /* ShiftedNormL0.iprox! shiftedNormL0.jl:61-80 */                                              \
+  int32_t spx_iprox_l0_##SUF(spx_ctx* ctx, int64_t n, R* y, const R* xk, const R* sj,            \
+                             const R* g, const R* d, double lambda, int64_t* first_bad_d,        \
+                             double* psi_out);                                                   \
+  /* ShiftedRootNormLhalf.prox! shiftedRootNormLhalf.jl:41-63 (ψ.sol is not materialised) */     \
+  int32_t spx_prox_lhalf_##SUF(spx_ctx* ctx, int64_t n, R* y, const R* xk, const R* sj,          \
+                               const R* q, double lambda, double sigma, double* psi_out);        \
+  /* ---------------------------------------------------- Box / BInf (a8-a12) */                 \
+  /* ShiftedNormL1Box.prox!  shiftedNormL1Box.jl:89-125 */                                       \
+  int32_t spx_prox_l1box_##SUF(spx_ctx* ctx, int64_t n, R* y, const R* xk, const R* sj,          \
+                               const R* q, const spx_bound* l, const spx_bound* u,               \
+                               const spx_sel* sel, double lambda, double sigma,                  \
+                               double* psi_out);                                                 \
+  /* ShiftedNormL1Box.iprox! shiftedNormL1Box.jl:131-225 */                                      \
+  int32_t spx_iprox_l1box_##SUF(spx_ctx* ctx, int64_t n, R* y, const R* xk, const R* sj,         \
+                                const R* g, const R* d, const spx_bound* l, const spx_bound* u,  \
+                                const spx_sel* sel, double lambda, double* psi_out);             \
+  /* ShiftedNormL0Box.prox!  shiftedNormL0Box.jl:89-131 */                                       \
+  int32_t spx_prox_l0box_##SUF(spx_ctx* ctx, int64_t n, R* y, const R* xk, const R* sj,          \
+                               const R* q, const spx_bound* l, const spx_bound* u,               \
+                               const spx_sel* sel, double lambda, double sigma,                  \
+                               double* psi_out);                                                 \
+  /* ShiftedNormL0Box.iprox! shiftedNormL0Box.jl:137-231 (a NaN g[i] with |d[i]| < eps, */      \
+  /* where the reference leaves y[i] untouched, yields NaN here: y is write-only) */            \
+  int32_t spx_iprox_l0box_##SUF(spx_ctx* ctx, int64_t n, R* y, const R* xk, const R* sj,         \
+                                const R* g, const R* d, const spx_bound* l, const spx_bound* u,  \
+                                const spx_sel* sel, double lambda, double* psi_out);             \
+  /* ShiftedRootNormLhalfBox.prox! shiftedRootNormLhalfBox.jl:86-120 */                          \
+  int32_t spx_prox_lhalfbox_##SUF(spx_ctx* ctx, int64_t n, R* y, const R* xk, const R* sj,       \
+                                  const R* q, const spx_bound* l, const spx_bound* u,            \
+                                  const spx_sel* sel, double lambda, double sigma,               \
+                                  double* psi_out);                                              \
+  /* ---------------------------------------------------- ShiftedNormL1B2 (a13) */               \
+  /* ShiftedNormL1B2.prox! shiftedNormL1B2.jl:47-64.  chi_lambda is χ.lambda (NormL2(1.0) */    \
+  /* in the reference's tests).  passes_out (host, may be NULL): number of vector passes. */    \
+  int32_t spx_prox_l1b2_##SUF(spx_ctx* ctx, int64_t n, R* y, const R* xk, const R* sj,           \
+                              const R* q, double lambda, double sigma, double delta,             \
+                              double chi_lambda, int32_t* passes_out, double* psi_out);          \
+  /* the same prox! on this rank's contiguous shard of a vector sharded over several GPUs: */   \
+  /* the K partial sums of squares of every pass (and the two ψ sums) go through `reduce`; */   \
+  /* the scalar root search is replicated, so every rank takes identical decisions */           \
+  int32_t spx_prox_l1b2_sharded_##SUF(spx_ctx* ctx, int64_t n, R* y, const R* xk, const R* sj,   \
+                                      const R* q, double lambda, double sigma, double delta,     \
+                                      double chi_lambda, spx_allreduce_sum_fn reduce,            \
+                                      void* user, int32_t* passes_out, double* psi_out);         \
+  /* building blocks (one pass each), exported for tests: */                                     \
+  /* sumsq_out[k] = Σ_i ProjB(-xk_i * scale[k])_i^2, k < nscale <= 16 (host arrays); */        \
+  /* scale == NULL -> the unscaled ProjB(-xk) of :56 */                                          \
+  int32_t spx_l1b2_projnorm2_##SUF(spx_ctx* ctx, int64_t n, const R* xk, const R* sj,            \
+                                   const R* q, double lambda, double sigma, int32_t nscale,      \
+                                   const double* scale_host, double* sumsq_out_host);            \
+  /* y = ProjB(-xk * scale) * post - sj  (:60-62); use_scale = 0 -> y = ProjB(-xk) - sj */      \
+  int32_t spx_l1b2_finish_##SUF(spx_ctx* ctx, int64_t n, R* y, const R* xk, const R* sj,         \
+                                const R* q, double lambda, double sigma, int32_t use_scale,      \
+                                double scale, double post, double delta, double* psi_sum_out,    \
+                                double* w_sumsq_out);                                            \
+  /* ------------------------------------------------------ group norms (a14-a15) */             \
+  /* ShiftedGroupNormL2.prox! shiftedGroupNormL2.jl:52-79; groups are contiguous index */       \
+  /* ranges offs[g]..offs[g+1]-1 (device int64, ngroups+1 entries), lambda_g device R[ngroups] */\
+  int32_t spx_prox_groupl2_##SUF(spx_ctx* ctx, int64_t n, R* y, const R* xk, const R* sj,        \
+                                 const R* q, int64_t ngroups, const int64_t* offs,               \
+                                 const R* lambda_g, double sigma, double* psi_out);              \
+  /* ShiftedGroupNormL2Binf.prox! shiftedGroupNormL2Binf.jl:67-119 */                            \
+  int32_t spx_prox_groupl2binf_##SUF(spx_ctx* ctx, int64_t n, R* y, const R* xk, const R* sj,    \
+                                     const R* q, int64_t ngroups, const int64_t* offs,           \
+                                     const R* lambda_g, double sigma, double delta,              \
+                                     double* psi_out);                                           \
+  /* ------------------------------------------------------ top-r (a16-a17) */                   \
+  /* ShiftedIndBallL0.prox! shiftedIndBallL0.jl:54-72 and ShiftedIndBallL0BInf.prox! */         \
+  /* shiftedIndBallL0BInf.jl:73-95 (binf != 0 -> clamp to ±delta).  nprob independent */        \
+  /* problems of length n stored back to back (nprob = 1 for a single ψ).  The `p` */           \
+  /* permutation scratch of the reference does not exist: radix-select, no sort. */             \
+  int32_t spx_prox_indballl0_##SUF(spx_ctx* ctx, int64_t nprob, int64_t n, R* y, const R* xk,    \
+                                   const R* sj, const R* q, int64_t r, int32_t binf,             \
+                                   double delta);                                                \
+  /* ------------------------------------------------------ ψ(y) (a18-a20) */                    \
+  /* generic ψ(y) = h(xk + sj + y), ShiftedProximalOperators.jl:51-54; kind = SPX_H_L1, */      \
+  /* _L0, _LHALF, _INDBALLL0 (param r) */                                                        \
+  int32_t spx_value_sep_##SUF(spx_ctx* ctx, int32_t kind, int64_t n, const R* xk, const R* sj,   \
+                              const R* y, double lambda, int64_t r, double* out);                \
+  /* Box ψ(y): shiftedNormL1Box.jl:70-82, shiftedNormL0Box.jl:70-82, */                          \
+  /* shiftedRootNormLhalfBox.jl:67-79 */                                                         \
+  int32_t spx_value_box_##SUF(spx_ctx* ctx, int32_t kind, int64_t n, const R* xk, const R* sj,   \
+                              const R* y, const spx_bound* l, const spx_bound* u,                \
+                              const spx_sel* sel, double lambda, double* out);                   \
+  /* ShiftedNormL1B2 ψ(y): shiftedNormL1B2.jl:32 */                                              \
+  int32_t spx_value_l1b2_##SUF(spx_ctx* ctx, int64_t n, const R* xk, const R* sj, const R* y,    \
+                               double lambda, double delta, double* out);                        \
+  /* BInf ψ(y): shiftedIndBallL0BInf.jl:44-49 (kind SPX_H_INDBALLL0) and */                      \
+  /* shiftedGroupNormL2Binf.jl:34-39 (kind SPX_H_GROUPL2) */                                     \
+  int32_t spx_value_binf_##SUF(spx_ctx* ctx, int32_t kind, int64_t n, const R* xk, const R* sj,  \
+                               const R* y, double delta, int64_t r, int64_t ngroups,             \
+                               const int64_t* offs, const R* lambda_g, double* out);             \
+  /* ShiftedGroupNormL2 ψ(y): ShiftedProximalOperators.jl:51-54 + groupNormL2.jl:33-39 */        \
+  int32_t spx_value_groupl2_##SUF(spx_ctx* ctx, int64_t n, const R* xk, const R* sj,             \
+                                  const R* y, int64_t ngroups, const int64_t* offs,              \
+                                  const R* lambda_g, double* out);                               \
+  /* partial sums for sharded vectors: out_host[0] = Σ (un-scaled by λ), out_host[1] = 1.0 */   \
+  /* if the shard is infeasible; the caller all-reduces (sum, max) and applies λ / Inf */       \
+  int32_t spx_value_partial_##SUF(spx_ctx* ctx, int32_t kind, int64_t n, const R* xk,            \
+                                  const R* sj, const R* y, const spx_bound* l,                   \
+                                  const spx_bound* u, const spx_sel* sel, int32_t boxed,         \
+                                  double* out_host);                                             \
+  /* ------------------------------ host-buffer entry points (end-to-end path) */              \
+  /* Box prox!/iprox! with every vector in HOST memory (pinned for full speed): chunked, */     \
+  /* H2D / kernel / D2H overlapped on three streams.  op: 0 L1Box, 1 L0Box, 2 LhalfBox; */      \
+  /* gd_host == NULL -> prox!(q_or_g = q, sigma); else iprox!(q_or_g = g, d)  */                \
+  int32_t spx_box_host_##SUF(spx_ctx* ctx, int32_t op, int64_t n, R* y_host, const R* xk_host,   \
+                             const R* sj_host, const R* q_or_g_host, const R* d_host,            \
+                             const R* l_host, double l_val, const R* u_host, double u_val,       \
+                             double lambda, double sigma, int64_t chunk_elems,                   \
+                             double* psi_out);
+
+SPX_DECL_SEPARABLE(f64, double)
+SPX_DECL_SEPARABLE(f32, float)
+
+/* scalar helpers, exported for the glue's unit tests:
+ * prox_zero  ShiftedProximalOperators.jl:203, iprox_zero :217-236 */
+double spx_prox_zero_f64(double q, double l, double u);
+double spx_iprox_zero_f64(double d, double g, double l, double u);
+float spx_prox_zero_f32(float q, float l, float u);
+float spx_iprox_zero_f32(float d, float g, float l, float u);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SHIFTEDPROX_H */

@@ -1,0 +1,343 @@
+// spx_l1b2.cu -- ShiftedNormL1B2 prox!  (shiftedNormL1B2.jl:47-64).
+//
+//   ProjB(z) = min(max(z, sj+q-λσ), sj+q+λσ);  y = ProjB(-xk)
+//   if Δ <= χ(y):  η = root of η - χ(ProjB(-xk η/Δ));  y = ProjB(-xk η/Δ) Δ/η
+//   y -= sj
+//
+// Every evaluation of the residual is a full streaming pass over xk, sj, q (3R
+// per element, nothing written), so the pass count is what matters.  One pass
+// evaluates up to 16 trial values of η at once (the pass is HBM-bound; the
+// extra clamps and squares are free), which turns Roots' one-point-per-pass
+// iteration into a 17-section / secant-clustered search: the bracket reaches
+// two adjacent floats in a handful of passes.  When the vector is sharded over
+// several GPUs the K partial sums are all-reduced by the caller's callback
+// between passes; the scalar search itself is replicated on every rank.
+#include <algorithm>
+#include <vector>
+
+#include "spx_elementwise.cuh"
+#include "spx_ops.cuh"
+
+namespace spx {
+
+template <int K> struct ScaleSet { double s[K]; };
+
+// Σ_i ProjB(z_i(k))^2 for K scalings in one pass
+template <class R, int K, int VEC>
+__global__ void __launch_bounds__(kEwThreads)
+    l1b2_norm_kernel(const R* xk, const R* sj, const R* q, long long n, R ls, bool use_scale, ScaleSet<K> sc,
+                     int nblocks_stride, Partial* __restrict__ partials) {
+  double acc[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) acc[k] = 0.0;
+  R scale[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) scale[k] = (R)sc.s[k];
+  const long long nvec = n / VEC;
+  auto body = [&](R x, R s, R qq) {
+    const R mid = s + qq;
+    const R lo = mid - ls, hi = mid + ls;
+    const R nx = -x;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const R z = use_scale ? nx * scale[k] : nx;
+      const double w = (double)jl_min(jl_max(z, lo), hi);
+      acc[k] += w * w;
+    }
+  };
+  for (long long v = (long long)blockIdx.x * kEwThreads + threadIdx.x; v < nvec; v += (long long)gridDim.x * kEwThreads) {
+    Pack<R, VEC> a, b, c;
+    ld_stream(xk + v * VEC, a);
+    ld_stream(sj + v * VEC, b);
+    ld_stream(q + v * VEC, c);
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) body(a.v[e], b.v[e], c.v[e]);
+  }
+  if (VEC > 1 && blockIdx.x == gridDim.x - 1) {
+    const long long i = nvec * VEC + threadIdx.x;
+    if (i < n) body(xk[i], sj[i], q[i]);
+  }
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    Partial p;
+    p.s = 0.0;
+    p.s2 = acc[k];
+    p.bad = -1;
+    p = block_fold<kEwThreads>(p);
+    if (threadIdx.x == 0) partials[(size_t)k * nblocks_stride + blockIdx.x] = p;
+  }
+}
+
+template <class R, int K>
+static int32_t norm_pass_k(spx_ctx* ctx, int64_t n, const R* xk, const R* sj, const R* q, R ls, const double* scale,
+                           int nscale, double* out) {
+  ScaleSet<K> sc;
+  for (int k = 0; k < K; ++k) sc.s[k] = scale ? scale[k < nscale ? k : nscale - 1] : 1.0;
+  const uintptr_t bits = (uintptr_t)xk | (uintptr_t)sj | (uintptr_t)q;
+  const bool vec = (bits & 15u) == 0;
+  constexpr int VECW = 16 / (int)sizeof(R);
+  const long long nv = vec ? n / VECW : n;
+  long long want = (nv + kEwThreads - 1) / kEwThreads;
+  if (want < 1) want = 1;
+  long long cap = (long long)ctx->sm_count * 4;
+  const int grid = (int)(want < cap ? want : cap);
+  if (vec)
+    l1b2_norm_kernel<R, K, VECW><<<grid, kEwThreads, 0, ctx->stream>>>(xk, sj, q, n, ls, scale != nullptr, sc, grid,
+                                                                      ctx->d_partials);
+  else
+    l1b2_norm_kernel<R, K, 1><<<grid, kEwThreads, 0, ctx->stream>>>(xk, sj, q, n, ls, scale != nullptr, sc, grid,
+                                                                   ctx->d_partials);
+  ctx->launches++;
+  SPX_CUDA(cudaGetLastError());
+  int32_t st = finalize_partials(ctx, grid, K, false);
+  if (st != SPX_OK) return st;
+  for (int k = 0; k < nscale; ++k) out[k] = ctx->h_result[k].s2;
+  return SPX_OK;
+}
+
+template <class R>
+static int32_t norm_pass(spx_ctx* ctx, int64_t n, const R* xk, const R* sj, const R* q, R ls, const double* scale,
+                         int nscale, double* out) {
+  if (n == 0) {
+    for (int k = 0; k < nscale; ++k) out[k] = 0.0;
+    return SPX_OK;
+  }
+  if (nscale <= 1) return norm_pass_k<R, 1>(ctx, n, xk, sj, q, ls, scale, nscale, out);
+  if (nscale <= 8) return norm_pass_k<R, 8>(ctx, n, xk, sj, q, ls, scale, nscale, out);
+  return norm_pass_k<R, 16>(ctx, n, xk, sj, q, ls, scale, nscale, out);
+}
+
+// y = ProjB(-xk scale) post - sj, with Σ|xk+sj+y| and Σ(sj+y)² for ψ(y)
+template <class R, bool PSI> struct L1B2Finish {
+  using Real = R;
+  static constexpr int NIN = 3, UNROLL = 2;
+  static constexpr bool OUT = true, ACC = PSI;
+  const R* in[NIN];  // xk, sj, q
+  R fill[NIN];
+  R* y;
+  R ls, scale, post;
+  bool use_scale;
+  __device__ __forceinline__ R apply(const R (&x)[NIN], long long, Partial& acc) const {
+    const R mid = x[1] + x[2];
+    const R lo = mid - ls, hi = mid + ls;
+    const R nx = -x[0];
+    const R z = use_scale ? nx * scale : nx;
+    R w = jl_min(jl_max(z, lo), hi);
+    if (use_scale) w = w * post;
+    const R o = w - x[1];
+    if (PSI) {
+      acc.s += (double)jl_abs((x[0] + x[1]) + o);
+      const double t = (double)(x[1] + o);
+      acc.s2 += t * t;
+    }
+    return o;
+  }
+};
+
+template <class R>
+static int32_t finish_pass(spx_ctx* ctx, int64_t n, R* y, const R* xk, const R* sj, const R* q, R ls, bool use_scale,
+                           R scale, R post, double* psi_sum, double* w_sumsq) {
+  const bool psi = psi_sum != nullptr || w_sumsq != nullptr;
+  int nb = 0;
+  int32_t st;
+  if (psi) {
+    L1B2Finish<R, true> op;
+    op.in[0] = xk; op.in[1] = sj; op.in[2] = q;
+    op.fill[0] = op.fill[1] = op.fill[2] = R(0);
+    op.y = y; op.ls = ls; op.scale = scale; op.post = post; op.use_scale = use_scale;
+    st = ew_launch(ctx, ctx->stream, op, n, 0, ctx->d_partials, &nb);
+    if (st != SPX_OK) return st;
+    st = finalize_partials(ctx, nb, 1, false);
+    if (st != SPX_OK) return st;
+    if (psi_sum) *psi_sum = ctx->h_result[0].s;
+    if (w_sumsq) *w_sumsq = ctx->h_result[0].s2;
+    return SPX_OK;
+  }
+  L1B2Finish<R, false> op;
+  op.in[0] = xk; op.in[1] = sj; op.in[2] = q;
+  op.fill[0] = op.fill[1] = op.fill[2] = R(0);
+  op.y = y; op.ls = ls; op.scale = scale; op.post = post; op.use_scale = use_scale;
+  return ew_launch(ctx, ctx->stream, op, n, 0, ctx->d_partials, &nb);
+}
+
+template <class R> static bool in_ball_l2(R nw, R delta) {
+  const R eps = std::numeric_limits<R>::epsilon();
+  if (nw <= delta) return true;
+  if (!std::isfinite(nw) || !std::isfinite(delta)) return false;
+  R tol = std::max(eps, std::sqrt(eps) * std::max(std::fabs(nw), std::fabs(delta)));
+  return std::fabs(nw - delta) <= tol;
+}
+
+template <class R>
+static int32_t prox_l1b2(spx_ctx* ctx, int64_t n, R* y, const R* xk, const R* sj, const R* q, double lambda_,
+                         double sigma_, double delta_, double chi_lambda_, spx_allreduce_sum_fn reduce, void* user,
+                         int32_t* passes_out, double* psi_out) {
+  SPX_REQUIRE(ctx != nullptr, "null context");
+  SPX_REQUIRE(n >= 0, "n < 0");
+  SPX_REQUIRE(n == 0 || (y && xk && sj && q), "null device vector");
+  DeviceGuard guard(ctx->device);
+  const R lam = (R)lambda_, sig = (R)sigma_, delta = (R)delta_, chil = (R)chi_lambda_;
+  const R ls = lam * sig;
+  int passes = 0;
+  // K residuals per pass: f_k = η_k - χ(ProjB(-xk η_k/Δ))
+  auto eval = [&](const std::vector<R>& etas, bool use_scale, std::vector<R>& f) -> int32_t {
+    const int m = (int)etas.size();
+    double scale[kMaxScale], ss[kMaxScale];
+    for (int k = 0; k < m; ++k) scale[k] = (double)(etas[k] / delta);
+    int32_t st = norm_pass<R>(ctx, n, xk, sj, q, ls, use_scale ? scale : nullptr, m, ss);
+    if (st != SPX_OK) return st;
+    ++passes;
+    if (reduce) {
+      st = reduce(user, ss, m);
+      if (st != SPX_OK) {
+        set_error("spx_prox_l1b2: all-reduce callback failed (%d)", (int)st);
+        return st;
+      }
+    }
+    f.resize(m);
+    for (int k = 0; k < m; ++k) f[k] = etas[k] - chil * (R)std::sqrt(ss[k]);
+    return SPX_OK;
+  };
+  auto finish = [&](bool use_scale, R scale, R post) -> int32_t {
+    double s = 0.0, s2 = 0.0;
+    int32_t st = finish_pass<R>(ctx, n, y, xk, sj, q, ls, use_scale, scale, post, psi_out ? &s : nullptr,
+                                psi_out ? &s2 : nullptr);
+    ++passes;
+    if (passes_out) *passes_out = passes;
+    if (st != SPX_OK || psi_out == nullptr) return st;
+    if (reduce) {
+      double v[2] = {s, s2};
+      st = reduce(user, v, 2);
+      if (st != SPX_OK) return st;
+      s = v[0];
+      s2 = v[1];
+    }
+    // ψ(y) = h(xk+sj+y) + IndBallL2(Δ)(sj+y)   shiftedNormL1B2.jl:32
+    *psi_out = in_ball_l2<R>((R)std::sqrt(s2), delta) ? (double)(lam * (R)s) : std::numeric_limits<double>::infinity();
+    return SPX_OK;
+  };
+
+  std::vector<R> f, pts(1, delta);
+  int32_t st = eval(pts, false, f);  // ‖ProjB(-xk)‖  (:56-58)
+  if (st != SPX_OK) return st;
+  // f[0] = Δ - χ(y); the reference tests Δ <= χ(y)  (:58) -- the sign of a difference is exact
+  if (!(f[0] <= R(0))) return finish(false, R(1), R(1));
+  R a = delta, fa = f[0], b = a, fb = fa;
+  R eta = a;
+  if (fa != R(0)) {
+    // bracket: b0 = max(2a, a+1), doubled until the residual is non-negative
+    bool have = false;
+    R b0 = std::max(R(2) * a, a + R(1));
+    while (!have) {
+      pts.clear();
+      for (int k = 0; k < 8; ++k) pts.push_back(b0 * (R)std::ldexp(1.0, k));
+      st = eval(pts, true, f);
+      if (st != SPX_OK) return st;
+      for (int k = 0; k < 8; ++k) {
+        if (f[k] < R(0)) {
+          a = pts[k];
+          fa = f[k];
+        } else {
+          b = pts[k];
+          fb = f[k];
+          have = true;
+          break;
+        }
+      }
+      if (!have) {
+        b0 = R(2) * a;
+        if (!std::isfinite(b0)) {
+          set_error("spx_prox_l1b2: no sign change of the trust-region residual");
+          return SPX_E_NOROOT;
+        }
+      }
+    }
+    eta = b;
+    bool exact = (fb == R(0));
+    bool uniform = true;
+    while (!exact) {
+      const R mid = a + (b - a) / R(2);
+      if (!(a < mid && mid < b)) break;
+      const R w = b - a;
+      pts.clear();
+      if (uniform) {
+        for (int k = 1; k <= kMaxScale; ++k) pts.push_back(a + w * ((R)k / (R)(kMaxScale + 1)));
+      } else {
+        R xs = a - fa * (w / (fb - fa));
+        if (!(xs > a && xs < b)) xs = mid;
+        for (int j = 3; j >= 0; --j) pts.push_back(xs - w * (R)std::ldexp(1.0, -(3 + 4 * j) - 0));
+        for (int j = 0; j <= 3; ++j) pts.push_back(xs + w * (R)std::ldexp(1.0, -(15 - 4 * j)));
+        pts.push_back(mid);
+      }
+      std::sort(pts.begin(), pts.end());
+      std::vector<R> in;
+      for (R x : pts)
+        if (x > a && x < b && (in.empty() || x > in.back())) in.push_back(x);
+      if (in.empty()) in.push_back(mid);
+      if ((int)in.size() > kMaxScale) in.resize(kMaxScale);
+      st = eval(in, true, f);
+      if (st != SPX_OK) return st;
+      for (size_t k = 0; k < in.size(); ++k) {
+        if (f[k] == R(0)) {
+          eta = in[k];
+          exact = true;
+          break;
+        }
+        if (f[k] < R(0)) {
+          a = in[k];
+          fa = f[k];
+        } else {
+          b = in[k];
+          fb = f[k];
+          break;
+        }
+      }
+      uniform = !((b - a) <= w / R(8));  // poor shrink -> next pass sections uniformly
+      if (passes > 200) break;
+    }
+    if (!exact) eta = (std::fabs(fa) <= std::fabs(fb)) ? a : b;
+  }
+  return finish(true, eta / delta, delta / eta);
+}
+
+}  // namespace spx
+
+using namespace spx;
+
+#define SPX_DEFINE_L1B2(SUF, R)                                                                                     \
+  extern "C" int32_t spx_prox_l1b2_##SUF(spx_ctx* ctx, int64_t n, R* y, const R* xk, const R* sj, const R* q,       \
+                                         double lambda, double sigma, double delta, double chi_lambda,              \
+                                         int32_t* passes_out, double* psi_out) {                                    \
+    return prox_l1b2<R>(ctx, n, y, xk, sj, q, lambda, sigma, delta, chi_lambda, nullptr, nullptr, passes_out,       \
+                        psi_out);                                                                                   \
+  }                                                                                                                 \
+  extern "C" int32_t spx_prox_l1b2_sharded_##SUF(spx_ctx* ctx, int64_t n, R* y, const R* xk, const R* sj,           \
+                                                 const R* q, double lambda, double sigma, double delta,             \
+                                                 double chi_lambda, spx_allreduce_sum_fn reduce, void* user,        \
+                                                 int32_t* passes_out, double* psi_out) {                            \
+    return prox_l1b2<R>(ctx, n, y, xk, sj, q, lambda, sigma, delta, chi_lambda, reduce, user, passes_out, psi_out); \
+  }                                                                                                                 \
+  extern "C" int32_t spx_l1b2_projnorm2_##SUF(spx_ctx* ctx, int64_t n, const R* xk, const R* sj, const R* q,        \
+                                              double lambda, double sigma, int32_t nscale,                          \
+                                              const double* scale_host, double* sumsq_out_host) {                   \
+    SPX_REQUIRE(ctx && sumsq_out_host, "null argument");                                                            \
+    SPX_REQUIRE(n >= 0 && nscale >= 1 && nscale <= kMaxScale, "bad sizes");                                         \
+    SPX_REQUIRE(n == 0 || (xk && sj && q), "null device vector");                                                   \
+    DeviceGuard g(ctx->device);                                                                                     \
+    return norm_pass<R>(ctx, n, xk, sj, q, (R)lambda * (R)sigma, scale_host, scale_host ? nscale : 1,               \
+                        sumsq_out_host);                                                                            \
+  }                                                                                                                 \
+  extern "C" int32_t spx_l1b2_finish_##SUF(spx_ctx* ctx, int64_t n, R* y, const R* xk, const R* sj, const R* q,     \
+                                           double lambda, double sigma, int32_t use_scale, double scale,            \
+                                           double post, double delta, double* psi_sum_out, double* w_sumsq_out) {   \
+    SPX_REQUIRE(ctx != nullptr, "null context");                                                                    \
+    SPX_REQUIRE(n >= 0, "n < 0");                                                                                   \
+    SPX_REQUIRE(n == 0 || (y && xk && sj && q), "null device vector");                                              \
+    (void)delta;                                                                                                    \
+    DeviceGuard g(ctx->device);                                                                                     \
+    return finish_pass<R>(ctx, n, y, xk, sj, q, (R)lambda * (R)sigma, use_scale != 0, (R)scale, (R)post,            \
+                          psi_sum_out, w_sumsq_out);                                                                \
+  }
+
+SPX_DEFINE_L1B2(f64, double)
+SPX_DEFINE_L1B2(f32, float)

@@ -1,0 +1,90 @@
+"""CPU-side checks of the drop-in boundary (no compute calls): the C-ABI library is built, loads,
+and exports every symbol include/shiftedprox.h declares; the host mirror imports without a GPU and
+refuses to compute without one (no CPU fallback)."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "shiftedprox.h")
+LIB = os.path.join(ROOT, "shiftedproximaloperators.jl_b200", "libshiftedprox.so")
+
+
+def declared_symbols():
+    pre = subprocess.run(["gcc", "-E", "-P", HEADER], check=True, capture_output=True, text=True).stdout
+    names = set(re.findall(r"\b(spx_[a-z0-9_]+)\s*\(", pre))
+    names -= {"spx_allreduce_sum_fn"}
+    return sorted(names)
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not os.path.exists(LIB):
+        import __graft_entry__ as g
+
+        g.build()
+    return ctypes.CDLL(LIB)
+
+
+def test_header_compiles_as_c():
+    subprocess.run(["gcc", "-std=c99", "-fsyntax-only", "-x", "c", HEADER], check=True)
+
+
+def test_library_exports_every_declared_symbol(lib):
+    names = declared_symbols()
+    assert len(names) >= 70, names
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+    for suf in ("f64", "f32"):
+        for op in ("prox_l1", "iprox_l1", "prox_l0", "iprox_l0", "prox_lhalf", "prox_l1box", "iprox_l1box",
+                   "prox_l0box", "iprox_l0box", "prox_lhalfbox", "prox_l1b2", "prox_l1b2_sharded", "prox_groupl2",
+                   "prox_groupl2binf", "prox_indballl0", "value_sep", "value_box", "value_l1b2", "value_binf",
+                   "value_groupl2", "value_partial", "box_host"):
+            assert f"spx_{op}_{suf}" in names
+
+
+def test_version_and_scalar_helpers(lib):
+    assert lib.spx_version() >= 100
+    lib.spx_prox_zero_f64.restype = ctypes.c_double
+    lib.spx_iprox_zero_f64.restype = ctypes.c_double
+    d = ctypes.c_double
+    # prox_zero / iprox_zero are plain host functions (ShiftedProximalOperators.jl:203, :217-236)
+    assert lib.spx_prox_zero_f64(d(5.0), d(-1.0), d(2.0)) == 2.0
+    assert lib.spx_iprox_zero_f64(d(2.0), d(1.0), d(-1.0), d(2.0)) == -0.5
+    assert lib.spx_iprox_zero_f64(d(-2.0), d(1.0), d(-1.0), d(2.0)) == 2.0
+    assert lib.spx_iprox_zero_f64(d(0.0), d(2.0), d(-1.0), d(1.0)) == -1.0
+    assert lib.spx_iprox_zero_f64(d(0.0), d(0.0), d(-1.0), d(1.0)) == 0.0
+
+
+def test_library_is_sm100a_only():
+    out = subprocess.run(["cuobjdump", "--list-elf", LIB], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_host_mirror_imports_and_fails_loudly_without_gpu():
+    import torch
+
+    import shiftedprox as sp
+
+    h = sp.NormL1(1.0)
+    assert h.lam == 1.0
+    with pytest.raises(ValueError):
+        sp.IndBallL0(0)
+    if not torch.cuda.is_available():
+        with pytest.raises(TypeError):
+            sp.shifted(h, torch.ones(4, dtype=torch.float64))  # host tensor: no CPU path
+        with pytest.raises(RuntimeError):
+            sp.context(0)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "shiftedproximaloperators.jl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".jl")):
+                text = open(os.path.join(dirpath, f), encoding="utf-8").read()
+                assert "liboracle" not in text and "from oracle" not in text and "import oracle" not in text, f

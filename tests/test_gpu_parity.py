@@ -1,0 +1,497 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star): identical support pattern; bit-exact wherever the arithmetic is
++,-,*,/,sqrt and comparisons (L1, L0, their Box forms, iprox, top-r); a few ulp of the value scale for
+the transcendental RootNormLhalf forms (Julia's and CUDA's cos/acos are each < 1-2 ulp but not
+correctly rounded -- the tolerance is written at each test); solver-limited for L1B2 / GroupNormL2Binf.
+"""
+import numpy as np
+import pytest
+import torch
+
+from gpu_util import DEV, N, T, bounds, diag, inputs, orc, sp, ulp_diff
+from test_oracle_golden import BOX9, GOLD, IPROX14, NU, Q5, isapprox
+
+pytestmark = pytest.mark.gpu
+
+DT = [np.float64, np.float32]
+SIZES = [1, 7, 1000, 262_147]
+
+
+def eps(dt):
+    return np.finfo(dt).eps
+
+
+# ------------------------------------------------------------------ separable ---
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("n", SIZES)
+@pytest.mark.parametrize("lam", [1.0, 10.0])
+def test_prox_l1_l0_bit_exact(dt, n, lam):
+    xk, sj, q = inputs(n, dt)
+    sigma = 0.1
+    for h, f in ((sp.NormL1(lam), orc.prox_l1), (sp.NormL0(lam), orc.prox_l0)):
+        psi = sp.shifted(sp.shifted(h, T(xk)), T(sj))
+        y = torch.empty(n, dtype=T(q).dtype, device=DEV)
+        sp.prox_(y, psi, T(q), sigma)
+        assert np.array_equal(N(y), f(xk, sj, q, lam, sigma), equal_nan=True)
+        # prox(ψ, q, σ) writes ψ.sol
+        assert sp.prox(psi, T(q), sigma) is psi.sol
+        assert np.array_equal(N(psi.sol), N(y))
+
+
+@pytest.mark.parametrize("dt", DT)
+def test_unaligned_views_take_the_scalar_path(dt):
+    n = 10_001
+    xk, sj, q = inputs(n + 1, dt)
+    txk, tsj, tq = T(xk)[1:], T(sj)[1:], T(q)[1:]
+    y = torch.empty(n + 1, dtype=tq.dtype, device=DEV)[1:]
+    psi = sp.shifted(sp.shifted(sp.NormL1(1.0), txk), tsj)
+    sp.prox_(y, psi, tq, 0.1)
+    assert np.array_equal(N(y), orc.prox_l1(xk[1:], sj[1:], q[1:], 1.0, 0.1))
+
+
+@pytest.mark.parametrize("dt", DT)
+def test_prox_aliasing_y_is_q(dt):
+    # test_allocs.jl:108 calls prox!(y, ψ, y, 1.0); single-pass semantics (documented in DESIGN.md)
+    n = 4099
+    xk, sj, q = inputs(n, dt)
+    psi = sp.shifted(sp.shifted(sp.NormL0(1.0), T(xk)), T(sj))
+    y = T(q).clone()
+    sp.prox_(y, psi, y, 0.1)
+    assert np.array_equal(N(y), orc.prox_l0(xk, sj, q, 1.0, 0.1))
+
+
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("n", SIZES)
+def test_iprox_l1_l0_bit_exact_and_assertion(dt, n):
+    xk, sj, g = inputs(n, dt)
+    d = (dt(0.5) + orc.uniform(n, 5, dt)).astype(dt)
+    for h, f in ((sp.NormL1(1.3), orc.iprox_l1), (sp.NormL0(1.3), orc.iprox_l0)):
+        psi = sp.shifted(sp.shifted(h, T(xk)), T(sj))
+        y = torch.empty(n, dtype=T(g).dtype, device=DEV)
+        sp.iprox_(y, psi, T(g), T(d))
+        assert np.array_equal(N(y), f(xk, sj, g, d, 1.3))
+        # @assert d[i] > 0 (shiftedNormL1.jl:70, partial_prox.jl:61)
+        dbad = d.copy()
+        k = n // 2
+        dbad[k] = 0
+        with pytest.raises(AssertionError, match=rf"d\[{k}\]"):
+            sp.iprox_(y, psi, T(g), T(dbad))
+
+
+@pytest.mark.parametrize("dt", DT)
+def test_iprox_equals_prox_identity(dt):
+    # partial_prox.jl:58-72: unboxed iprox(ψ, q, d·1) == prox(ψ, q, σ = d) on ... exactly, d ∈ {1, 2}
+    n = 5
+    rng = np.random.default_rng(2)
+    x = rng.random(n).astype(dt); q = (rng.random(n) - 0.5).astype(dt)
+    z = np.zeros(n, dt)
+    for h, fi, fp in ((sp.NormL0(3.14), orc.iprox_l0, orc.prox_l0), (sp.NormL1(3.14), orc.iprox_l1, orc.prox_l1)):
+        psi = sp.shifted(h, T(x))
+        for dv in (1.0, 2.0):
+            a = N(sp.iprox(psi, T(q), T(np.full(n, dv, dt)))).copy()
+            b = N(sp.prox(psi, T(q), dv)).copy()
+            assert np.array_equal(a, fi(x, z, q, np.full(n, dv, dt), 3.14))
+            assert np.array_equal(b, fp(x, z, q, 3.14, dv))
+
+
+def lhalf_scale(xk, sj, q):
+    return np.abs(xk) + np.abs(sj) + np.abs(q) + 1.0
+
+
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("n", SIZES)
+@pytest.mark.parametrize("lam", [1.0, 10.0])
+def test_prox_lhalf(dt, n, lam):
+    xk, sj, q = inputs(n, dt)
+    sigma = 0.1
+    psi = sp.shifted(sp.shifted(sp.RootNormLhalf(lam), T(xk)), T(sj))
+    y = torch.empty(n, dtype=T(q).dtype, device=DEV)
+    sp.prox_(y, psi, T(q), sigma)
+    ref = orc.prox_lhalf(xk, sj, q, lam, sigma)
+    got = N(y)
+    # support: y == -(xk+sj) exactly where the oracle thresholds to zero
+    zero_ref = ref == (np.zeros(n, dt) - (xk + sj))
+    zero_got = got == (np.zeros(n, dt) - (xk + sj))
+    assert np.array_equal(zero_ref, zero_got)
+    # values: the closed form is evaluated in Float64 then rounded to R; tolerance 4 ulp(R) of the
+    # magnitude of the un-shifted value (y + xs cancels, so ulps of y itself are meaningless)
+    tol = 4 * eps(dt) * lhalf_scale(xk, sj, q)
+    assert np.all(np.abs(got.astype(np.float64) - ref.astype(np.float64)) <= tol)
+
+
+def test_lhalf_closed_form_against_mpmath():
+    """Both the oracle and the GPU are within 4 ulp of the exact closed form (x = s = 0)."""
+    mp = pytest.importorskip("mpmath")
+    mp.mp.prec = 200
+    n = 600
+    q = orc.uniform(n, 7, np.float64, 8.0, -4.0)
+    lam, sigma = 1.0, 0.1
+    z = np.zeros(n)
+    psi = sp.shifted(sp.RootNormLhalf(lam), T(z))
+    got = N(sp.prox(psi, T(q), sigma))
+    ref = orc.prox_lhalf(z, z, q, lam, sigma)
+    nl = mp.mpf(sigma) * mp.mpf(lam)
+    for i in range(n):
+        if ref[i] == 0.0:
+            assert got[i] == 0.0
+            continue
+        a = mp.mpf(abs(float(q[i])))
+        t = nl / 4 * (a / 3) ** mp.mpf(-1.5)
+        exact = mp.mpf(2) / 3 * a * (1 + mp.cos(2 * mp.pi / 3 - 2 * mp.acos(t) / 3)) * (1 if q[i] > 0 else -1)
+        u = np.spacing(abs(float(exact)))
+        assert abs(mp.mpf(float(got[i])) - exact) <= 4 * u, (i, q[i], got[i], exact)
+        assert abs(mp.mpf(float(ref[i])) - exact) <= 4 * u
+
+
+# ------------------------------------------------------------------------ values ---
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("n", [1, 1000, 262_147])
+def test_values_and_fused_values(dt, n):
+    xk, sj, q = inputs(n, dt)
+    y0 = orc.uniform(n, 9, dt, 1.0, -0.5)
+    rtol = 1e-13 if dt == np.float64 else 2e-6
+    for name, h, kind in (("l1", sp.NormL1(1.7), "l1"), ("l0", sp.NormL0(1.7), "l0"),
+                          ("lhalf", sp.RootNormLhalf(1.7), "lhalf")):
+        psi = sp.shifted(sp.shifted(h, T(xk)), T(sj))
+        v = psi(T(y0))
+        vref = orc.value_plain(kind, xk, sj, y0, 1.7)
+        assert v == pytest.approx(vref, rel=rtol)
+        # fused: prox! + ψ(y) in one pass equals the stand-alone value at the same y
+        y = torch.empty(n, dtype=T(q).dtype, device=DEV)
+        _, vf = sp.prox_(y, psi, T(q), 0.1, want_value=True)
+        assert vf == pytest.approx(psi(y), rel=rtol)
+        assert vf == pytest.approx(orc.value_plain(kind, xk, sj, N(y), 1.7), rel=rtol)
+    # exact identities of runtests.jl:175-194: ψ(0) == h(x)
+    psi = sp.shifted(sp.NormL0(1.2), T(np.ones(3, dt)))
+    assert psi(T(np.zeros(3, dt))) == float(dt(1.2) * dt(3))
+    psi = sp.shifted(sp.IndBallL0(2), T(np.ones(3, dt)))
+    assert psi(T(np.zeros(3, dt))) == np.inf
+    assert psi(T(np.array([-1, 0, 0], dt))) == 0.0
+
+
+# --------------------------------------------------------------------------- Box ---
+SELS = [None, "range", "list"]
+
+
+def make_sel(kind, n):
+    if kind is None:
+        return None, None
+    if kind == "range":
+        return range(0, n, 2), np.arange(0, n, 2)
+    rng = np.random.default_rng(7)
+    lst = rng.integers(0, n, size=max(1, n // 2))  # unsorted, duplicates (test_allocs.jl:78)
+    return lst.tolist(), lst
+
+
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("n", [1, 9, 65_539])
+@pytest.mark.parametrize("vecb", [True, False])
+@pytest.mark.parametrize("selk", SELS)
+def test_box_prox(dt, n, vecb, selk):
+    xk, sj, q = inputs(n, dt)
+    l, u = bounds(n, dt) if vecb else (dt(-1.0), dt(1.0))
+    sel_dev, sel_host = make_sel(selk, n)
+    lam, sigma = 1.0, 0.1
+    tl, tu = (T(l), T(u)) if vecb else (float(l), float(u))
+    for name, h in (("l1", sp.NormL1(lam)), ("l0", sp.NormL0(lam)), ("lhalf", sp.RootNormLhalf(lam))):
+        psi = sp.shifted(sp.shifted(h, T(xk), tl, tu, sel_dev), T(sj))
+        y = torch.empty(n, dtype=T(q).dtype, device=DEV)
+        sp.prox_(y, psi, T(q), sigma)
+        ref = orc.prox_box(name, xk, sj, q, l, u, lam, sigma, selected=sel_host)
+        got = N(y)
+        if name != "lhalf":
+            assert np.array_equal(got, ref, equal_nan=True), (name, np.flatnonzero(got != ref)[:5])
+        else:
+            # candidates 1-3 are bit-exact; candidate 4 (val - xs) within 4 ulp(R) of the value scale;
+            # the chosen candidate may flip only where two candidates' objectives tie to ~1e-15
+            tol = 4 * eps(dt) * lhalf_scale(xk, sj, q)
+            bad = np.abs(got.astype(np.float64) - ref.astype(np.float64)) > tol
+            assert bad.mean() <= 1e-4, bad.sum()
+
+
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("n", [1, 9, 65_539])
+@pytest.mark.parametrize("vecb", [True, False])
+@pytest.mark.parametrize("selk", SELS)
+def test_box_iprox_bit_exact(dt, n, vecb, selk):
+    xk, sj, g = inputs(n, dt)
+    d = diag(n, dt)
+    l, u = bounds(n, dt) if vecb else (dt(-1.0), dt(1.0))
+    sel_dev, sel_host = make_sel(selk, n)
+    tl, tu = (T(l), T(u)) if vecb else (float(l), float(u))
+    for name, h in (("l1", sp.NormL1(0.8)), ("l0", sp.NormL0(0.8))):
+        psi = sp.shifted(sp.shifted(h, T(xk), tl, tu, sel_dev), T(sj))
+        y = torch.empty(n, dtype=T(g).dtype, device=DEV)
+        sp.iprox_(y, psi, T(g), T(d))
+        ref = orc.iprox_box(name, xk, sj, g, d, l, u, 0.8, selected=sel_host)
+        assert np.array_equal(N(y), ref, equal_nan=True), (name, np.flatnonzero(N(y) != ref)[:5])
+
+
+@pytest.mark.parametrize("op", ["l0", "l1", "lhalf"])
+def test_box_binf_golden_vectors(op):
+    # runtests.jl:449-494: x = 1, Δ = 0.01, λ = 1, ν = 1/9.1e4
+    h = {"l0": sp.NormL0(1.0), "l1": sp.NormL1(1.0), "lhalf": sp.RootNormLhalf(1.0)}[op]
+    psi = sp.shifted(h, T(np.ones(5)), 0.01, sp.NormLinf(1.0))
+    s = N(sp.prox(psi, T(Q5), NU))
+    for a, b in zip(s, GOLD[op]):
+        assert isapprox(a, b)
+    assert np.max(np.abs(s)) <= 0.01
+    # set_radius! -> ψ.l == -Δ2, ψ.u == Δ2 (runtests.jl:502-509)
+    sp.set_radius_(psi, 0.02)
+    assert psi.l == -0.02 and psi.u == 0.02
+
+
+@pytest.mark.parametrize("op", ["l0", "l1", "lhalf"])
+def test_box_prox_nine_cases(op):
+    # testsbox.jl:1-99 (l = 0, u = 3, s = -1, σ = 1), atol 1e-2
+    c = BOX9[op]
+    H = {"l0": sp.NormL0, "l1": sp.NormL1, "lhalf": sp.RootNormLhalf}[op]
+    for i in range(9):
+        psi = sp.shifted(H(float(c["lam"][i])), T(np.array([float(c["x"][i])])), T(np.array([0.0])), T(np.array([3.0])))
+        psi = sp.shifted(psi, T(np.array([-1.0])))
+        y = N(sp.prox(psi, T(np.array([float(c["q"][i])])), 1.0))
+        assert abs(y[0] - c["sol"][i]) <= 1e-2, (op, i, y[0])
+
+
+@pytest.mark.parametrize("op", ["l0", "l1"])
+def test_box_iprox_fourteen_cases_exact(op):
+    # testsbox.jl:101-304 (l = -2, u = 1, s = -1): exact
+    c = IPROX14[op]
+    H = {"l0": sp.NormL0, "l1": sp.NormL1}[op]
+    for i in range(14):
+        psi = sp.shifted(H(float(c["lam"][i])), T(np.array([float(c["x"][i])])), T(np.array([-2.0])), T(np.array([1.0])))
+        psi = sp.shifted(psi, T(np.array([-1.0])))
+        y = N(sp.iprox(psi, T(np.array([float(c["g"][i])])), T(np.array([float(c["d"][i])]))))
+        assert y[0] == c["sol"][i], (op, i, y[0])
+
+
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("selk", SELS)
+def test_box_values(dt, selk):
+    n = 10_007
+    xk, sj, _ = inputs(n, dt)
+    l, u = bounds(n, dt)
+    sel_dev, sel_host = make_sel(selk, n)
+    rtol = 1e-13 if dt == np.float64 else 2e-6
+    # feasible y: sj + y inside [l, u]
+    w = (l + (u - l) * orc.uniform(n, 11, dt)).astype(dt)
+    y = (w - sj).astype(dt)
+    for name, h in (("l1", sp.NormL1(1.1)), ("l0", sp.NormL0(1.1)), ("lhalf", sp.RootNormLhalf(1.1))):
+        psi = sp.shifted(sp.shifted(h, T(xk), T(l), T(u), sel_dev), T(sj))
+        ref = orc.value_box(name, xk, sj, y, l, u, 1.1, selected=sel_host)
+        assert np.isfinite(ref)
+        assert psi(T(y)) == pytest.approx(ref, rel=rtol)
+        ybad = y.copy()
+        ybad[n // 3] += dt(10.0)
+        assert psi(T(ybad)) == np.inf
+        assert orc.value_box(name, xk, sj, ybad, l, u, 1.1, selected=sel_host) == np.inf
+        # fused value equals the stand-alone one (set semantics of `selected`)
+        if selk != "list":
+            q = orc.uniform(n, 2, dt, 4.0, -2.0)
+            yy = torch.empty(n, dtype=T(q).dtype, device=DEV)
+            _, vf = sp.prox_(yy, psi, T(q), 0.1, want_value=True)
+            assert vf == pytest.approx(psi(yy), rel=rtol)
+
+
+def test_box_constructor_rejects_l_gt_u():
+    # shiftedNormL0Box.jl:33-35
+    x = T(np.ones(5))
+    with pytest.raises(ValueError):
+        sp.shifted(sp.NormL0(1.0), x, T(np.ones(5)), T(np.zeros(5)))
+    with pytest.raises(ValueError):
+        sp.shifted(sp.NormL1(1.0), x, 1.0, 0.0)
+
+
+def test_shift_and_set_bounds_semantics():
+    # runtests.jl:183-191: shift! writes through into the aliased array
+    x = T(np.ones(4)); s = T(np.zeros(4))
+    psi = sp.shifted(sp.NormL1(1.0), x)
+    assert psi.xk.data_ptr() == x.data_ptr() and float(psi.sj.abs().sum()) == 0.0
+    sp.shift_(psi, T(np.full(4, 2.0)))
+    assert np.array_equal(N(x), np.full(4, 2.0))
+    phi = sp.shifted(psi, s)
+    assert phi.shifted_twice and phi.xk.data_ptr() == x.data_ptr()
+    sp.shift_(phi, T(np.full(4, 0.5)))
+    assert np.array_equal(N(s), np.full(4, 0.5)) and np.array_equal(N(x), np.full(4, 2.0))
+    l = T(np.zeros(4)); u = T(np.ones(4))
+    box = sp.shifted(sp.NormL0(1.0), x, l, u)
+    sp.set_bounds_(box, T(np.full(4, -1.0)), 3.0)
+    assert np.array_equal(N(l), np.full(4, -1.0)) and np.array_equal(N(u), np.full(4, 3.0))
+
+
+# ---------------------------------------------------------------------------- L1B2 ---
+def test_l1b2_golden_vector():
+    gold = [-0.006367076930786, 0.001288947922799, -0.001130889587543, -0.004285677352167, 0.006176811716709]
+    psi = sp.shifted(sp.NormL1(1.0), T(np.ones(5)), 0.01, sp.NormL2(1.0))
+    s = N(sp.prox(psi, T(Q5), NU))
+    for a, b in zip(s, gold):
+        assert isapprox(a, b)
+    assert np.linalg.norm(s) <= 0.01 * (1 + 1e-12)
+    y = 0.5 * 0.01 * np.ones(5) / np.sqrt(5)
+    assert psi(T(y)) == pytest.approx(np.sum(np.abs(1 + y)), rel=1e-14)
+    assert psi(T(3 * y)) == np.inf
+
+
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("n", [5, 1000, 262_147])
+def test_l1b2_against_oracle(dt, n):
+    xk, sj, q = inputs(n, dt)
+    lam, sigma = 1.0, 0.1
+    y0 = orc.prox_l1b2(xk, sj, q, lam, sigma, 1e30)  # ball inactive
+    full = float(np.linalg.norm((y0 + sj).astype(np.float64)))
+    for delta in (2.0 * full, 0.5 * full):
+        psi = sp.shifted(sp.shifted(sp.NormL1(lam), T(xk), delta, sp.NormL2(1.0)), T(sj))
+        y = torch.empty(n, dtype=T(q).dtype, device=DEV)
+        _, val = sp.prox_(y, psi, T(q), sigma, want_value=True)
+        ref = orc.prox_l1b2(xk, sj, q, lam, sigma, delta)
+        got = N(y)
+        # solver-limited: η agrees to a few ulp, y is linear in 1/η between kinks
+        tol = (64 if dt == np.float64 else 16) * eps(dt) * (np.abs(ref) + np.abs(sj) + 1)
+        assert np.all(np.abs(got.astype(np.float64) - ref.astype(np.float64)) <= tol)
+        assert np.isfinite(val)
+        assert val == pytest.approx(orc.value_l1b2(xk, sj, got, lam, delta), rel=1e-12 if dt == np.float64 else 1e-5)
+        if delta < full:
+            assert psi.last_passes <= (14 if dt == np.float64 else 9)
+            nrm = np.linalg.norm((got + sj).astype(np.float64))
+            assert nrm == pytest.approx(delta, rel=1e-10 if dt == np.float64 else 1e-5)
+
+
+# -------------------------------------------------------------------------- groups ---
+def ragged_offsets(ngroups, maxlen, seed=3):
+    rng = np.random.default_rng(seed)
+    sizes = np.floor(np.exp(rng.uniform(0, np.log(maxlen + 1), ngroups))).astype(np.int64).clip(1, maxlen)
+    return np.concatenate([[0], np.cumsum(sizes)])
+
+
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("layout", ["one", "two", "g64", "ragged"])
+def test_group_l2_prox_and_value(dt, layout):
+    offs = {"one": np.array([0, 777]), "two": np.array([0, 3, 6]), "g64": np.arange(0, 64 * 501, 64),
+            "ragged": ragged_offsets(300, 4096)}[layout]
+    n = int(offs[-1]); ng = len(offs) - 1
+    xk, sj, q = inputs(n, dt)
+    lam_g = (dt(0.5) + orc.uniform(ng, 12, dt)).astype(dt)
+    sigma = 0.3
+    h = sp.GroupNormL2(T(lam_g), None, offsets=T(offs))
+    psi = sp.shifted(sp.shifted(h, T(xk)), T(sj))
+    y = torch.empty(n, dtype=T(q).dtype, device=DEV)
+    _, val = sp.prox_(y, psi, T(q), sigma, want_value=True)
+    ref = orc.prox_groupl2(xk, sj, q, offs, lam_g, sigma)
+    got = N(y)
+    # α = max(1 - σλ/‖sol‖, 0); the norm is within 1 ulp of exact on both sides (order unspecified
+    # in the reference: BLAS nrm2).  Tolerance: 8 ulp of the un-shifted magnitude.
+    tol = 8 * eps(dt) * (np.abs(xk) + np.abs(sj) + np.abs(q) + 1)
+    assert np.all(np.abs(got.astype(np.float64) - ref.astype(np.float64)) <= tol)
+    # support: whole groups thresholded to zero agree
+    zr = ref == (np.zeros(n, dt) - (xk + sj)); zg = got == (np.zeros(n, dt) - (xk + sj))
+    assert np.array_equal(zr, zg)
+    rtol = 1e-13 if dt == np.float64 else 2e-6
+    assert val == pytest.approx(orc.value_groupl2(xk, sj, got, offs, lam_g), rel=rtol)
+    assert psi(y) == pytest.approx(val, rel=rtol)
+
+
+def test_group_l2_from_norml2_differential():
+    # runtests.jl:244-251: ShiftedGroupNormL2 from NormL2 == NormL2 prox of (q + x) minus x
+    rng = np.random.default_rng(5)
+    x = rng.random(6); q = rng.random(6); lam, nu = 0.7, 0.4
+    psi = sp.shifted(sp.NormL2(lam), T(x))
+    y = N(sp.prox(psi, T(q), nu))
+    v = q + x
+    ytrue = max(1 - nu * lam / np.linalg.norm(v), 0) * v - x
+    assert np.linalg.norm(y - ytrue) <= 1e-11
+
+
+def test_group_l2binf_golden_vectors():
+    # runtests.jl:587-606 (from NormL2, one group) and :648-705 (two groups)
+    gold = [-0.010000000000000, 0.005862191941930, -0.005131948291800, -0.010000000000000, 0.010000000000000]
+    psi = sp.shifted(sp.NormL2(1.0), T(np.ones(5)), 0.01, sp.NormLinf(1.0))
+    s = N(sp.prox(psi, T(Q5), NU))
+    for a, b in zip(s, gold):
+        assert isapprox(a, b)
+    lam = np.array([0.396767474230670, 0.538816734003357])
+    q = np.array([-0.649013765191241, 1.181166041965532, -0.758453297283692, -1.109613038501522,
+                  -0.845551240007797, -0.572664866457950])
+    psi = sp.shifted(sp.GroupNormL2(lam.tolist(), [range(0, 3), range(3, 6)]), T(np.ones(6)), 0.01, sp.NormLinf(1.0))
+    s = N(sp.prox(psi, T(q), 0.419194514403295))
+    for a, b in zip(s, [-0.01, 0.01, -0.01, -0.01, -0.01, -0.01]):
+        assert isapprox(a, b)
+    y = 0.004 * np.ones(6)
+    v = 1 + y
+    assert psi(T(y)) == pytest.approx(lam[0] * np.linalg.norm(v[:3]) + lam[1] * np.linalg.norm(v[3:]), rel=1e-14)
+    assert psi(T(3 * y)) == np.inf
+
+
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("layout", ["g64", "ragged"])
+def test_group_l2binf_against_oracle(dt, layout):
+    offs = {"g64": np.arange(0, 64 * 201, 64), "ragged": ragged_offsets(120, 1500)}[layout]
+    n = int(offs[-1]); ng = len(offs) - 1
+    xk, sj, q = inputs(n, dt)
+    lam_g = (dt(0.5) + orc.uniform(ng, 12, dt)).astype(dt)
+    sigma, delta = 0.3, 0.5
+    h = sp.GroupNormL2(T(lam_g), None, offsets=T(offs))
+    psi = sp.shifted(sp.shifted(h, T(xk), delta, sp.NormLinf(1.0)), T(sj))
+    y = torch.empty(n, dtype=T(q).dtype, device=DEV)
+    sp.prox_(y, psi, T(q), sigma)
+    ref = orc.prox_groupl2binf(xk, sj, q, offs, lam_g, sigma, delta)
+    got = N(y)
+    # solver-limited (bisection to adjacent floats on both sides, independent norm rounding):
+    # the reference's own tests ask `≈` (rtol √eps); we ask 1e-9 / 1e-4 of the value scale
+    scale = np.abs(xk) + np.abs(sj) + np.abs(q) + 1
+    tol = (1e-9 if dt == np.float64 else 2e-4) * scale
+    assert np.all(np.abs(got.astype(np.float64) - ref.astype(np.float64)) <= tol)
+    zr = ref == (np.zeros(n, dt) - (xk + sj)); zg = got == (np.zeros(n, dt) - (xk + sj))
+    assert np.array_equal(zr, zg)
+
+
+# --------------------------------------------------------------------------- top-r ---
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("n,r", [(6, 2), (1000, 1), (1000, 999), (1000, 1000), (1000, 2000), (16_384, 100),
+                                 (16_385, 1024), (65_536, 1024), (100_003, 5000), (131_072, 77), (300_001, 1234)])
+@pytest.mark.parametrize("binf", [False, True])
+def test_indballl0_bit_exact(dt, n, r, binf):
+    xk, sj, q = inputs(n, dt)
+    h = sp.IndBallL0(r)
+    psi = sp.shifted(h, T(xk), 1.0, sp.NormLinf(1.0)) if binf else sp.shifted(h, T(xk))
+    psi = sp.shifted(psi, T(sj))
+    y = torch.empty(n, dtype=T(q).dtype, device=DEV)
+    sp.prox_(y, psi, T(q), 1.0)
+    ref = orc.prox_indballl0(xk, sj, q, r, delta=1.0 if binf else None)
+    assert np.array_equal(N(y), ref), np.flatnonzero(N(y) != ref)[:8]
+
+
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("n,r", [(4096, 300), (70_001, 1024), (200_000, 4321)])
+def test_indballl0_ties_keep_lowest_index(dt, n, r):
+    # magnitudes quantised to 1/64: massive ties at the threshold (SURVEY.md §8d tie-stress)
+    xk = np.zeros(n, dt); sj = np.zeros(n, dt)
+    q = (np.round(orc.uniform(n, 2, dt, 4.0, -2.0) * 64) / 64).astype(dt)
+    psi = sp.shifted(sp.IndBallL0(r), T(xk))
+    y = N(sp.prox(psi, T(q), 1.0))
+    ref = orc.prox_indballl0(xk, sj, q, r)
+    assert np.array_equal(y, ref)
+    assert np.count_nonzero(y) <= r
+
+
+def test_indballl0_nan_and_source_text():
+    z = np.array([1.0, np.nan, 3.0])
+    psi = sp.shifted(sp.IndBallL0(1), T(np.zeros(3)))
+    y = N(sp.prox(psi, T(z), 1.0))
+    assert np.isnan(y[1]) and y[0] == 0 and y[2] == 0
+    z = np.array([1.0, -2.0, 2.0, 0.5, -2.0, 2.0])
+    psi = sp.shifted(sp.IndBallL0(3), T(np.zeros(6)))
+    assert np.array_equal(N(sp.prox(psi, T(z), 1.0)), [0, -2.0, 2.0, 0, -2.0, 0])
+
+
+@pytest.mark.parametrize("dt", DT)
+def test_indballl0_batched(dt):
+    nprob, n, r = 37, 8192 + 64, 100
+    xk, sj, q = inputs(nprob * n, dt)
+    psi = sp.shifted(sp.shifted(sp.IndBallL0(r), T(xk), 1.0, sp.NormLinf(1.0), nprob=nprob), T(sj))
+    y = torch.empty(nprob * n, dtype=T(q).dtype, device=DEV)
+    sp.prox_(y, psi, T(q), 1.0)
+    got = N(y)
+    for p in range(nprob):
+        sl = slice(p * n, (p + 1) * n)
+        assert np.array_equal(got[sl], orc.prox_indballl0(xk[sl], sj[sl], q[sl], r, delta=1.0)), p
