@@ -153,7 +153,7 @@ class ClockSampler(threading.Thread):
         self.index, self.period = index, period
         self.samples, self.reasons = [], set()
         self.max_mhz = None
-        self._stop = threading.Event()
+        self._halt = threading.Event()
         try:
             import pynvml
 
@@ -171,7 +171,7 @@ class ClockSampler(threading.Thread):
     def run(self):
         if self.nv is None:
             return
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
                 r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
@@ -183,7 +183,7 @@ class ClockSampler(threading.Thread):
             time.sleep(self.period)
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=2)
         s = sorted(self.samples)
         return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,

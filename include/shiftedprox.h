@@ -87,9 +87,11 @@ typedef int32_t (*spx_allreduce_sum_fn)(void* user, double* vals, int32_t count)
 /* ------------------------------------------------------------- context --- */
 int32_t spx_version(void);
 const char* spx_last_error(void);
-/* stream: a cudaStream_t to enqueue on (e.g. the host framework's current
- * stream), or NULL to let the context create its own non-blocking stream. */
-int32_t spx_ctx_create(spx_ctx** out, int32_t device, void* stream);
+/* stream: the cudaStream_t to enqueue on, e.g. the host framework's current
+ * stream; NULL is CUDA's default stream (stream 0), as everywhere in the CUDA
+ * API.  own_stream != 0: ignore `stream`, the context creates (and later
+ * destroys) its own non-blocking stream. */
+int32_t spx_ctx_create(spx_ctx** out, int32_t device, void* stream, int32_t own_stream);
 int32_t spx_ctx_destroy(spx_ctx* ctx);
 int32_t spx_ctx_set_stream(spx_ctx* ctx, void* stream);
 int32_t spx_ctx_synchronize(spx_ctx* ctx);

@@ -240,7 +240,7 @@ extern "C" {
 int32_t spx_version(void) { return 100; }
 const char* spx_last_error(void) { return spx::g_err; }
 
-int32_t spx_ctx_create(spx_ctx** out, int32_t device, void* stream) {
+int32_t spx_ctx_create(spx_ctx** out, int32_t device, void* stream, int32_t own_stream) {
   SPX_REQUIRE(out != nullptr, "null out");
   *out = nullptr;
   int ndev = 0;
@@ -256,8 +256,8 @@ int32_t spx_ctx_create(spx_ctx** out, int32_t device, void* stream) {
   spx_ctx* c = new spx_ctx();
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
-  if (stream != nullptr) {
-    c->stream = (cudaStream_t)stream;
+  if (own_stream == 0) {
+    c->stream = (cudaStream_t)stream;  // NULL = the default stream
   } else {
     SPX_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     c->owns_stream = true;

@@ -51,7 +51,7 @@ class _Ctx:
         self.device = device
         self.handle = C.c_void_p()
         stream = torch.cuda.current_stream(device).cuda_stream
-        L.call("spx_ctx_create", C.byref(self.handle), C.c_int32(device), C.c_void_p(stream))
+        L.call("spx_ctx_create", C.byref(self.handle), C.c_int32(device), C.c_void_p(stream), C.c_int32(0))
         self.stream = stream
 
     def use_current_stream(self):
