@@ -83,6 +83,7 @@ static int32_t prox_lhalf(spx_ctx* ctx, int64_t n, R* y, const R* xk, const R* s
     op.nulam = nulam;
     op.p = lhalf_threshold(nulam);
     op.c4 = (double)(nulam / R(4));
+    op.by3.set(R(3));
   });
 }
 
@@ -160,6 +161,9 @@ static int32_t launch_box_t(spx_ctx* ctx, cudaStream_t stream, int opc, bool inv
       op.y = y; op.sel = sel; op.lambda = lambda; op.sigma = sigma;
       op.c4 = (double)(sigma * lambda / R(4));
       op.cos_2pi3 = std::cos(kTwoPiOver3);
+      op.by3.set(R(3));
+      op.by_sigma.set(sigma);
+      op.by_sigma64.set((double)sigma);
       return ew_launch(ctx, stream, op, n, base, partials, nb);
     }
   } else {
@@ -172,6 +176,7 @@ static int32_t launch_box_t(spx_ctx* ctx, cudaStream_t stream, int opc, bool inv
       IproxL0Box<R, PSI> op;
       set_box(op, xk, sj, qg, d, lvec, lval, uvec, uval);
       op.y = y; op.sel = sel; op.lambda = lambda;
+      op.lam_ok = lambda == R(0) || (std::fabs((double)lambda) > 1e-150 && std::fabs((double)lambda) < 1e150);
       return ew_launch(ctx, stream, op, n, base, partials, nb);
     }
   }

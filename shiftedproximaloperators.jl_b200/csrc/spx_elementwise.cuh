@@ -7,6 +7,8 @@
 // same pass (warp shuffle -> block -> one slot per block, fixed order).
 // Grid = resident CTAs per SM x 148 SMs, grid-stride over tiles.
 #pragma once
+#include <type_traits>
+
 #include "spx_common.cuh"
 
 namespace spx {
@@ -17,8 +19,12 @@ constexpr int kEwThreads = 256;
 //   using Real = R;  static constexpr int NIN; static constexpr bool OUT, ACC;
 //   const R* in[NIN]; R fill[NIN]; R* y;
 //   __device__ R apply(const R (&x)[NIN], long long i, Partial& acc) const;
+// resident CTAs per SM an operator asks for (Op::MINB, default 1 = let ptxas choose registers)
+template <class Op, class = void> struct MinBlocks { static constexpr int value = 1; };
+template <class Op> struct MinBlocks<Op, std::void_t<decltype(Op::MINB)>> { static constexpr int value = Op::MINB; };
+
 template <int VEC, int UNROLL, class Op>
-__global__ void __launch_bounds__(kEwThreads)
+__global__ void __launch_bounds__(kEwThreads, MinBlocks<Op>::value)
     ew_kernel(const Op op, const long long n, const long long index_base, Partial* __restrict__ partials) {
   using R = typename Op::Real;
   constexpr int NIN = Op::NIN;

@@ -101,28 +101,117 @@ template <class R, bool PSI> struct IproxL0 {
 // every R (Float64 literals -3/2, 2π/3 promote); the leading factors stay in R.
 constexpr double kTwoPiOver3 = 6.283185307179586 / 3.0;  // (2*π)/3 in Float64
 
-// t = (νλ/4) * w^(-3/2), w = |z|/3.  w*sqrt(w) is within 1 ulp of w^(3/2)
-// (sqrt and the product are each correctly rounded) and the quotient adds half
-// an ulp: same accuracy class as a < 1 ulp `pow`, at a fraction of the FP64 work.
-__device__ __forceinline__ double lhalf_t(double c4, double w) { return c4 / (w * sqrt(w)); }
+// ---- FP64 building blocks sized for the B200 FP64 pipe (64 lanes/clk/SM: at
+// the HBM roofline a Float64 element has ~150 FP64 issue slots in total) -------
 
-// real part of 1 + cos(2π/3 - 2ϕ/3) with ϕ = acos(t + 0im)  (complex for t > 1:
-// shiftedRootNormLhalfBox.jl:92,106): t <= 1 -> the real formula; t > 1 ->
-// ϕ = -i acosh(t), cos(a + ib) = cos a cosh b - i sin a sinh b.
-__device__ __forceinline__ double lhalf_one_plus_cos(double t, double cos_2pi3) {
-  double re;
-  if (t <= 1.0) {
-    re = cos(kTwoPiOver3 - (2.0 * acos(t)) / 3.0);
-  } else {
-    re = cos_2pi3 * cosh((2.0 * acosh(t)) / 3.0);
-  }
-  return 1.0 + re;
+// Correctly rounded a / s for a warp-uniform divisor s, given y = RN(1/s)
+// (Markstein: q faithful + exact FMA residual => the corrected quotient is the
+// IEEE quotient; two correction steps, checked exhaustively-by-sampling in
+// tests/test_div_markstein.py).  Falls back to the true division outside the
+// range where every intermediate is a normal number.
+__device__ __forceinline__ double div_uniform(double a, double s, double y) {
+  const double q0 = a * y;
+  const double r0 = __fma_rn(-s, q0, a);
+  const double q1 = __fma_rn(r0, y, q0);
+  const double r1 = __fma_rn(-s, q1, a);
+  double q2 = __fma_rn(r1, y, q1);
+  const double aa = fabs(a);
+  if (!(aa > 1e-250 && aa < 1e250)) q2 = (aa == 0.0) ? q0 : __ddiv_rn(a, s);  // rare: a real branch
+  return q2;
 }
+
+// t = c4 * w^(-3/2) to ~1.5 ulp (the reference's `^` is < 1 ulp, its product adds
+// half an ulp): s = sqrt(w) from rsqrt + one FMA correction, u = w*s, then the
+// quotient c4/u by one Markstein step on the reciprocal estimate r^3.
+__device__ __forceinline__ double lhalf_t(double c4, double w) {
+  if (!(w > 1e-200 && w < 1e200)) return c4 * pow(w, -1.5);  // 0, Inf, NaN, denormal: library path
+  const double r = rsqrt(w);
+  double s = w * r;
+  const double e = __fma_rn(-s, s, w);
+  s = __fma_rn(e, 0.5 * r, s);
+  const double u = w * s;
+  const double y = (r * r) * r;
+  const double q0 = c4 * y;
+  const double e2 = __fma_rn(-u, q0, c4);
+  return __fma_rn(e2, y, q0);
+}
+
+// One Newton step on T3(x) = 4x^3 - 3x = rhs with a compensated residual: the
+// square is split into p + e (exact), 4p - 3 is exact, so the residual carries
+// one rounding of a quantity that is ~0 at the root; the slope is inverted in
+// Float32 (error 1e-7: the step stays quadratic down to 1e-19).
+__device__ __forceinline__ double cubic_newton(double x, double rhs) {
+  const double p = x * x;
+  const double e = __fma_rn(x, x, -p);
+  const double u = __fma_rn(4.0, p, -3.0);
+  double f = __fma_rn(x, u, -rhs);
+  f = __fma_rn(4.0 * x, e, f);
+  const float slope = (float)__fma_rn(12.0, p, -3.0);
+  const double y = (double)__frcp_rn(slope);
+  return __fma_rn(-f, y, x);
+}
+
+// G(t) = real(1 + cos(2π/3 - (2/3) acos(t + 0im)))   (shiftedRootNormLhalf.jl:57,
+// shiftedRootNormLhalfBox.jl:92,106) without acos/cos:
+//   t <= 1:  ψ = π/3 - acos(t)/3 ∈ [π/6, π/3] has cos 3ψ = -t, and 1 + cos 2ψ = 2 cos²ψ,
+//            so G = 2 d² with d the root of 4d³ - 3d = -t in [1/2, √3/2];
+//   t >  1:  acos(t + 0im) = -i acosh t, real(cos(a + ib)) = cos a cosh b, and
+//            cosh(2x) = 2cosh²x - 1, so G = 1 + cos(2π/3) (2c² - 1) with c >= 1 the root of
+//            4c³ - 3c = t.
+// Start values come from Float32 (SFU) evaluations of the closed forms, then two
+// compensated Newton steps in Float64 (a third next to the double root t -> 1).
+// Measured against 200-bit mpmath: <= 2 ulp for t <= 0.9999, i.e. at the level of
+// the reference's own acos/cos chain (tests/test_gpu_parity.py).
+__device__ __forceinline__ double lhalf_G_real(double t) {  // 0 <= t <= 1
+  const float tf = (float)t;
+  double d = (double)__cosf(1.0471975511965976f - acosf(tf) * 0.33333334f);
+  d = cubic_newton(d, -t);
+  d = cubic_newton(d, -t);
+  if (t > 0.98) {
+    d = cubic_newton(d, -t);
+    d = cubic_newton(d, -t);
+  }
+  return 2.0 * (d * d);
+}
+// The complex branch (t > 1), kept for reference and for tools/check_lhalf_branch.py:
+// G = 1 + cos(2π/3) (2c² - 1), c = cosh(acosh(t)/3) the root >= 1 of 4c³ - 3c = t.
+__device__ __forceinline__ double lhalf_G(double t, double cos_2pi3) {
+  if (t <= 1.0) return lhalf_G_real(t);
+  if (t < 1e30) {
+    const float tf = (float)t;
+    const float w = tf > 1e15f ? 2.0f * tf : tf + sqrtf(fmaf(tf, tf, -1.0f));
+    const float k = exp2f(__log2f(w) * 0.33333334f);
+    double c = (double)(0.5f * (k + __fdividef(1.0f, k)));
+    c = cubic_newton(c, t);
+    c = cubic_newton(c, t);
+    return 1.0 + cos_2pi3 * __fma_rn(2.0 * c, c, -1.0);
+  }
+  return 1.0 + cos_2pi3 * cosh((2.0 * acosh(t)) / 3.0);
+}
+
+// a / s for a warp-uniform divisor s: Float64 goes through div_uniform, Float32
+// through the native (FP32-pipe) division
+template <class R> struct UDiv;
+template <> struct UDiv<double> {
+  double s, y;
+  bool fast;
+  __host__ void set(double s_) {
+    s = s_;
+    y = 1.0 / s_;
+    fast = std::isfinite(s_) && std::fabs(s_) > 1e-30 && std::fabs(s_) < 1e30;
+  }
+  __device__ __forceinline__ double operator()(double a) const { return fast ? div_uniform(a, s, y) : a / s; }
+};
+template <> struct UDiv<float> {
+  float s;
+  __host__ void set(float s_) { s = s_; }
+  __device__ __forceinline__ float operator()(float a) const { return a / s; }
+};
 
 // shiftedRootNormLhalf.jl:41-63
 template <class R, bool PSI> struct ProxLhalf {
   using Real = R;
-  static constexpr int NIN = 3, UNROLL = 2;
+  static constexpr int NIN = 3, UNROLL = 1;
   static constexpr bool OUT = true, ACC = PSI;
   const R* in[NIN];  // xk, sj, q
   R fill[NIN];
@@ -130,6 +219,7 @@ template <class R, bool PSI> struct ProxLhalf {
   R nulam;      // σλ
   double p;     // 54^(1/3) (2νλ)^(2/3) / 4  (Float64)
   double c4;    // (double)(νλ/4)
+  UDiv<R> by3;  // x / 3 in R
   __device__ __forceinline__ R apply(const R (&x)[NIN], long long, Partial& acc) const {
     R xs = x[0] + x[1];
     R z = x[2] + xs;  // ψ.sol[i]  (:50)
@@ -138,15 +228,71 @@ template <class R, bool PSI> struct ProxLhalf {
     if ((double)az <= p) {
       o = R(0);
     } else {
-      double t = lhalf_t(c4, (double)(az / R(3)));
-      R coef = (R(2) * jl_sign(z)) / R(3) * az;
-      o = (R)((double)coef * (1.0 + cos(kTwoPiOver3 - (2.0 * acos(t)) / 3.0)));
+      // above the threshold t = νλ/4 (|z|/3)^(-3/2) lies in (0, 1/√2]: real branch only
+      const double t = lhalf_t(c4, (double)by3(az));
+      const R coef = (jl_sign(z) * (R(2) / R(3))) * az;  // == ((2 sign z) / 3) |z| bit for bit
+      o = (R)((double)coef * lhalf_G_real(t));
     }
     o = o - xs;
     if (PSI) acc.s += h_term(SPX_H_LHALF, xs + o);
     return o;
   }
 };
+
+// The three quotients the Box iprox! regimes with |d| >= eps need (shiftedNormL0Box.jl:179-188):
+//   a = (-g)/d,  b = g/(d/2),  c = λ/(d/2).
+// Reference form: three IEEE divisions.  Float64 fast form: ONE division (the correctly rounded
+// reciprocal y = 1/d), a and λ/d by two Markstein corrections each (= the IEEE quotients, see
+// div_uniform), and b = -2a, c = 2(λ/d): scaling by 2 commutes with rounding while nothing is subnormal
+// and nothing overflows.  Elements outside that range take the reference form through one
+// non-inlined call, so the straight-line path carries no fallback code.
+template <class R> struct Quot3 { R a, b, c; };
+
+template <class R> __device__ __forceinline__ Quot3<R> quot3_ref(R g, R d, R lambda) {
+  Quot3<R> q;
+  const R d_2 = d / R(2);
+  q.a = (-g) / d;
+  q.b = g / d_2;
+  q.c = lambda / d_2;
+  return q;
+}
+static __device__ __noinline__ Quot3<double> quot3_ref_call(double g, double d, double lambda) {
+  return quot3_ref<double>(g, d, lambda);
+}
+__device__ __forceinline__ double markstein(double a, double d, double y) {
+  const double q0 = a * y;
+  const double r0 = __fma_rn(-d, q0, a);
+  const double q1 = __fma_rn(r0, y, q0);
+  const double r1 = __fma_rn(-d, q1, a);
+  const double q2 = __fma_rn(r1, y, q1);
+  return a == 0.0 ? q0 : q2;  // ±0 numerators: the product already carries the IEEE sign
+}
+__device__ __forceinline__ Quot3<float> quot3(float g, float d, float lambda, bool) {
+  return quot3_ref<float>(g, d, lambda);  // FP32 divisions run on the FP32 pipe
+}
+__device__ __forceinline__ Quot3<double> quot3(double g, double d, double lambda, bool lam_ok) {
+  const double ad = fabs(d), ag = fabs(g);
+  const bool fast = lam_ok && ad > 1e-100 && ad < 1e100 && (g == 0.0 || (ag > 1e-150 && ag < 1e150));
+  if (!fast) return quot3_ref_call(g, d, lambda);
+  const double y = 1.0 / d;
+  Quot3<double> q;
+  q.a = markstein(-g, d, y);
+  q.b = -2.0 * q.a;
+  q.c = 2.0 * markstein(lambda, d, y);
+  return q;
+}
+
+// iprox_zero (ShiftedProximalOperators.jl:217-236) reusing an already computed (-g)/d
+template <class R> __device__ __forceinline__ R iprox_zero_q(R d, R g, R l, R u, R neg_g_over_d) {
+  const R eps = Eps<R>::value;
+  const R r1 = jl_min(jl_max(neg_g_over_d, l), u);
+  const R d_2 = d * R(0.5);
+  const R val_l = d_2 * (l * l) + g * l;
+  const R val_u = d_2 * (u * u) + g * u;
+  const R r2 = (val_l < val_u) ? l : u;
+  const R r3 = (g > R(0)) ? l : ((g < R(0)) ? u : R(0));
+  return (d > eps) ? r1 : ((d < -eps) ? r2 : r3);
+}
 
 // ------------------------------------------------------------------ Box types --
 // inputs: 0 xk, 1 sj, 2 q (or g), [3 d], then l, u (nullable -> scalar fill)
@@ -165,7 +311,7 @@ template <class R> struct BoxPsi {
 // shiftedNormL1Box.jl:89-125
 template <class R, bool PSI> struct ProxL1Box {
   using Real = R;
-  static constexpr int NIN = 5, UNROLL = 2;
+  static constexpr int NIN = 5, UNROLL = 2, MINB = 4;
   static constexpr bool OUT = true, ACC = PSI;
   const R* in[NIN];  // xk, sj, q, l, u
   R fill[NIN];
@@ -192,7 +338,7 @@ template <class R, bool PSI> struct ProxL1Box {
 // shiftedNormL1Box.jl:131-225
 template <class R, bool PSI> struct IproxL1Box {
   using Real = R;
-  static constexpr int NIN = 6, UNROLL = 2;
+  static constexpr int NIN = 6, UNROLL = 1, MINB = 3;
   static constexpr bool OUT = true, ACC = PSI;
   const R* in[NIN];  // xk, sj, g, d, l, u
   R fill[NIN];
@@ -261,7 +407,7 @@ template <class R, bool PSI> struct IproxL1Box {
 // shiftedNormL0Box.jl:89-131
 template <class R, bool PSI> struct ProxL0Box {
   using Real = R;
-  static constexpr int NIN = 5, UNROLL = 2;
+  static constexpr int NIN = 5, UNROLL = 2, MINB = 4;
   static constexpr bool OUT = true, ACC = PSI;
   const R* in[NIN];  // xk, sj, q, l, u
   R fill[NIN];
@@ -298,72 +444,68 @@ template <class R, bool PSI> struct ProxL0Box {
   }
 };
 
-// shiftedNormL0Box.jl:137-231
+// shiftedNormL0Box.jl:137-231.  The three regimes (|d| < eps, d >= eps, d <= -eps) are evaluated
+// straight-line and selected: with 64 elements per warp and mixed-sign d every warp needs all of them,
+// so predication beats divergence, and the two lanes of a 128-bit pair interleave.
 template <class R, bool PSI> struct IproxL0Box {
   using Real = R;
-  static constexpr int NIN = 6, UNROLL = 2;
+  static constexpr int NIN = 6, UNROLL = 1, MINB = 3;
   static constexpr bool OUT = true, ACC = PSI;
   const R* in[NIN];  // xk, sj, g, d, l, u
   R fill[NIN];
   R* y;
   DevSel sel;
   R lambda;
+  bool lam_ok;  // λ is 0 or a normal number far from the range limits (host-checked)
   __device__ __forceinline__ R apply(const R (&x)[NIN], long long i, Partial& acc) const {
     const R xi = x[0], si = x[1], gi = x[2], di = x[3], li = x[4], ui = x[5];
     const R eps = Eps<R>::value;
     const bool s = sel.has(i);
-    const R xs = xi + si;
+    const R xs = xi + si, mxs = -xs;
     const R left = li - si, right = ui - si;
     const bool zero_in = (li <= -xi) && (-xi <= ui);
-    R yi;
-    if (!s) {
-      yi = iprox_zero(di, gi, left, right);
-    } else if (jl_abs(di) < eps) {  // :155-177
-      if (gi == R(0)) {
-        yi = zero_in ? -xs : R(0);
-      } else {
-        // gi > 0 -> left edge, gi < 0 -> right edge; a NaN g leaves y[i] untouched in the
-        // reference (no branch taken): NaN is written here (y is write-only)
-        R val_min = gi - gi;  // 0, or NaN for NaN g
-        yi = val_min / val_min;  // NaN placeholder, overwritten below for finite g
-        if (gi > R(0)) {
-          val_min = gi * left + ((xi == -li) ? R(0) : lambda);
-          yi = left;
-        } else if (gi < R(0)) {
-          val_min = gi * right + ((xi == -ui) ? R(0) : lambda);
-          yi = right;
-        }
-        if (zero_in) {
-          R val_0 = (-gi) * xs;
-          if (val_0 < val_min) yi = -xs;
-        }
-      }
-    } else {  // :179-224
-      const R di_2 = di / R(2);
-      const R lx = li + xi, ux = ui + xi;
-      const R gi2_di = gi / di_2;
-      const R fi2_di = gi2_di - R(2) * xs;
-      const R l2_di = lambda / di_2;
-      const R val_left = (lx == R(0)) ? R(0) : (lx * lx + fi2_di * lx + l2_di);
-      const R val_right = (ux == R(0)) ? R(0) : (ux * ux + fi2_di * ux + l2_di);
-      if (di >= eps) {  // :189-209
-        const R aq_y = (-gi) / di;
-        const R aq_v = aq_y + xs;
-        R val_min;
-        if ((lx <= aq_v) && (aq_v <= ux)) {
-          val_min = (aq_v == R(0)) ? -(aq_v * aq_v) : (-(aq_v * aq_v) + l2_di);
-          yi = aq_y;
-        } else {
-          yi = (val_left < val_right) ? left : right;
-          val_min = jl_min(val_left, val_right);
-        }
-        if (zero_in && (R(0) < val_min)) yi = -xs;
-      } else {  // :211-223
-        yi = (val_left > val_right) ? left : right;
-        R val_max = jl_max(val_left, val_right);
-        if (zero_in && (R(0) > val_max)) yi = -xs;
-      }
+    const R lx = li + xi, ux = ui + xi;
+    // ---- regime |d| < eps  (:155-177) ----
+    R y1;
+    {
+      const R vl = gi * left + ((xi == -li) ? R(0) : lambda);
+      const R vr = gi * right + ((xi == -ui) ? R(0) : lambda);
+      const bool gpos = gi > R(0), gneg = gi < R(0);
+      // a NaN g takes no branch in the reference (y[i] untouched); NaN is written here
+      const R nan = gi - gi;
+      const R val_min = gpos ? vl : (gneg ? vr : nan / nan);
+      R yy = gpos ? left : (gneg ? right : nan / nan);
+      const R val_0 = (-gi) * xs;
+      if (zero_in && (val_0 < val_min)) yy = mxs;
+      y1 = (gi == R(0)) ? (zero_in ? mxs : R(0)) : yy;
     }
+    // ---- regimes |d| >= eps  (:179-224): one reciprocal serves every quotient ----
+    const bool small_d = jl_abs(di) < eps;
+    const Quot3<R> qt = quot3(gi, small_d ? R(1) : di, lambda, lam_ok);
+    const R aq_y = qt.a;    // (-g)/d
+    const R gi2_di = qt.b;  // g/(d/2)
+    const R l2_di = qt.c;   // λ/(d/2)
+    const R fi2_di = gi2_di - R(2) * xs;
+    const R val_left = (lx == R(0)) ? R(0) : (lx * lx + fi2_di * lx + l2_di);
+    const R val_right = (ux == R(0)) ? R(0) : (ux * ux + fi2_di * ux + l2_di);
+    R y2;
+    {  // d >= eps  (:189-209)
+      const R aq_v = aq_y + xs;
+      const bool inside = (lx <= aq_v) && (aq_v <= ux);
+      const R sq = aq_v * aq_v;
+      const R vin = (aq_v == R(0)) ? -sq : (-sq + l2_di);
+      const R val_min = inside ? vin : jl_min(val_left, val_right);
+      y2 = inside ? aq_y : ((val_left < val_right) ? left : right);
+      if (zero_in && (R(0) < val_min)) y2 = mxs;
+    }
+    R y3;
+    {  // d <= -eps  (:211-223)
+      y3 = (val_left > val_right) ? left : right;
+      const R val_max = jl_max(val_left, val_right);
+      if (zero_in && (R(0) > val_max)) y3 = mxs;
+    }
+    R yi = small_d ? y1 : ((di >= eps) ? y2 : y3);
+    if (!s) yi = iprox_zero_q(di, gi, left, right, aq_y);
     if (PSI) BoxPsi<R>{SPX_H_L0}.add(acc, s, xi, si, yi, li, ui);
     return yi;
   }
@@ -384,7 +526,7 @@ __device__ __forceinline__ bool jl_isgreater(double x, double y) {
 // shiftedRootNormLhalfBox.jl:86-120
 template <class R, bool PSI> struct ProxLhalfBox {
   using Real = R;
-  static constexpr int NIN = 5, UNROLL = 2;
+  static constexpr int NIN = 5, UNROLL = 1, MINB = 3;
   static constexpr bool OUT = true, ACC = PSI;
   const R* in[NIN];  // xk, sj, q, l, u
   R fill[NIN];
@@ -393,6 +535,8 @@ template <class R, bool PSI> struct ProxLhalfBox {
   R lambda, sigma;
   double c4;        // (double)(σλ/4), σλ/4 evaluated in R
   double cos_2pi3;  // cos((2π)/3) in Float64
+  UDiv<R> by3, by_sigma;
+  UDiv<double> by_sigma64;
   __device__ __forceinline__ R apply(const R (&x)[NIN], long long i, Partial& acc) const {
     const R xi = x[0], si = x[1], qi = x[2], li = x[3], ui = x[4];
     const bool s = sel.has(i);
@@ -403,31 +547,39 @@ template <class R, bool PSI> struct ProxLhalfBox {
       const R xs = xi + si;  // ψ.sol[i]  (:94)
       const R xsq = xs + qi;
       const R axsq = jl_abs(xsq);
-      const double t = lhalf_t(c4, (double)(axsq / R(3)));
-      const R coef = (R(2) * jl_sign(xsq)) / R(3) * axsq;
-      const double val = (double)coef * lhalf_one_plus_cos(t, cos_2pi3);
-      // RNorm(tt) = (tt - q)^2 / 2 / σ + λ sqrt(|tt + xs|)   (:95)
+      const double t = lhalf_t(c4, (double)by3(axsq));
+      const R coef = (jl_sign(xsq) * (R(2) / R(3))) * axsq;  // == ((2 sign) / 3) |xsq| bit for bit
+      // Candidate 4 (`val - xs`) only matters on the real branch t <= 1.  For t > 1 (|xsq| below
+      // 3 (σλ/4)^(2/3)) the objective RNorm has no stationary point besides the kink at tt = -xs: it
+      // decreases towards the kink from both sides, so whatever real(val) is, an endpoint or the kink is
+      // never worse and `findmin` (strict improvement, candidate 4 last) cannot pick it; t = NaN/Inf
+      // make val NaN/Inf, which the reference's range test rejects as well.  The complex-branch value is
+      // therefore never evaluated here ("LhalfBox candidate 4").
+      const bool real_branch = t <= 1.0;
+      const double val = (double)coef * lhalf_G_real(real_branch ? t : 1.0);
+      // RNorm(tt) = (tt - q)^2 / 2 / σ + λ sqrt(|tt + xs|)   (:95); x/2 == x*0.5 exactly.
+      // All four candidates are evaluated straight-line (nearly every warp needs all of them) and
+      // masked with +Inf afterwards.
       const R left = li - si, right = ui - si, mxs = -xs;
-      auto rnorm = [&](R tt) -> double {
-        R dq = tt - qi;
-        return (double)((dq * dq) / R(2) / sigma + lambda * sqrt(jl_abs(tt + xs)));
-      };
-      double c0 = rnorm(left);
-      double c1 = rnorm(right);
+      const R dl = left - qi, dr = right - qi;
       const double inf = __longlong_as_double(0x7ff0000000000000ll);
-      double c2 = ((li <= -xi) && (-xi <= ui)) ? rnorm(mxs) : inf;
+      const double c0 = (double)(by_sigma((dl * dl) * R(0.5)) + lambda * sqrt(jl_abs(left + xs)));
+      const double c1 = (double)(by_sigma((dr * dr) * R(0.5)) + lambda * sqrt(jl_abs(right + xs)));
+      // tt = -xs: tt - q = -(xs + q), and tt + xs is 0 (NaN for a non-finite xs) where sqrt|.| == |.|
+      const double c2v = (double)(by_sigma((xsq * xsq) * R(0.5)) + lambda * jl_abs(mxs + xs));
+      const double c2 = ((li <= -xi) && (-xi <= ui)) ? c2v : inf;
       const double vmx = val - (double)xi;
       const double cand4 = val - (double)xs;  // Float64 (val is Float64)
-      double c3 = inf;
-      if (((double)li <= vmx) && (vmx <= (double)ui)) {
-        double dq = cand4 - (double)qi;
-        c3 = (dq * dq) / 2.0 / (double)sigma + (double)lambda * sqrt(fabs(cand4 + (double)xs));
-      }
+      const double dq4 = cand4 - (double)qi;
+      const double c3v = by_sigma64((dq4 * dq4) * 0.5) + (double)lambda * sqrt(fabs(cand4 + (double)xs));
+      const double c3 = (real_branch && ((double)li <= vmx) && (vmx <= (double)ui)) ? c3v : inf;
+      // findmin over (c0, c1, c2, c3): first minimal index, NaN counts as minimal.  The values are
+      // NaN, +Inf or >= +0, so Base.isless reduces to `<` plus the NaN rule.
       int a = 0;
       double fm = c0;
-      if (jl_isgreater(fm, c1)) { fm = c1; a = 1; }
-      if (jl_isgreater(fm, c2)) { fm = c2; a = 2; }
-      if (jl_isgreater(fm, c3)) { fm = c3; a = 3; }
+      if ((c1 < fm) || ((c1 != c1) && (fm == fm))) { fm = c1; a = 1; }
+      if ((c2 < fm) || ((c2 != c2) && (fm == fm))) { fm = c2; a = 2; }
+      if ((c3 < fm) || ((c3 != c3) && (fm == fm))) { fm = c3; a = 3; }
       o = a == 0 ? left : (a == 1 ? right : (a == 2 ? mxs : (R)cand4));
     }
     if (PSI) BoxPsi<R>{SPX_H_LHALF}.add(acc, s, xi, si, o, li, ui);
@@ -453,7 +605,7 @@ template <class R> struct ValueSep {
 // Box ψ(y) (membership weights; a list with duplicates goes through ValueGather)
 template <class R> struct ValueBox {
   using Real = R;
-  static constexpr int NIN = 5, UNROLL = 2;
+  static constexpr int NIN = 5, UNROLL = 2, MINB = 4;
   static constexpr bool OUT = false, ACC = true;
   const R* in[NIN];  // xk, sj, y, l, u
   R fill[NIN];
