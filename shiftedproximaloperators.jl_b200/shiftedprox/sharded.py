@@ -1,0 +1,128 @@
+"""Host-side logic for one vector (or one batch) sharded over the GPUs of a box, one process per GPU.
+
+Nothing here touches the data path: elementwise / Box / group / batched top-r proxes run on each rank's
+contiguous shard with no collective.  Collectives exist only where the path has a real
+exchange: the scalar ψ(y) (sum + infeasibility flag) and the K partial sums per pass of the ℓ2 trust-region
+root search (ShiftedNormL1B2).  `torch.distributed` is plumbing (NCCL on GPUs, gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+# ------------------------------------------------------------------ partitioning ---
+def shard_bounds(n: int, world: int, rank: int, align: int = 4) -> Tuple[int, int]:
+    """Contiguous shard [lo, hi) of rank `rank`; interior boundaries are multiples of `align` elements so that
+    every shard base stays 16-byte aligned (align=4 covers Float32; 2 suffices for Float64)."""
+    if world <= 0 or not (0 <= rank < world):
+        raise ValueError("bad world/rank")
+    per = -(-n // world)
+    per = -(-per // align) * align
+    lo = min(n, rank * per)
+    hi = min(n, lo + per)
+    return lo, hi
+
+
+def shard_groups(offsets: Sequence[int], world: int) -> List[Tuple[int, int]]:
+    """Split groups (CSR offsets) at group boundaries into `world` contiguous runs balancing the number of
+    elements.  Returns [(g_lo, g_hi)] per rank (possibly empty runs at the end)."""
+    offs = np.asarray(offsets, dtype=np.int64)
+    ng = offs.size - 1
+    n = int(offs[-1])
+    cuts = [0]
+    for r in range(1, world):
+        target = n * r // world
+        g = int(np.searchsorted(offs, target, side="left"))
+        g = max(cuts[-1], min(ng, g))
+        cuts.append(g)
+    cuts.append(ng)
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
+def shard_problems(nprob: int, world: int, rank: int) -> Tuple[int, int]:
+    """Batch of independent problems (top-r): problems [lo, hi) of rank `rank`."""
+    per = -(-nprob // world)
+    lo = min(nprob, rank * per)
+    return lo, min(nprob, lo + per)
+
+
+# ----------------------------------------------------------------------- ψ(y) ---
+def combine_value(kind: str, partial_sum: float, infeasible: float, lam: float, dtype, r: int = 0) -> float:
+    """Turn the all-reduced (Σ, infeasible-flag) into ψ(y): λ·Σ rounded like the reference's value functor
+    (in R), count ≤ r ? 0 : Inf for IndBallL0, Inf if any shard was infeasible."""
+    if infeasible > 0:
+        return math.inf
+    if kind == "indballl0":
+        return 0.0 if partial_sum <= r else math.inf
+    rt = np.float64 if dtype in (torch.float64, np.float64) else np.float32
+    return float(rt(lam) * rt(partial_sum))
+
+
+def allreduce_value(kind: str, local_sum: float, local_infeasible: bool, lam: float, dtype, r: int = 0,
+                    device=None, group=None) -> float:
+    """Scalar all-reduce of ψ(y) partials: SUM for Σ, MAX for the infeasibility flag (so `Inf` survives as a
+    flag, never as Inf - Inf)."""
+    t = torch.tensor([local_sum, 1.0 if local_infeasible else 0.0], dtype=torch.float64, device=device or "cpu")
+    if dist.is_available() and dist.is_initialized():
+        s = t[:1].clone()
+        f = t[1:].clone()
+        dist.all_reduce(s, op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(f, op=dist.ReduceOp.MAX, group=group)
+        t = torch.cat([s, f])
+    return combine_value(kind, float(t[0]), float(t[1]), lam, dtype, r)
+
+
+_KIND = {"l1": 0, "l0": 1, "lhalf": 2, "indballl0": 3}
+
+
+def value_sharded(psi, y_local: torch.Tensor, group=None) -> float:
+    """ψ(y) of a separable / Box ψ whose vectors are this rank's shard (GPU path)."""
+    from . import _lib as L, _BoxBase, _p  # local import: needs the CUDA library
+
+    kind = {L.H_L1: "l1", L.H_L0: "l0", L.H_LHALF: "lhalf", L.H_INDBALLL0: "indballl0"}[psi._H_KIND]
+    out = (C.c_double * 2)()
+    boxed = isinstance(psi, _BoxBase)
+    if boxed:
+        lb, ub = psi._bounds()
+        psi._call("value_partial", C.c_int32(psi._H_KIND), C.c_int64(psi.n), _p(psi.xk), _p(psi.sj), _p(y_local),
+                  C.byref(lb), C.byref(ub), psi._sel.ref(), C.c_int32(1), out)
+    else:
+        psi._call("value_partial", C.c_int32(psi._H_KIND), C.c_int64(psi.n), _p(psi.xk), _p(psi.sj), _p(y_local),
+                  None, None, None, C.c_int32(0), out)
+    return allreduce_value(kind, out[0], out[1] > 0, getattr(psi.h, "lam", 0.0), psi.xk.dtype,
+                           getattr(psi.h, "r", 0), device=psi.xk.device, group=group)
+
+
+# ---------------------------------------------------------------- L1B2 sharded ---
+def prox_l1b2_sharded_(y_local, psi, q_local, sigma, group=None, want_value=False):
+    """ShiftedNormL1B2 prox! on a sharded vector: every pass's K partial sums of squares go through one
+    all-reduce (SUM, Float64); the scalar root search runs replicated inside libshiftedprox."""
+    from . import _lib as L, _p
+
+    dev = psi.xk.device
+
+    def _reduce(_user, vals, count):
+        try:
+            buf = torch.tensor([vals[i] for i in range(count)], dtype=torch.float64, device=dev)
+            dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+            host = buf.cpu()
+            for i in range(count):
+                vals[i] = float(host[i])
+            return 0
+        except Exception:  # pragma: no cover
+            return 1
+
+    cb = L.ALLREDUCE_FN(_reduce)
+    passes = C.c_int32()
+    out = C.c_double() if want_value else None
+    psi._call("prox_l1b2_sharded", C.c_int64(psi.n), _p(y_local), _p(psi.xk), _p(psi.sj), _p(q_local),
+              C.c_double(psi.h.lam), C.c_double(sigma), C.c_double(psi.Delta), C.c_double(psi.chi.lam), cb, None,
+              C.byref(passes), C.byref(out) if want_value else None)
+    psi.last_passes = passes.value
+    return (y_local, out.value) if want_value else y_local

@@ -1,0 +1,70 @@
+"""GPU checks of the sharded entry points on ONE device (two shards processed one after the other; the
+collective is emulated by adding the partials).  The real 2..8-rank NCCL path is exercised by
+tools/check_sharded_nccl.py under torchrun (gpurun --gpus N)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from gpu_util import DEV, N, T, bounds, inputs, orc, sp
+from shiftedprox import _lib as L
+from shiftedprox import sharded
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_value_partials_add_up(dt):
+    n = 100_003
+    xk, sj, _ = inputs(n, dt)
+    l, u = bounds(n, dt)
+    w = (l + (u - l) * orc.uniform(n, 11, dt)).astype(dt)
+    y = (w - sj).astype(dt)
+    rtol = 1e-13 if dt == np.float64 else 2e-6
+    for kind, h in (("l1", sp.NormL1(1.7)), ("l0", sp.NormL0(1.7)), ("lhalf", sp.RootNormLhalf(1.7))):
+        tot, bad = 0.0, False
+        for r in range(2):
+            lo, hi = sharded.shard_bounds(n, 2, r)
+            psi = sp.shifted(sp.shifted(h, T(xk[lo:hi]), T(l[lo:hi]), T(u[lo:hi])), T(sj[lo:hi]))
+            out = (C.c_double * 2)()
+            lb, ub = psi._bounds()
+            yl = T(y[lo:hi])
+            psi._call("value_partial", C.c_int32(psi._H_KIND), C.c_int64(psi.n), C.c_void_p(psi.xk.data_ptr()),
+                      C.c_void_p(psi.sj.data_ptr()), C.c_void_p(yl.data_ptr()), C.byref(lb), C.byref(ub),
+                      psi._sel.ref(), C.c_int32(1), out)
+            tot += out[0]
+            bad = bad or out[1] > 0
+        val = sharded.combine_value(kind, tot, 1.0 if bad else 0.0, 1.7, torch.float64 if dt == np.float64 else torch.float32)
+        assert val == pytest.approx(orc.value_box(kind, xk, sj, y, l, u, 1.7), rel=rtol)
+        # un-initialised process group: value_sharded degenerates to the local value
+        psi = sp.shifted(sp.shifted(h, T(xk), T(l), T(u)), T(sj))
+        assert sharded.value_sharded(psi, T(y)) == pytest.approx(psi(T(y)), rel=rtol)
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_l1b2_sharded_callback_matches_single_device(dt):
+    n = 200_001
+    xk, sj, q = inputs(n, dt)
+    y0 = orc.prox_l1b2(xk, sj, q, 1.0, 0.1, 1e30)
+    delta = 0.5 * float(np.linalg.norm((y0 + sj).astype(np.float64)))
+    psi = sp.shifted(sp.shifted(sp.NormL1(1.0), T(xk), delta, sp.NormL2(1.0)), T(sj))
+    y1 = torch.empty(n, dtype=T(q).dtype, device=DEV)
+    sp.prox_(y1, psi, T(q), 0.1)
+    calls = []
+
+    def ident(_u, vals, count):  # world size 1: the all-reduce is the identity
+        calls.append(count)
+        return 0
+
+    cb = L.ALLREDUCE_FN(ident)
+    y2 = torch.empty_like(y1)
+    passes = C.c_int32()
+    val = C.c_double()
+    tq = T(q)
+    psi._call("prox_l1b2_sharded", C.c_int64(n), C.c_void_p(y2.data_ptr()), C.c_void_p(psi.xk.data_ptr()),
+              C.c_void_p(psi.sj.data_ptr()), C.c_void_p(tq.data_ptr()), C.c_double(1.0), C.c_double(0.1),
+              C.c_double(delta), C.c_double(1.0), cb, None, C.byref(passes), C.byref(val))
+    assert np.array_equal(N(y1), N(y2))
+    assert len(calls) == passes.value  # one all-reduce per norm pass + one for the ψ sums
+    assert val.value == pytest.approx(psi(y2), rel=1e-12 if dt == np.float64 else 1e-5)

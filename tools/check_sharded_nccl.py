@@ -1,0 +1,82 @@
+#!/usr/bin/env python
+"""Multi-rank (NCCL) check of the sharded paths; run under torchrun on N GPUs of one box:
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port 29533 tools/check_sharded_nccl.py
+
+Every rank holds a contiguous shard of the same synthetic vectors.  Checks that (1) the all-reduced ψ(y)
+equals the single-device value, (2) the sharded ShiftedNormL1B2 prox! (K partial sums all-reduced per pass,
+root search replicated) reproduces the single-device result bit for bit on every shard."""
+import ctypes as C
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "shiftedproximaloperators.jl_b200"))
+import shiftedprox as sp  # noqa: E402
+from shiftedprox import _lib as L, sharded  # noqa: E402
+
+SEED = 20261018
+
+
+def uniform(dev, n, stream, scale=1.0, shift=0.0, i0=0, dtype=torch.float64):
+    t = torch.empty(n, dtype=dtype, device=dev)
+    suf, ct = ("f64", C.c_double) if dtype == torch.float64 else ("f32", C.c_float)
+    L.call(f"spx_fill_uniform_{suf}", sp.context(dev), C.c_void_p(t.data_ptr()), C.c_int64(n), C.c_int64(i0),
+           C.c_uint64(SEED), C.c_uint64(stream), ct(scale), ct(shift))
+    return t
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    n = 1 << 24
+    ok = True
+    for dtype in (torch.float64, torch.float32):
+        full = [uniform(dev, n, 0, 4.0, -2.0, dtype=dtype), uniform(dev, n, 1, 1.0, -0.5, dtype=dtype),
+                uniform(dev, n, 2, 4.0, -2.0, dtype=dtype)]
+        lo, hi = sharded.shard_bounds(n, world, rank)
+        xk, sj, q = (t[lo:hi].clone() for t in full)
+        # (1) ψ(y) all-reduce
+        psi_f = sp.shifted(sp.shifted(sp.NormL1(1.3), full[0]), full[1])
+        psi_s = sp.shifted(sp.shifted(sp.NormL1(1.3), xk), sj)
+        yf = torch.empty_like(full[2])
+        sp.prox_(yf, psi_f, full[2], 0.1)
+        v_full = psi_f(yf)
+        v_sh = sharded.value_sharded(psi_s, yf[lo:hi].clone())
+        rel = abs(v_full - v_sh) / abs(v_full)
+        ok &= rel < (1e-13 if dtype == torch.float64 else 1e-6)
+        # (2) L1B2 sharded
+        b0 = sp.shifted(sp.shifted(sp.NormL1(1.0), full[0], 1e30, sp.NormL2(1.0)), full[1])
+        sp.prox_(yf, b0, full[2], 0.1)
+        delta = 0.5 * float(torch.linalg.vector_norm((yf + full[1]).double()))
+        bf = sp.shifted(sp.shifted(sp.NormL1(1.0), full[0], delta, sp.NormL2(1.0)), full[1])
+        _, vf = sp.prox_(yf, bf, full[2], 0.1, want_value=True)
+        bs = sp.shifted(sp.shifted(sp.NormL1(1.0), xk, delta, sp.NormL2(1.0)), sj)
+        ys = torch.empty_like(q)
+        _, vs = sharded.prox_l1b2_sharded_(ys, bs, q, 0.1, want_value=True)
+        # the K sums differ from the single-device fold only in summation order: η may move by an ulp
+        tol = (64 if dtype == torch.float64 else 16) * torch.finfo(dtype).eps
+        diff = float((ys - yf[lo:hi]).abs().max())
+        ok &= diff <= tol * 4.0
+        ok &= abs(vs - vf) <= 1e-9 * abs(vf) if dtype == torch.float64 else abs(vs - vf) <= 1e-4 * abs(vf)
+        if rank == 0:
+            print(f"[{dtype}] world={world} psi rel err {rel:.2e}; l1b2 passes {bs.last_passes} (single {bf.last_passes}), "
+                  f"max |y_sharded - y_single| {diff:.3e}, psi {vs:.12g} vs {vf:.12g}", flush=True)
+    flag = torch.tensor([1.0 if ok else 0.0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print("SHARDED CHECK", "OK" if flag.item() == 1.0 else "FAILED", flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if flag.item() == 1.0 else 1)
+
+
+if __name__ == "__main__":
+    main()
