@@ -124,6 +124,11 @@ int32_t spx_fill_uniform_f64(spx_ctx* ctx, double* out, int64_t n, int64_t i0, u
                              uint64_t stream, double scale, double shift);
 int32_t spx_fill_uniform_f32(spx_ctx* ctx, float* out, int64_t n, int64_t i0, uint64_t seed,
                              uint64_t stream, float scale, float shift);
+/* Device self-test of the FP64 building blocks the kernels use instead of library calls: on n
+ * pseudo-random operands, counts results that differ from the IEEE operation in any bit.
+ * mismatches_out[0]: branch-free sqrt vs sqrt();  [1]: reciprocal + two Markstein corrections vs a/d;
+ * [2]: uniform-divisor quotient vs a/s.  All three must be 0. */
+int32_t spx_selftest_math(spx_ctx* ctx, int64_t n, uint64_t seed, int64_t* mismatches_out);
 /* order-independent 64-bit checksum of a buffer's bits (Σ mix(word_i, i) mod 2^64),
  * identical to oracle.checksum(); used for full-size parity */
 int32_t spx_checksum(spx_ctx* ctx, const void* p, int64_t nwords64, uint64_t* out);

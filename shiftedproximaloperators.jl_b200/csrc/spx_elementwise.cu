@@ -469,3 +469,58 @@ using namespace spx;
 
 SPX_DEFINE_EW(f64, double)
 SPX_DEFINE_EW(f32, float)
+
+// ------------------------------------------------------------------ self-test --
+namespace spx {
+__device__ __forceinline__ unsigned long long st_mix(unsigned long long x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+// random double with a uniformly random mantissa and an exponent in [-emax, emax]
+__device__ __forceinline__ double st_rand(unsigned long long h, int emax) {
+  const unsigned long long mant = h & 0x000fffffffffffffull;
+  const int e = (int)((h >> 52) % (unsigned)(2 * emax + 1)) - emax;
+  const double m = __longlong_as_double((long long)(mant | 0x3ff0000000000000ull));
+  return ldexp(m, e) * ((h >> 63) ? -1.0 : 1.0);
+}
+__global__ void __launch_bounds__(256) selftest_kernel(long long n, unsigned long long seed,
+                                                       unsigned long long* __restrict__ bad) {
+  unsigned long long b0 = 0, b1 = 0, b2 = 0;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+    const unsigned long long h1 = st_mix(seed + 3 * (unsigned long long)i);
+    const unsigned long long h2 = st_mix(seed + 3 * (unsigned long long)i + 1);
+    const unsigned long long h3 = st_mix(seed + 3 * (unsigned long long)i + 2);
+    const double x = fabs(st_rand(h1, 60)), a = st_rand(h2, 40), d = st_rand(h3, 40);
+    if (__double_as_longlong(sqrt_fast(x)) != __double_as_longlong(sqrt(x))) ++b0;
+    const Quot3<double> q = quot3(a, d, 1.0 + fabs(x), true);
+    const Quot3<double> r = quot3_ref<double>(a, d, 1.0 + fabs(x));
+    if (__double_as_longlong(q.a) != __double_as_longlong(r.a) || __double_as_longlong(q.b) != __double_as_longlong(r.b) ||
+        __double_as_longlong(q.c) != __double_as_longlong(r.c))
+      ++b1;
+    const double s = 0.05 + fabs(ldexp(d, -ilogb(d)));  // divisor of order 1
+    if (__double_as_longlong(div_uniform(a, s, 1.0 / s)) != __double_as_longlong(a / s)) ++b2;
+  }
+  if (b0) atomicAdd(bad + 0, b0);
+  if (b1) atomicAdd(bad + 1, b1);
+  if (b2) atomicAdd(bad + 2, b2);
+}
+}  // namespace spx
+
+extern "C" int32_t spx_selftest_math(spx_ctx* ctx, int64_t n, uint64_t seed, int64_t* mismatches_out) {
+  SPX_REQUIRE(ctx && mismatches_out, "null argument");
+  SPX_REQUIRE(n >= 0, "n < 0");
+  DeviceGuard g(ctx->device);
+  int32_t st = ensure_scratch(ctx, 4096);
+  if (st != SPX_OK) return st;
+  SPX_CUDA(cudaMemsetAsync(ctx->d_scratch, 0, 24, ctx->stream));
+  if (n > 0) {
+    selftest_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(n, seed, (unsigned long long*)ctx->d_scratch);
+    ctx->launches++;
+    SPX_CUDA(cudaGetLastError());
+  }
+  SPX_CUDA(cudaMemcpyAsync(mismatches_out, ctx->d_scratch, 24, cudaMemcpyDeviceToHost, ctx->stream));
+  SPX_CUDA(cudaStreamSynchronize(ctx->stream));
+  return SPX_OK;
+}

@@ -123,14 +123,42 @@ __device__ __forceinline__ double div_uniform(double a, double s, double y) {
 // t = c4 * w^(-3/2) to ~1.5 ulp (the reference's `^` is < 1 ulp, its product adds
 // half an ulp): s = sqrt(w) from rsqrt + one FMA correction, u = w*s, then the
 // quotient c4/u by one Markstein step on the reciprocal estimate r^3.
+// sqrt(x) and 1/(2 sqrt(x)) for a normal positive x, branch-free: MUFU.RSQ64H seed
+// (rsqrt.approx.ftz.f64, ~2^-22), two Goldschmidt rounds (g -> sqrt x, h -> 1/(2 sqrt x), each
+// round squares the error), one final residual correction, which makes g the correctly
+// rounded square root (same construction as the library's, minus its special-case branches).
+__device__ __forceinline__ void sqrt_pair(double x, double& g, double& h) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  g = x * y;
+  h = 0.5 * y;
+  double r = __fma_rn(-g, h, 0.5);
+  g = __fma_rn(g, r, g);
+  h = __fma_rn(h, r, h);
+  r = __fma_rn(-g, h, 0.5);
+  g = __fma_rn(g, r, g);
+  h = __fma_rn(h, r, h);
+  const double d = __fma_rn(-g, g, x);
+  g = __fma_rn(d, h, g);
+}
+// IEEE sqrt for the candidate objectives; zero / subnormal / huge / NaN take the library
+static __device__ __noinline__ double sqrt_slow(double x) { return sqrt(x); }
+__device__ __forceinline__ double sqrt_fast(double x) {
+  if (!(x > 1e-290 && x < 1e290)) return sqrt_slow(x);
+  double g, h;
+  sqrt_pair(x, g, h);
+  return g;
+}
+__device__ __forceinline__ float sqrt_fast(float x) { return sqrtf(x); }
+
+static __device__ __noinline__ double lhalf_t_slow(double c4, double w) { return c4 * pow(w, -1.5); }
 __device__ __forceinline__ double lhalf_t(double c4, double w) {
-  if (!(w > 1e-200 && w < 1e200)) return c4 * pow(w, -1.5);  // 0, Inf, NaN, denormal: library path
-  const double r = rsqrt(w);
-  double s = w * r;
-  const double e = __fma_rn(-s, s, w);
-  s = __fma_rn(e, 0.5 * r, s);
-  const double u = w * s;
-  const double y = (r * r) * r;
+  if (!(w > 1e-200 && w < 1e200)) return lhalf_t_slow(c4, w);  // 0, Inf, NaN, denormal: library path
+  double s, h;
+  sqrt_pair(w, s, h);
+  const double u = w * s;         // w^(3/2), <= 1 ulp
+  const double r = h + h;         // ~ w^(-1/2)
+  const double y = (r * r) * r;   // reciprocal estimate of u
   const double q0 = c4 * y;
   const double e2 = __fma_rn(-u, q0, c4);
   return __fma_rn(e2, y, q0);
@@ -163,8 +191,17 @@ __device__ __forceinline__ double cubic_newton(double x, double rhs) {
 // Measured against 200-bit mpmath: <= 2 ulp for t <= 0.9999, i.e. at the level of
 // the reference's own acos/cos chain (tests/test_gpu_parity.py).
 __device__ __forceinline__ double lhalf_G_real(double t) {  // 0 <= t <= 1
-  const float tf = (float)t;
-  double d = (double)__cosf(1.0471975511965976f - acosf(tf) * 0.33333334f);
+  // start value: d = cos(π/3 - acos(t)/3) is analytic in s = sqrt(1 - t) on [0, 1]; a degree-5
+  // Float32 fit (|err| < 3e-7) is all two Newton steps need (error after two steps ~ K³ e⁴)
+  float sf;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sf) : "f"((float)(1.0 - t)));
+  float pf = 0.0011198767460882664f;
+  pf = fmaf(pf, sf, -0.005838877987116575f);
+  pf = fmaf(pf, sf, 0.01784452795982361f);
+  pf = fmaf(pf, sf, -0.05533028766512871f);
+  pf = fmaf(pf, sf, 0.40823012590408325f);
+  pf = fmaf(pf, sf, 0.5000002384185791f);
+  double d = (double)pf;
   d = cubic_newton(d, -t);
   d = cubic_newton(d, -t);
   if (t > 0.98) {
@@ -211,7 +248,13 @@ template <> struct UDiv<float> {
 // shiftedRootNormLhalf.jl:41-63
 template <class R, bool PSI> struct ProxLhalf {
   using Real = R;
-  static constexpr int NIN = 3, UNROLL = 1;
+#ifndef SPX_LH_UNROLL
+#define SPX_LH_UNROLL 1
+#endif
+#ifndef SPX_LH_MINB
+#define SPX_LH_MINB 4
+#endif
+  static constexpr int NIN = 3, UNROLL = SPX_LH_UNROLL, MINB = SPX_LH_MINB;
   static constexpr bool OUT = true, ACC = PSI;
   const R* in[NIN];  // xk, sj, q
   R fill[NIN];
@@ -526,7 +569,13 @@ __device__ __forceinline__ bool jl_isgreater(double x, double y) {
 // shiftedRootNormLhalfBox.jl:86-120
 template <class R, bool PSI> struct ProxLhalfBox {
   using Real = R;
-  static constexpr int NIN = 5, UNROLL = 1, MINB = 3;
+#ifndef SPX_LHB_UNROLL
+#define SPX_LHB_UNROLL 1
+#endif
+#ifndef SPX_LHB_MINB
+#define SPX_LHB_MINB 4
+#endif
+  static constexpr int NIN = 5, UNROLL = SPX_LHB_UNROLL, MINB = SPX_LHB_MINB;
   static constexpr bool OUT = true, ACC = PSI;
   const R* in[NIN];  // xk, sj, q, l, u
   R fill[NIN];
@@ -563,15 +612,15 @@ template <class R, bool PSI> struct ProxLhalfBox {
       const R left = li - si, right = ui - si, mxs = -xs;
       const R dl = left - qi, dr = right - qi;
       const double inf = __longlong_as_double(0x7ff0000000000000ll);
-      const double c0 = (double)(by_sigma((dl * dl) * R(0.5)) + lambda * sqrt(jl_abs(left + xs)));
-      const double c1 = (double)(by_sigma((dr * dr) * R(0.5)) + lambda * sqrt(jl_abs(right + xs)));
+      const double c0 = (double)(by_sigma((dl * dl) * R(0.5)) + lambda * sqrt_fast(jl_abs(left + xs)));
+      const double c1 = (double)(by_sigma((dr * dr) * R(0.5)) + lambda * sqrt_fast(jl_abs(right + xs)));
       // tt = -xs: tt - q = -(xs + q), and tt + xs is 0 (NaN for a non-finite xs) where sqrt|.| == |.|
       const double c2v = (double)(by_sigma((xsq * xsq) * R(0.5)) + lambda * jl_abs(mxs + xs));
       const double c2 = ((li <= -xi) && (-xi <= ui)) ? c2v : inf;
       const double vmx = val - (double)xi;
       const double cand4 = val - (double)xs;  // Float64 (val is Float64)
       const double dq4 = cand4 - (double)qi;
-      const double c3v = by_sigma64((dq4 * dq4) * 0.5) + (double)lambda * sqrt(fabs(cand4 + (double)xs));
+      const double c3v = by_sigma64((dq4 * dq4) * 0.5) + (double)lambda * sqrt_fast(fabs(cand4 + (double)xs));
       const double c3 = (real_branch && ((double)li <= vmx) && (vmx <= (double)ui)) ? c3v : inf;
       // findmin over (c0, c1, c2, c3): first minimal index, NaN counts as minimal.  The values are
       // NaN, +Inf or >= +0, so Base.isless reduces to `<` plus the NaN rule.

@@ -11,7 +11,8 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 PKG_DIR = os.path.dirname(_HERE)
-LIB_PATH = os.path.join(PKG_DIR, "libshiftedprox.so")
+# SPX_LIB: developer override used by tools/ to A/B kernel build variants
+LIB_PATH = os.environ.get("SPX_LIB") or os.path.join(PKG_DIR, "libshiftedprox.so")
 
 SPX_OK = 0
 SPX_E_INVALID = -1
