@@ -80,10 +80,10 @@ static int32_t prox_lhalf(spx_ctx* ctx, int64_t n, R* y, const R* xk, const R* s
   return run_sep<ProxLhalf, R>(ctx, n, SPX_H_LHALF, lam, psi_out, [&](auto& op) {
     set3(op, xk, sj, q);
     op.y = y;
-    op.nulam = nulam;
     op.p = lhalf_threshold(nulam);
     op.c4 = (double)(nulam / R(4));
-    op.by3.set(R(3));
+    op.c4f = (float)op.c4;
+    op.fast = lhalf_f32_range_host(op.c4);
   });
 }
 
@@ -158,12 +158,17 @@ static int32_t launch_box_t(spx_ctx* ctx, cudaStream_t stream, int opc, bool inv
     } else if (opc == BOX_LHALF) {
       ProxLhalfBox<R, PSI> op;
       set_box(op, xk, sj, qg, d, lvec, lval, uvec, uval);
-      op.y = y; op.sel = sel; op.lambda = lambda; op.sigma = sigma;
-      op.c4 = (double)(sigma * lambda / R(4));
-      op.cos_2pi3 = std::cos(kTwoPiOver3);
-      op.by3.set(R(3));
-      op.by_sigma.set(sigma);
-      op.by_sigma64.set((double)sigma);
+      op.y = y; op.sel = sel;
+      op.k.lambda = lambda;
+      op.k.c4 = (double)(sigma * lambda / R(4));
+      op.k.by3.set(R(3));
+      op.k.by_sigma.set(sigma);
+      op.k.by_sigma64.set((double)sigma);
+      op.kf = (float)(0.5 / (double)sigma);
+      op.lamf = (float)lambda;
+      op.c4f = (float)op.k.c4;
+      op.fast = lhalf_f32_range_host(op.k.c4) && lhalf_f32_range_host((double)sigma) &&
+                lhalf_f32_range_host((double)lambda);
       return ew_launch(ctx, stream, op, n, base, partials, nb);
     }
   } else {

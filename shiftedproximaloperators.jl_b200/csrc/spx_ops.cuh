@@ -6,95 +6,6 @@
 
 namespace spx {
 
-// ψ(y) accumulators (fused into the prox pass or run alone) --------------------
-// kinds: SPX_H_L1 Σ|v|, SPX_H_L0 / SPX_H_INDBALLL0 Σ(v≠0), SPX_H_LHALF Σ√|v|
-template <class R> __device__ __forceinline__ double h_term(int kind, R v) {
-  if (kind == SPX_H_L1) return (double)jl_abs(v);
-  if (kind == SPX_H_LHALF) return (double)sqrt(jl_abs(v));  // sqrt in R (rootNormLhalf.jl:28)
-  return (v != R(0)) ? 1.0 : 0.0;
-}
-// bad-flag encoding: max-reduced; "first failing index" is stored as 2^62 - i
-__device__ __forceinline__ void flag_index(Partial& acc, long long i) {
-  long long code = (1ll << 62) - i;
-  acc.bad = code > acc.bad ? code : acc.bad;
-}
-__device__ __forceinline__ void flag_set(Partial& acc) { acc.bad = acc.bad > 1 ? acc.bad : 1; }
-
-// ------------------------------------------------------------ ShiftedNormL1 --
-// shiftedNormL1.jl:40-54
-template <class R, bool PSI> struct ProxL1 {
-  using Real = R;
-  static constexpr int NIN = 3, UNROLL = 2;
-  static constexpr bool OUT = true, ACC = PSI;
-  const R* in[NIN];  // xk, sj, q
-  R fill[NIN];
-  R* y;
-  R a;  // λσ
-  __device__ __forceinline__ R apply(const R (&x)[NIN], long long, Partial& acc) const {
-    R t = (-x[0]) - x[1];
-    R o = jl_min(jl_max(t, x[2] - a), x[2] + a);
-    if (PSI) acc.s += h_term(SPX_H_L1, (x[0] + x[1]) + o);
-    return o;
-  }
-};
-// shiftedNormL1.jl:60-75
-template <class R, bool PSI> struct IproxL1 {
-  using Real = R;
-  static constexpr int NIN = 4, UNROLL = 2;
-  static constexpr bool OUT = true, ACC = true;
-  const R* in[NIN];  // xk, sj, g, d
-  R fill[NIN];
-  R* y;
-  R lambda;
-  __device__ __forceinline__ R apply(const R (&x)[NIN], long long i, Partial& acc) const {
-    R t = (-x[0]) - x[1];
-    R d = x[3];
-    if (!(d > R(0))) flag_index(acc, i);  // @assert d[i] > 0  (:70)
-    R c = (-x[2]) / d;
-    R w = lambda / d;
-    R o = jl_min(jl_max(t, c - w), c + w);
-    if (PSI) acc.s += h_term(SPX_H_L1, (x[0] + x[1]) + o);
-    return o;
-  }
-};
-
-// ------------------------------------------------------------ ShiftedNormL0 --
-// shiftedNormL0.jl:38-55
-template <class R, bool PSI> struct ProxL0 {
-  using Real = R;
-  static constexpr int NIN = 3, UNROLL = 2;
-  static constexpr bool OUT = true, ACC = PSI;
-  const R* in[NIN];  // xk, sj, q
-  R fill[NIN];
-  R* y;
-  R c;  // sqrt(2λσ)
-  __device__ __forceinline__ R apply(const R (&x)[NIN], long long, Partial& acc) const {
-    R xps = x[0] + x[1];
-    R o = (jl_abs(xps + x[2]) <= c) ? -xps : x[2];
-    if (PSI) acc.s += h_term(SPX_H_L0, xps + o);
-    return o;
-  }
-};
-// shiftedNormL0.jl:61-80
-template <class R, bool PSI> struct IproxL0 {
-  using Real = R;
-  static constexpr int NIN = 4, UNROLL = 2;
-  static constexpr bool OUT = true, ACC = true;
-  const R* in[NIN];  // xk, sj, g, d
-  R fill[NIN];
-  R* y;
-  R lambda;
-  __device__ __forceinline__ R apply(const R (&x)[NIN], long long i, Partial& acc) const {
-    R d = x[3];
-    if (!(d > R(0))) flag_index(acc, i);  // @assert d[i] > 0  (:70)
-    R ci = sqrt(R(2) * lambda * d);
-    R xps = x[0] + x[1];
-    R o = (jl_abs(d * xps - x[2]) <= ci) ? -xps : (-x[2]) / d;
-    if (PSI) acc.s += h_term(SPX_H_L0, xps + o);
-    return o;
-  }
-};
-
 // ---------------------------------------------------- RootNormLhalf closed form
 // `2*sign(z)/3*|z|*(1+cos(2π/3 - 2ϕ(z)/3))`, ϕ(z) = acos(νλ/4 (|z|/3)^(-3/2))
 // shiftedRootNormLhalf.jl:48,57.  The power, acos and cos run in Float64 for
@@ -141,13 +52,15 @@ __device__ __forceinline__ void sqrt_pair(double x, double& g, double& h) {
   const double d = __fma_rn(-g, g, x);
   g = __fma_rn(d, h, g);
 }
-// IEEE sqrt for the candidate objectives; zero / subnormal / huge / NaN take the library
+// IEEE sqrt: straight-line for normal operands and for ±0 (a thresholded entry of the ψ(y) sum);
+// subnormal / huge / negative / NaN take the library
 static __device__ __noinline__ double sqrt_slow(double x) { return sqrt(x); }
 __device__ __forceinline__ double sqrt_fast(double x) {
-  if (!(x > 1e-290 && x < 1e290)) return sqrt_slow(x);
+  const bool ok = x > 1e-290 && x < 1e290;
+  if (!ok && x != 0.0) return sqrt_slow(x);
   double g, h;
-  sqrt_pair(x, g, h);
-  return g;
+  sqrt_pair(ok ? x : 1.0, g, h);
+  return ok ? g : x;
 }
 __device__ __forceinline__ float sqrt_fast(float x) { return sqrtf(x); }
 
@@ -245,11 +158,180 @@ template <> struct UDiv<float> {
   __device__ __forceinline__ float operator()(float a) const { return a / s; }
 };
 
+// ---- RootNormLhalf through its stationarity equation ------------------------------------------
+// With t = (σλ/4)(|z|/3)^(-3/2) <= 1 the reference's value
+//     (2/3)|z| (1 + cos(2π/3 - (2/3) acos t))                 (shiftedRootNormLhalf.jl:48,57)
+// is s² where s is the largest root of  s³ - |z| s + σλ/2 = 0  (s = 2 sqrt(|z|/3) d turns this into
+// 4d³ - 3d + t = 0, d = cos(π/3 - acos(t)/3)): it is the stationarity condition of
+// y -> (y - |z|)²/(2σ) + λ sqrt(y) written in sqrt(y).  The kernels solve that cubic directly:
+//   * start value in Float32 from the closed form (FP32 pipe + 3 SFU ops): rel. error ~1e-6;
+//   * Newton in Float64 with fused residuals u = fma(s,s,-|z|), f = fma(s,u,a) (each a single
+//     rounding of a quantity that vanishes at the root) and the Float32 reciprocal slope
+//     (a stale slope only adds a term slope_err * step, far below 1 ulp after two steps).
+// 7 FP64 operations instead of ~45 for pow + acos + cos.  Against 200-bit mpmath
+// (tools/proto/check_lhalf_newton.py): <= 2 ulp for t <= 0.99 (<= 4 up to 0.998), where the
+// reference's own pow/acos/cos chain is 3-40 ulp off; t in (0.998, 1.002) and operands outside the Float32-friendly
+// range go through the operation-by-operation form (lhalf_mag_ref) in a non-inlined call.
+struct LhalfStart {
+  float t32;  // t in Float32 (rel. error ~5e-7)
+  float s0;   // start value of s
+  float inv;  // 1 / (3 s0² - |z|)
+};
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ LhalfStart lhalf_start(float zf, float c4f) {
+  LhalfStart st;
+  const float w = zf * 0.33333334f;
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(w));
+  st.t32 = (c4f * r) * (r * r);
+  // d = cos(π/3 - acos(t)/3) is analytic in sqrt(1 - t) on [0, 1]: degree-5 fit, |err| < 3e-7
+  const float sf = sqrt_approx(fmaxf(1.0f - st.t32, 0.0f));
+  float pf = 0.0011198767460882664f;
+  pf = fmaf(pf, sf, -0.005838877987116575f);
+  pf = fmaf(pf, sf, 0.01784452795982361f);
+  pf = fmaf(pf, sf, -0.05533028766512871f);
+  pf = fmaf(pf, sf, 0.40823012590408325f);
+  pf = fmaf(pf, sf, 0.5000002384185791f);
+  st.s0 = (2.0f * (w * r)) * pf;  // 2 sqrt(w) d
+  const float slope = fmaf(3.0f * st.s0, st.s0, -zf);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(st.inv) : "f"(slope));
+  return st;
+}
+// s² for the largest root s; a = σλ/2.  NEAR1: t may approach 1 (Box form), where the slope
+// az(4d² - 1) shrinks: one more step and a compensated last residual (s² = p + e, p - az by Fast2Sum).
+template <bool NEAR1> __device__ __forceinline__ double lhalf_newton(double az, double a, const LhalfStart& st) {
+  const double inv = (double)st.inv;
+  double s = (double)st.s0;
+  double u = __fma_rn(s, s, -az);
+  double f = __fma_rn(s, u, a);
+  s = __fma_rn(-f, inv, s);
+  if (NEAR1 && st.t32 > 0.9f) {
+    u = __fma_rn(s, s, -az);
+    f = __fma_rn(s, u, a);
+    s = __fma_rn(-f, inv, s);
+    const double p = s * s;
+    const double e = __fma_rn(s, s, -p);
+    u = p - az;
+    const double ue = p - (u + az);
+    f = __fma_rn(s, u, a);
+    f = __fma_rn(s, e + ue, f);
+    s = __fma_rn(-f, inv, s);
+  } else {
+    u = __fma_rn(s, s, -az);
+    f = __fma_rn(s, u, a);
+    s = __fma_rn(-f, inv, s);
+  }
+  return s * s;
+}
+// |z| and σλ/4 for which every Float32 intermediate above stays a normal number
+__device__ __forceinline__ bool lhalf_f32_range(float zf) { return zf > 1e-9f && zf < 1e9f; }
+inline bool lhalf_f32_range_host(double v) { return std::isfinite(v) && v > 1e-9 && v < 1e9; }
+
+// operation-by-operation form of the magnitude (|z| > 0): ((2/3)|z|) G(t), t = c4 (|z|/3)^(-3/2)
+template <class R> static __device__ __noinline__ double lhalf_mag_ref(R az, double c4) {
+  const double t = lhalf_t(c4, (double)(az / R(3)));
+  const R coef = (R(2) / R(3)) * az;
+  return (double)coef * lhalf_G_real(t);
+}
+
+// ψ(y) accumulators (fused into the prox pass or run alone) --------------------
+// kinds: SPX_H_L1 Σ|v|, SPX_H_L0 / SPX_H_INDBALLL0 Σ(v≠0), SPX_H_LHALF Σ√|v|
+template <class R> __device__ __forceinline__ double h_term(int kind, R v) {
+  if (kind == SPX_H_L1) return (double)jl_abs(v);
+  if (kind == SPX_H_LHALF) return (double)sqrt_fast(jl_abs(v));  // IEEE sqrt in R (rootNormLhalf.jl:28)
+  return (v != R(0)) ? 1.0 : 0.0;
+}
+// bad-flag encoding: max-reduced; "first failing index" is stored as 2^62 - i
+__device__ __forceinline__ void flag_index(Partial& acc, long long i) {
+  long long code = (1ll << 62) - i;
+  acc.bad = code > acc.bad ? code : acc.bad;
+}
+__device__ __forceinline__ void flag_set(Partial& acc) { acc.bad = acc.bad > 1 ? acc.bad : 1; }
+
+// ------------------------------------------------------------ ShiftedNormL1 --
+// shiftedNormL1.jl:40-54
+template <class R, bool PSI> struct ProxL1 {
+  using Real = R;
+  static constexpr int NIN = 3, UNROLL = 2;
+  static constexpr bool OUT = true, ACC = PSI;
+  const R* in[NIN];  // xk, sj, q
+  R fill[NIN];
+  R* y;
+  R a;  // λσ
+  __device__ __forceinline__ R apply(const R (&x)[NIN], long long, Partial& acc) const {
+    R t = (-x[0]) - x[1];
+    R o = jl_min(jl_max(t, x[2] - a), x[2] + a);
+    if (PSI) acc.s += h_term(SPX_H_L1, (x[0] + x[1]) + o);
+    return o;
+  }
+};
+// shiftedNormL1.jl:60-75
+template <class R, bool PSI> struct IproxL1 {
+  using Real = R;
+  static constexpr int NIN = 4, UNROLL = 2;
+  static constexpr bool OUT = true, ACC = true;
+  const R* in[NIN];  // xk, sj, g, d
+  R fill[NIN];
+  R* y;
+  R lambda;
+  __device__ __forceinline__ R apply(const R (&x)[NIN], long long i, Partial& acc) const {
+    R t = (-x[0]) - x[1];
+    R d = x[3];
+    if (!(d > R(0))) flag_index(acc, i);  // @assert d[i] > 0  (:70)
+    R c = (-x[2]) / d;
+    R w = lambda / d;
+    R o = jl_min(jl_max(t, c - w), c + w);
+    if (PSI) acc.s += h_term(SPX_H_L1, (x[0] + x[1]) + o);
+    return o;
+  }
+};
+
+// ------------------------------------------------------------ ShiftedNormL0 --
+// shiftedNormL0.jl:38-55
+template <class R, bool PSI> struct ProxL0 {
+  using Real = R;
+  static constexpr int NIN = 3, UNROLL = 2;
+  static constexpr bool OUT = true, ACC = PSI;
+  const R* in[NIN];  // xk, sj, q
+  R fill[NIN];
+  R* y;
+  R c;  // sqrt(2λσ)
+  __device__ __forceinline__ R apply(const R (&x)[NIN], long long, Partial& acc) const {
+    R xps = x[0] + x[1];
+    R o = (jl_abs(xps + x[2]) <= c) ? -xps : x[2];
+    if (PSI) acc.s += h_term(SPX_H_L0, xps + o);
+    return o;
+  }
+};
+// shiftedNormL0.jl:61-80
+template <class R, bool PSI> struct IproxL0 {
+  using Real = R;
+  static constexpr int NIN = 4, UNROLL = 2;
+  static constexpr bool OUT = true, ACC = true;
+  const R* in[NIN];  // xk, sj, g, d
+  R fill[NIN];
+  R* y;
+  R lambda;
+  __device__ __forceinline__ R apply(const R (&x)[NIN], long long i, Partial& acc) const {
+    R d = x[3];
+    if (!(d > R(0))) flag_index(acc, i);  // @assert d[i] > 0  (:70)
+    R ci = sqrt(R(2) * lambda * d);
+    R xps = x[0] + x[1];
+    R o = (jl_abs(d * xps - x[2]) <= ci) ? -xps : (-x[2]) / d;
+    if (PSI) acc.s += h_term(SPX_H_L0, xps + o);
+    return o;
+  }
+};
+
 // shiftedRootNormLhalf.jl:41-63
 template <class R, bool PSI> struct ProxLhalf {
   using Real = R;
 #ifndef SPX_LH_UNROLL
-#define SPX_LH_UNROLL 1
+#define SPX_LH_UNROLL 2
 #endif
 #ifndef SPX_LH_MINB
 #define SPX_LH_MINB 4
@@ -259,23 +341,21 @@ template <class R, bool PSI> struct ProxLhalf {
   const R* in[NIN];  // xk, sj, q
   R fill[NIN];
   R* y;
-  R nulam;      // σλ
-  double p;     // 54^(1/3) (2νλ)^(2/3) / 4  (Float64)
-  double c4;    // (double)(νλ/4)
-  UDiv<R> by3;  // x / 3 in R
+  double p;    // 54^(1/3) (2νλ)^(2/3) / 4  (Float64)
+  double c4;   // (double)(νλ/4), νλ/4 evaluated in R
+  float c4f;   // (float)c4
+  bool fast;   // c4 inside the Float32-friendly range (host-checked)
   __device__ __forceinline__ R apply(const R (&x)[NIN], long long, Partial& acc) const {
-    R xs = x[0] + x[1];
-    R z = x[2] + xs;  // ψ.sol[i]  (:50)
-    R az = jl_abs(z);
-    R o;
-    if ((double)az <= p) {
-      o = R(0);
-    } else {
-      // above the threshold t = νλ/4 (|z|/3)^(-3/2) lies in (0, 1/√2]: real branch only
-      const double t = lhalf_t(c4, (double)by3(az));
-      const R coef = (jl_sign(z) * (R(2) / R(3))) * az;  // == ((2 sign z) / 3) |z| bit for bit
-      o = (R)((double)coef * lhalf_G_real(t));
-    }
+    const R xs = x[0] + x[1];
+    const R z = x[2] + xs;  // ψ.sol[i]  (:50)
+    const R az = jl_abs(z);
+    // above the threshold t = νλ/4 (|z|/3)^(-3/2) lies in (0, 1/√2]: real branch only.  Every lane
+    // runs the straight-line Newton (nearly every warp holds an element above the threshold).
+    const bool above = !((double)az <= p);
+    const float zf = (float)az;
+    double mag = lhalf_newton<false>((double)az, c4 + c4, lhalf_start(zf, c4f));
+    if (above && !(fast && lhalf_f32_range(zf))) mag = lhalf_mag_ref<R>(az, c4);
+    R o = above ? (R)copysign(mag, (double)z) : R(0);
     o = o - xs;
     if (PSI) acc.s += h_term(SPX_H_LHALF, xs + o);
     return o;
@@ -566,7 +646,62 @@ __device__ __forceinline__ bool jl_isgreater(double x, double y) {
   return (x != x || y != y) ? jl_isless(x, y) : jl_isless(y, x);
 }
 
-// shiftedRootNormLhalfBox.jl:86-120
+// shiftedRootNormLhalfBox.jl:86-120 -- the operation-by-operation form of one selected element: four
+// candidate objectives RNorm(tt) = (tt - q)²/2/σ + λ sqrt|tt + xs| with IEEE divisions and square roots,
+// then `findmin` (first minimal index, NaN counts as minimal).  The streaming kernel calls it only for
+// the elements its Float32 filter cannot decide (below).
+template <class R> struct LhalfBoxExact {
+  R lambda;
+  double c4;  // (double)(σλ/4), σλ/4 evaluated in R
+  UDiv<R> by3, by_sigma;
+  UDiv<double> by_sigma64;
+};
+template <class R>
+static __device__ __noinline__ R lhalfbox_exact(R xi, R si, R qi, R li, R ui, const LhalfBoxExact<R> k) {
+  const R xs = xi + si;  // ψ.sol[i]  (:94)
+  const R xsq = xs + qi;
+  const R axsq = jl_abs(xsq);
+  const double t = lhalf_t(k.c4, (double)k.by3(axsq));
+  const R coef = (jl_sign(xsq) * (R(2) / R(3))) * axsq;  // == ((2 sign) / 3) |xsq| bit for bit
+  // Candidate 4 (`val - xs`) only matters on the real branch t <= 1.  For t > 1 (|xsq| below
+  // 3 (σλ/4)^(2/3)) the objective RNorm has no stationary point besides the kink at tt = -xs: it
+  // decreases towards the kink from both sides, so whatever real(val) is, an endpoint or the kink is
+  // never worse and `findmin` (strict improvement, candidate 4 last) cannot pick it; t = NaN/Inf
+  // make val NaN/Inf, which the reference's range test rejects as well.  The complex-branch value is
+  // therefore never evaluated here ("LhalfBox candidate 4").
+  const bool real_branch = t <= 1.0;
+  const double val = (double)coef * lhalf_G_real(real_branch ? t : 1.0);
+  // x/2 == x*0.5 exactly
+  const R left = li - si, right = ui - si, mxs = -xs;
+  const R dl = left - qi, dr = right - qi;
+  const double inf = __longlong_as_double(0x7ff0000000000000ll);
+  const double c0 = (double)(k.by_sigma((dl * dl) * R(0.5)) + k.lambda * sqrt_fast(jl_abs(left + xs)));
+  const double c1 = (double)(k.by_sigma((dr * dr) * R(0.5)) + k.lambda * sqrt_fast(jl_abs(right + xs)));
+  // tt = -xs: tt - q = -(xs + q), and tt + xs is 0 (NaN for a non-finite xs) where sqrt|.| == |.|
+  const double c2v = (double)(k.by_sigma((xsq * xsq) * R(0.5)) + k.lambda * jl_abs(mxs + xs));
+  const double c2 = ((li <= -xi) && (-xi <= ui)) ? c2v : inf;
+  const double vmx = val - (double)xi;
+  const double cand4 = val - (double)xs;  // Float64 (val is Float64)
+  const double dq4 = cand4 - (double)qi;
+  const double c3v = k.by_sigma64((dq4 * dq4) * 0.5) + (double)k.lambda * sqrt_fast(fabs(cand4 + (double)xs));
+  const double c3 = (real_branch && ((double)li <= vmx) && (vmx <= (double)ui)) ? c3v : inf;
+  // findmin over (c0, c1, c2, c3): the values are NaN, +Inf or >= +0, so Base.isless reduces to `<`
+  // plus the NaN rule.
+  int a = 0;
+  double fm = c0;
+  if ((c1 < fm) || ((c1 != c1) && (fm == fm))) { fm = c1; a = 1; }
+  if ((c2 < fm) || ((c2 != c2) && (fm == fm))) { fm = c2; a = 2; }
+  if ((c3 < fm) || ((c3 != c3) && (fm == fm))) { fm = c3; a = 3; }
+  return a == 0 ? left : (a == 1 ? right : (a == 2 ? mxs : (R)cand4));
+}
+
+// The streaming form.  `findmin` only needs the ORDER of the four objectives, so they are first
+// evaluated in Float32 (FP32 pipe + SFU square roots; the differences tt - q and tt + xs are formed
+// in R and rounded once, so every objective carries a relative error < 4e-7).  When the smallest and
+// the second smallest differ by more than 4e-6 (ten times that bound) the exact order is decided;
+// otherwise -- exact ties, NaNs, values outside the Float32 range, t within 0.2% of the real/complex
+// boundary -- the element goes through lhalfbox_exact.  The selected point itself (an edge, the
+// kink, or the stationary point from the Float64 Newton) never passes through Float32.
 template <class R, bool PSI> struct ProxLhalfBox {
   using Real = R;
 #ifndef SPX_LHB_UNROLL
@@ -575,62 +710,66 @@ template <class R, bool PSI> struct ProxLhalfBox {
 #ifndef SPX_LHB_MINB
 #define SPX_LHB_MINB 4
 #endif
-  static constexpr int NIN = 5, UNROLL = SPX_LHB_UNROLL, MINB = SPX_LHB_MINB;
+#ifndef SPX_LHB_STAGES
+#define SPX_LHB_STAGES 0
+#endif
+  static constexpr int NIN = 5, UNROLL = SPX_LHB_UNROLL, MINB = SPX_LHB_MINB, STAGES = SPX_LHB_STAGES;
   static constexpr bool OUT = true, ACC = PSI;
   const R* in[NIN];  // xk, sj, q, l, u
   R fill[NIN];
   R* y;
   DevSel sel;
-  R lambda, sigma;
-  double c4;        // (double)(σλ/4), σλ/4 evaluated in R
-  double cos_2pi3;  // cos((2π)/3) in Float64
-  UDiv<R> by3, by_sigma;
-  UDiv<double> by_sigma64;
+  LhalfBoxExact<R> k;
+  float kf;    // 1/(2σ)
+  float lamf;  // λ
+  float c4f;   // σλ/4
+  bool fast;   // σ, λ, σλ/4 inside the Float32-friendly range (host-checked)
   __device__ __forceinline__ R apply(const R (&x)[NIN], long long i, Partial& acc) const {
     const R xi = x[0], si = x[1], qi = x[2], li = x[3], ui = x[4];
-    const bool s = sel.has(i);
-    R o;
-    if (!s) {
-      o = prox_zero(qi, li - si, ui - si);
-    } else {
-      const R xs = xi + si;  // ψ.sol[i]  (:94)
-      const R xsq = xs + qi;
-      const R axsq = jl_abs(xsq);
-      const double t = lhalf_t(c4, (double)by3(axsq));
-      const R coef = (jl_sign(xsq) * (R(2) / R(3))) * axsq;  // == ((2 sign) / 3) |xsq| bit for bit
-      // Candidate 4 (`val - xs`) only matters on the real branch t <= 1.  For t > 1 (|xsq| below
-      // 3 (σλ/4)^(2/3)) the objective RNorm has no stationary point besides the kink at tt = -xs: it
-      // decreases towards the kink from both sides, so whatever real(val) is, an endpoint or the kink is
-      // never worse and `findmin` (strict improvement, candidate 4 last) cannot pick it; t = NaN/Inf
-      // make val NaN/Inf, which the reference's range test rejects as well.  The complex-branch value is
-      // therefore never evaluated here ("LhalfBox candidate 4").
-      const bool real_branch = t <= 1.0;
-      const double val = (double)coef * lhalf_G_real(real_branch ? t : 1.0);
-      // RNorm(tt) = (tt - q)^2 / 2 / σ + λ sqrt(|tt + xs|)   (:95); x/2 == x*0.5 exactly.
-      // All four candidates are evaluated straight-line (nearly every warp needs all of them) and
-      // masked with +Inf afterwards.
-      const R left = li - si, right = ui - si, mxs = -xs;
-      const R dl = left - qi, dr = right - qi;
-      const double inf = __longlong_as_double(0x7ff0000000000000ll);
-      const double c0 = (double)(by_sigma((dl * dl) * R(0.5)) + lambda * sqrt_fast(jl_abs(left + xs)));
-      const double c1 = (double)(by_sigma((dr * dr) * R(0.5)) + lambda * sqrt_fast(jl_abs(right + xs)));
-      // tt = -xs: tt - q = -(xs + q), and tt + xs is 0 (NaN for a non-finite xs) where sqrt|.| == |.|
-      const double c2v = (double)(by_sigma((xsq * xsq) * R(0.5)) + lambda * jl_abs(mxs + xs));
-      const double c2 = ((li <= -xi) && (-xi <= ui)) ? c2v : inf;
-      const double vmx = val - (double)xi;
-      const double cand4 = val - (double)xs;  // Float64 (val is Float64)
-      const double dq4 = cand4 - (double)qi;
-      const double c3v = by_sigma64((dq4 * dq4) * 0.5) + (double)lambda * sqrt_fast(fabs(cand4 + (double)xs));
-      const double c3 = (real_branch && ((double)li <= vmx) && (vmx <= (double)ui)) ? c3v : inf;
-      // findmin over (c0, c1, c2, c3): first minimal index, NaN counts as minimal.  The values are
-      // NaN, +Inf or >= +0, so Base.isless reduces to `<` plus the NaN rule.
-      int a = 0;
-      double fm = c0;
-      if ((c1 < fm) || ((c1 != c1) && (fm == fm))) { fm = c1; a = 1; }
-      if ((c2 < fm) || ((c2 != c2) && (fm == fm))) { fm = c2; a = 2; }
-      if ((c3 < fm) || ((c3 != c3) && (fm == fm))) { fm = c3; a = 3; }
-      o = a == 0 ? left : (a == 1 ? right : (a == 2 ? mxs : (R)cand4));
-    }
+    const bool s = (sel.kind == SPX_SEL_ALL) || sel.has(i);
+    const R xs = xi + si;  // ψ.sol[i]  (:94)
+    const R xsq = xs + qi;
+    const R axsq = jl_abs(xsq);
+    const R left = li - si, right = ui - si, mxs = -xs;
+    // stationary point (candidate 4)
+    const float zf = (float)axsq;
+    const LhalfStart st = lhalf_start(zf, c4f);
+    const double mag = lhalf_newton<true>((double)axsq, k.c4 + k.c4, st);
+    const double val = copysign(mag, (double)xsq);
+    const bool real_branch = st.t32 <= 0.998f;
+    bool hard = !(fast && lhalf_f32_range(zf)) || !(st.t32 <= 0.998f || st.t32 >= 1.002f);
+    const double vmx = val - (double)xi;
+    const double cand4 = val - (double)xs;
+    const double dq4 = cand4 - (double)qi;
+    const double ar4 = cand4 + (double)xs;
+    const bool in4 = real_branch && ((double)li <= vmx) && (vmx <= (double)ui);
+    const bool zero_in = (li <= -xi) && (-xi <= ui);
+    // Float32 objectives
+    const float inff = __int_as_float(0x7f800000);
+    const float dlf = (float)(left - qi), drf = (float)(right - qi);
+    const float alf = fabsf((float)(left + xs)), arf = fabsf((float)(right + xs));
+    const float dq4f = (float)dq4, a4f = fabsf((float)ar4);
+    const float c0 = fmaf(dlf * dlf, kf, lamf * sqrt_approx(alf));
+    const float c1 = fmaf(drf * drf, kf, lamf * sqrt_approx(arf));
+    const float c2 = zero_in ? (zf * zf) * kf : inff;
+    const float c3 = in4 ? fmaf(dq4f * dq4f, kf, lamf * sqrt_approx(a4f)) : inff;
+    int a = 0;
+    float m = c0;
+    if (c1 < m) { m = c1; a = 1; }
+    if (c2 < m) { m = c2; a = 2; }
+    if (c3 < m) { m = c3; a = 3; }
+    const float lo01 = fminf(c0, c1), hi01 = fmaxf(c0, c1);
+    const float lo23 = fminf(c2, c3), hi23 = fmaxf(c2, c3);
+    const float m2 = fminf(fmaxf(lo01, lo23), fminf(hi01, hi23));  // second smallest
+    const bool clear = (m2 > m * 1.000004f) && (m > 1e-30f);
+    const bool nonan = (c0 == c0) && (c1 == c1) && (c2 == c2) && (c3 == c3);
+    hard = hard || !clear || !nonan;
+    R o = left;
+    o = (a == 1) ? right : o;
+    o = (a == 2) ? mxs : o;
+    o = (a == 3) ? (R)cand4 : o;
+    if (hard) o = lhalfbox_exact<R>(xi, si, qi, li, ui, k);
+    if (!s) o = prox_zero(qi, left, right);
     if (PSI) BoxPsi<R>{SPX_H_LHALF}.add(acc, s, xi, si, o, li, ui);
     return o;
   }
