@@ -176,6 +176,7 @@ static int32_t launch_box_t(spx_ctx* ctx, cudaStream_t stream, int opc, bool inv
       IproxL1Box<R, PSI> op;
       set_box(op, xk, sj, qg, d, lvec, lval, uvec, uval);
       op.y = y; op.sel = sel; op.lambda = lambda;
+      op.lam_ok = lambda == R(0) || (std::fabs((double)lambda) > 1e-100 && std::fabs((double)lambda) < 1e100);
       return ew_launch(ctx, stream, op, n, base, partials, nb);
     } else if (opc == BOX_L0) {
       IproxL0Box<R, PSI> op;

@@ -458,7 +458,42 @@ template <class R, bool PSI> struct ProxL1Box {
   }
 };
 
-// shiftedNormL1Box.jl:131-225
+// The four quotients of the L1Box iprox! regimes with |d| > eps (shiftedNormL1Box.jl:161-171):
+//   g/(d/2) = 2 (g/d),  λ/(d/2) = 2 (λ/d),  a1 = (-(g+λ))/d,  a2 = (λ-g)/d
+// from one reciprocal (see Quot3).  Sums and differences of g and λ are 0 or at least 2^-53 of the larger,
+// so the range test on g and λ covers all four numerators.
+template <class R> struct Quot4 { R g2, l2, a1, a2; };
+template <class R> __device__ __forceinline__ Quot4<R> quot4_ref(R g, R d, R lambda) {
+  Quot4<R> q;
+  const R d_2 = d / R(2);
+  q.g2 = g / d_2;
+  q.l2 = lambda / d_2;
+  q.a1 = (-(g + lambda)) / d;
+  q.a2 = (lambda - g) / d;
+  return q;
+}
+static __device__ __noinline__ Quot4<double> quot4_ref_call(double g, double d, double lambda) {
+  return quot4_ref<double>(g, d, lambda);
+}
+__device__ __forceinline__ Quot4<float> quot4(float g, float d, float lambda, bool) {
+  return quot4_ref<float>(g, d, lambda);
+}
+__device__ __forceinline__ Quot4<double> quot4(double g, double d, double lambda, bool lam_ok) {
+  const double ad = fabs(d), ag = fabs(g);
+  const bool fast = lam_ok && ad > 1e-100 && ad < 1e100 && (g == 0.0 || (ag > 1e-100 && ag < 1e100));
+  if (!fast) return quot4_ref_call(g, d, lambda);
+  const double y = 1.0 / d;
+  Quot4<double> q;
+  q.g2 = 2.0 * markstein(g, d, y);
+  q.l2 = 2.0 * markstein(lambda, d, y);
+  q.a1 = markstein(-(g + lambda), d, y);
+  q.a2 = markstein(lambda - g, d, y);
+  return q;
+}
+
+// shiftedNormL1Box.jl:131-225.  Straight-line like IproxL0Box below: the three regimes are evaluated
+// for every element and selected.  `x < min(a, b)` is written `x < a && x < b` (same truth table,
+// NaNs included, since Base.min propagates NaN and every comparison with NaN is false).
 template <class R, bool PSI> struct IproxL1Box {
   using Real = R;
   static constexpr int NIN = 6, UNROLL = 1, MINB = 3;
@@ -468,60 +503,49 @@ template <class R, bool PSI> struct IproxL1Box {
   R* y;
   DevSel sel;
   R lambda;
+  bool lam_ok;  // λ is 0 or a normal number far from the range limits (host-checked)
   __device__ __forceinline__ R apply(const R (&x)[NIN], long long i, Partial& acc) const {
     const R xi = x[0], si = x[1], gi = x[2], di = x[3], li = x[4], ui = x[5];
     const R eps = Eps<R>::value;
-    const bool s = sel.has(i);
-    const R xs = xi + si;
+    const bool s = (sel.kind == SPX_SEL_ALL) || sel.has(i);
+    const R xs = xi + si, mxs = -xs;
     const R left = li - si, right = ui - si;
-    R yi;
-    if (!s) {
-      yi = iprox_zero(di, gi, left, right);
-    } else if (jl_abs(di) <= eps) {  // :152-159
-      if (jl_abs(gi) <= lambda) yi = jl_min(jl_max(left, -xs), right);
-      else yi = (gi > R(0)) ? left : right;
-    } else {
-      const R di_2 = di / R(2);
-      const R lx = li + xi, ux = ui + xi;
-      const R gi2_di = gi / di_2;
-      const R fi2_di = gi2_di - R(2) * xs;
-      const R l2_di = lambda / di_2;
-      const R val_left = lx * lx + fi2_di * lx + l2_di * jl_abs(lx);
-      const R val_right = ux * ux + fi2_di * ux + l2_di * jl_abs(ux);
-      if (di > eps) {  // :161-198
-        R val_min = jl_min(val_left, val_right);
-        yi = (val_left < val_right) ? left : right;
-        const R a1 = (-(gi + lambda)) / di;
-        const R a2 = (lambda - gi) / di;
-        const bool in1 = (left <= a1) && (a1 <= right);
-        const bool in2 = (left <= a2) && (a2 <= right);
-        if (lx >= R(0)) {
-          if (in1) yi = a1;
-        } else if (R(0) >= ux) {
-          if (in2) yi = a2;
-        } else {
-          if (in1) {
-            R v1 = xs + a1;
-            R val1 = v1 * v1 + fi2_di * v1 + l2_di * jl_abs(v1);
-            if (val1 < val_min) yi = a1;
-            val_min = jl_min(val1, val_min);
-          }
-          if (in2) {
-            R v2 = xs + a2;
-            R val2 = v2 * v2 + fi2_di * v2 + l2_di * jl_abs(v2);
-            if (val2 < val_min) yi = a2;
-            val_min = jl_min(val2, val_min);
-          }
-          if (R(0) < val_min) yi = -xs;
-        }
-      } else {  // :200-218
-        R val_max = jl_max(val_left, val_right);
-        yi = (val_left > val_right) ? left : right;
-        if ((li <= -xi) && (-xi <= ui)) {
-          if (R(0) > val_max) yi = -xs;
-        }
-      }
+    // ---- |d| <= eps  (:152-159)
+    const R yA = (jl_abs(gi) <= lambda) ? jl_min(jl_max(left, mxs), right) : ((gi > R(0)) ? left : right);
+    // ---- |d| > eps: one reciprocal serves the four quotients
+    const bool small_d = jl_abs(di) <= eps;
+    const Quot4<R> qt = quot4(gi, small_d ? R(1) : di, lambda, lam_ok);
+    const R lx = li + xi, ux = ui + xi;
+    const R fi2_di = qt.g2 - R(2) * xs;
+    const R l2_di = qt.l2;
+    const R vl = lx * lx + fi2_di * lx + l2_di * jl_abs(lx);
+    const R vr = ux * ux + fi2_di * ux + l2_di * jl_abs(ux);
+    R yB;
+    {  // d > eps  (:161-198)
+      const R edge = (vl < vr) ? left : right;
+      const R a1 = qt.a1, a2 = qt.a2;
+      const bool in1 = (left <= a1) && (a1 <= right);
+      const bool in2 = (left <= a2) && (a2 <= right);
+      const R v1 = xs + a1, v2 = xs + a2;
+      const R val1 = v1 * v1 + fi2_di * v1 + l2_di * jl_abs(v1);
+      const R val2 = v2 * v2 + fi2_di * v2 + l2_di * jl_abs(v2);
+      const bool c1 = in1 && (val1 < vl) && (val1 < vr);
+      const bool c2 = in2 && (val2 < vl) && (val2 < vr) && (!in1 || (val2 < val1));
+      const bool c0 = (R(0) < vl) && (R(0) < vr) && (!in1 || (R(0) < val1)) && (!in2 || (R(0) < val2));
+      R mid = c1 ? a1 : edge;
+      mid = c2 ? a2 : mid;
+      mid = c0 ? mxs : mid;
+      const R pos = in1 ? a1 : edge;  // lx >= 0
+      const R neg = in2 ? a2 : edge;  // 0 >= ux
+      yB = (lx >= R(0)) ? pos : ((R(0) >= ux) ? neg : mid);
     }
+    R yC;
+    {  // d < -eps  (:200-218)
+      yC = (vl > vr) ? left : right;
+      if ((li <= -xi) && (-xi <= ui) && (R(0) > vl) && (R(0) > vr)) yC = mxs;
+    }
+    R yi = small_d ? yA : ((di > eps) ? yB : yC);
+    if (!s) yi = iprox_zero(di, gi, left, right);
     if (PSI) BoxPsi<R>{SPX_H_L1}.add(acc, s, xi, si, yi, li, ui);
     return yi;
   }
@@ -583,7 +607,7 @@ template <class R, bool PSI> struct IproxL0Box {
   __device__ __forceinline__ R apply(const R (&x)[NIN], long long i, Partial& acc) const {
     const R xi = x[0], si = x[1], gi = x[2], di = x[3], li = x[4], ui = x[5];
     const R eps = Eps<R>::value;
-    const bool s = sel.has(i);
+    const bool s = (sel.kind == SPX_SEL_ALL) || sel.has(i);
     const R xs = xi + si, mxs = -xs;
     const R left = li - si, right = ui - si;
     const bool zero_in = (li <= -xi) && (-xi <= ui);
@@ -595,9 +619,9 @@ template <class R, bool PSI> struct IproxL0Box {
       const R vr = gi * right + ((xi == -ui) ? R(0) : lambda);
       const bool gpos = gi > R(0), gneg = gi < R(0);
       // a NaN g takes no branch in the reference (y[i] untouched); NaN is written here
-      const R nan = gi - gi;
-      const R val_min = gpos ? vl : (gneg ? vr : nan / nan);
-      R yy = gpos ? left : (gneg ? right : nan / nan);
+      const R nan = gi - gi;  // NaN exactly when g is NaN, the only case in which it is used
+      const R val_min = gpos ? vl : (gneg ? vr : nan);
+      R yy = gpos ? left : (gneg ? right : nan);
       const R val_0 = (-gi) * xs;
       if (zero_in && (val_0 < val_min)) yy = mxs;
       y1 = (gi == R(0)) ? (zero_in ? mxs : R(0)) : yy;
@@ -617,15 +641,15 @@ template <class R, bool PSI> struct IproxL0Box {
       const bool inside = (lx <= aq_v) && (aq_v <= ux);
       const R sq = aq_v * aq_v;
       const R vin = (aq_v == R(0)) ? -sq : (-sq + l2_di);
-      const R val_min = inside ? vin : jl_min(val_left, val_right);
+      // 0 < min(val_left, val_right)  <=>  0 < val_left && 0 < val_right  (Base.min propagates NaN)
+      const bool pos_min = inside ? (R(0) < vin) : ((R(0) < val_left) && (R(0) < val_right));
       y2 = inside ? aq_y : ((val_left < val_right) ? left : right);
-      if (zero_in && (R(0) < val_min)) y2 = mxs;
+      if (zero_in && pos_min) y2 = mxs;
     }
     R y3;
     {  // d <= -eps  (:211-223)
       y3 = (val_left > val_right) ? left : right;
-      const R val_max = jl_max(val_left, val_right);
-      if (zero_in && (R(0) > val_max)) y3 = mxs;
+      if (zero_in && (R(0) > val_left) && (R(0) > val_right)) y3 = mxs;
     }
     R yi = small_d ? y1 : ((di >= eps) ? y2 : y3);
     if (!s) yi = iprox_zero_q(di, gi, left, right, aq_y);
