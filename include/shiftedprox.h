@@ -137,6 +137,25 @@ int32_t spx_checksum(spx_ctx* ctx, const void* p, int64_t nwords64, uint64_t* ou
  * psi_out (host, may be NULL): if given, ψ(y) at the freshly computed y is
  * accumulated in the same pass (ShiftedProximalOperators.jl:51-54 fused) and
  * the call synchronises. */
+/* one operation of spx_box_multi_host_*: op 0 L1Box, 1 L0Box, 2 LhalfBox; d_host == NULL -> */
+/* prox!(y, ψ, q_or_g = q, sigma), else iprox!(y, ψ, q_or_g = g, d) */
+typedef struct spx_box_job_f64 {
+  int32_t op;
+  int32_t reserved;
+  double* y_host;
+  const double* q_or_g_host;
+  const double* d_host;
+  double lambda, sigma;
+} spx_box_job_f64;
+typedef struct spx_box_job_f32 {
+  int32_t op;
+  int32_t reserved;
+  float* y_host;
+  const float* q_or_g_host;
+  const float* d_host;
+  double lambda, sigma;
+} spx_box_job_f32;
+
 #define SPX_DECL_SEPARABLE(SUF, R)                                                               \
   /* ShiftedNormL1.prox!  shiftedNormL1.jl:40-54 */                                              \
   int32_t spx_prox_l1_##SUF(spx_ctx* ctx, int64_t n, R* y, const R* xk, const R* sj, const R* q, \
@@ -260,7 +279,17 @@ int32_t spx_checksum(spx_ctx* ctx, const void* p, int64_t nwords64, uint64_t* ou
                              const R* sj_host, const R* q_or_g_host, const R* d_host,            \
                              const R* l_host, double l_val, const R* u_host, double u_val,       \
                              double lambda, double sigma, int64_t chunk_elems,                   \
-                             double* psi_out);
+                             double* psi_out);                                                   \
+  /* Several Box prox!/iprox! at the SAME shifted point (xk, sj, l, u) in one pass over the */   \
+  /* host vectors: each chunk of xk, sj, l, u and of every distinct q/g/d vector crosses PCIe */ \
+  /* once, the nops kernels run back to back on it, and the nops outputs travel back while */    \
+  /* the next chunk is uploaded.  This is the solver-side pattern (several regularizers / */    \
+  /* a prox! and an iprox! evaluated at one iterate).  Host vectors named by several ops are */  \
+  /* recognised by pointer.  psi_out: NULL or nops doubles (ψ(y) of each op).  */                \
+  int32_t spx_box_multi_host_##SUF(spx_ctx* ctx, int32_t nops, const spx_box_job_##SUF* jobs,    \
+                                   int64_t n, const R* xk_host, const R* sj_host,                \
+                                   const R* l_host, double l_val, const R* u_host, double u_val, \
+                                   int64_t chunk_elems, double* psi_out);
 
 SPX_DECL_SEPARABLE(f64, double)
 SPX_DECL_SEPARABLE(f32, float)

@@ -73,3 +73,12 @@ def call(name: str, *args) -> None:
     f = getattr(lib(), name)
     f.restype = C.c_int32
     check(f(*args))
+
+
+class BoxJobF64(C.Structure):
+    """spx_box_job_f64 (include/shiftedprox.h)"""
+    _fields_ = [("op", C.c_int32), ("reserved", C.c_int32), ("y_host", C.c_void_p), ("q_or_g_host", C.c_void_p),
+                ("d_host", C.c_void_p), ("lambda_", C.c_double), ("sigma", C.c_double)]
+
+
+BoxJobF32 = BoxJobF64  # same layout: the pointers are untyped here
