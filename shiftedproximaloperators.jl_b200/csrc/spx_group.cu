@@ -1,18 +1,26 @@
-// spx_group.cu -- group-norm operators: segmented warp-shuffle reductions.
+// spx_group.cu -- group-norm operators: segmented sub-warp reductions.
 //
-// One warp owns one group at a time (grid-stride over groups, so neighbouring
-// warps stream neighbouring groups: every 128-byte line is consumed while it is
-// in flight).  Groups of up to 32*EPL elements live in registers for the whole
-// prox (one HBM read per operand, one write); longer groups stash `sol` in the
-// output vector and re-read it through L1/L2.  Sums of squares are accumulated
-// in Float64 whatever R is; the butterfly order is fixed, so results are
-// deterministic.
+// A warp walks over tasks of 32 consecutive groups.  Inside a task it packs as many groups as fit
+// into one ROUND: 2^j groups of L = 32 / 2^j lanes each, L the smallest power of two such that every
+// group of the round holds at most 8 L elements (8 elements per lane stay in registers for the whole
+// prox: one HBM read per operand, one write).  Groups of 64 run four to a warp, groups of <= 8
+// thirty-two to a warp, so the per-group scalar work -- the norm, and for the Binf form the whole root
+// search -- is shared by the groups of a round instead of being repeated on 32 idle lanes.  Groups of
+// more than 256 elements take the whole warp, stash `sol` in the output vector and re-read it through
+// L1/L2.  Sums of squares are accumulated in Float64 whatever R is; the butterfly order is fixed, so
+// results are deterministic.
 #include "spx_common.cuh"
+#include "spx_ops.cuh"
 
 namespace spx {
 
 constexpr int kGroupThreads = 256;
-constexpr int kEPL = 4;  // elements per lane kept in registers (groups <= 128 elements)
+constexpr int kEPL = 8;    // elements per lane kept in registers
+constexpr int kTask = 32;  // consecutive groups per warp task
+
+#ifdef SPX_GROUP_STATS
+__device__ unsigned long long g_stat_evals = 0, g_stat_groups = 0;
+#endif
 
 template <class R> __device__ __forceinline__ R ldv(const R* p) {
   Pack<R, 1> t;
@@ -25,12 +33,133 @@ template <class R> __device__ __forceinline__ void stv(R* p, R v) {
   st_stream(p, t);
 }
 
+// reference form (shiftedGroupNormL2Binf.jl:83): sign(x) max(0, |x| - a)
 template <class R> __device__ __forceinline__ R softthres(R x, R a) {
   return jl_sign(x) * jl_max(R(0), jl_abs(x) - a);
 }
+// same value for non-NaN operands, three instructions (used inside the root search only)
+__device__ __forceinline__ double softthres_fast(double x, double a) { return copysign(fmax(fabs(x) - a, 0.0), x); }
+__device__ __forceinline__ float softthres_fast(float x, float a) { return copysignf(fmaxf(fabsf(x) - a, 0.0f), x); }
+
+// a / b to ~1 ulp for normal operands (reciprocal seed + two Newton steps + one residual correction);
+// anything else yields Inf/NaN, which every caller treats as "no usable candidate"
+__device__ __forceinline__ double div_fast(double a, double b) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(b));
+  double e = __fma_rn(-b, y, 1.0);
+  y = __fma_rn(y, e, y);
+  e = __fma_rn(-b, y, 1.0);
+  y = __fma_rn(y, e, y);
+  const double q = a * y;
+  const double r = __fma_rn(-b, q, a);
+  return __fma_rn(r, y, q);
+}
+__device__ __forceinline__ float div_fast(float a, float b) { return a / b; }
+
+// sum over the L lanes of a group (L a power of two, lanes aligned); every lane gets the total
+__device__ __forceinline__ double sub_sum(double v, int L) {
+  for (int o = L >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---- round planning ----------------------------------------------------------------------------
+// le[k] bit j: group j of the task has at most 8 << k elements (k = 0..5).  Returns k such that the
+// round holds 32 >> k groups of 1 << k lanes, or -1 when the group at `pos` is a long one.
+__device__ __forceinline__ int plan_round(const unsigned (&le)[6], int pos) {
+#pragma unroll
+  for (int k = 0; k <= 5; ++k) {
+    const int c = 32 >> k;
+    const unsigned need = (c >= 32 ? 0xffffffffu : ((1u << c) - 1u)) << pos;
+    if ((le[k] & need) == need) return k;
+  }
+  return -1;
+}
+
+struct TaskHead {
+  long long lo, hi;  // lane j: offsets of group g0 + j (0, 0 beyond the task)
+  unsigned le[6];
+  int cnt;
+};
+__device__ __forceinline__ TaskHead load_task(const long long* __restrict__ offs, long long g0, long long ngroups,
+                                              int lane) {
+  TaskHead t;
+  const long long left = ngroups - g0;
+  t.cnt = left < kTask ? (int)left : kTask;
+  t.lo = 0;
+  t.hi = 0;
+  if (lane < t.cnt) {
+    t.lo = offs[g0 + lane];
+    t.hi = offs[g0 + lane + 1];
+  }
+  const long long m = t.hi - t.lo;
+#pragma unroll
+  for (int k = 0; k <= 5; ++k) t.le[k] = __ballot_sync(0xffffffffu, m <= ((long long)kEPL << k));
+  return t;
+}
+
+// the part of a group a lane holds during a round
+// KEEP_XS: xk + sj stays in registers (the one-pass GroupNormL2); the Binf form, which holds the tile
+// through a root search, drops it and re-reads sj (an L2 hit) when it writes the result
+template <class R, bool KEEP_XS> struct Tile {
+  R sol[kEPL], xkr[kEPL], xs[KEEP_XS ? kEPL : 1];
+  long long b, e;  // the lane's group (b == e: none)
+  int L, sub;
+  bool valid;
+  __device__ __forceinline__ void load(const TaskHead& t, int k, int pos, int lane, const R* xk, const R* sj,
+                                       const R* q) {
+    L = 1 << k;
+    sub = lane & (L - 1);
+    const int gi = pos + (lane >> k);
+    const long long lo = __shfl_sync(0xffffffffu, t.lo, gi & 31);
+    const long long hi = __shfl_sync(0xffffffffu, t.hi, gi & 31);
+    valid = gi < t.cnt;
+    b = valid ? lo : 0;
+    e = valid ? hi : 0;
+#pragma unroll
+    for (int j = 0; j < kEPL; ++j) {
+      const long long i = b + (long long)j * L + sub;
+      sol[j] = R(0);
+      xkr[j] = R(0);
+      if (KEEP_XS) xs[j] = R(0);
+      if (i < e) {
+        const R xi = ldv(xk + i), si = ldv(sj + i), qi = ldv(q + i);
+        sol[j] = (qi + xi) + si;  // shiftedGroupNormL2.jl:65, shiftedGroupNormL2Binf.jl:80
+        xkr[j] = xi;
+        if (KEEP_XS) xs[j] = xi + si;
+      }
+    }
+  }
+  __device__ __forceinline__ int group_in_task(int pos, int k, int lane) const { return pos + (lane >> k); }
+};
 
 // ------------------------------------------------------- ShiftedGroupNormL2 --
 // shiftedGroupNormL2.jl:52-79
+template <class R, bool PSI>
+__device__ __forceinline__ double l2_long_group(R* y, const R* xk, const R* sj, const R* q, long long b, long long e,
+                                                R lam, R sigma, int lane) {
+  double ss = 0.0;
+  for (long long i = b + lane; i < e; i += 32) {
+    const R s = (q[i] + xk[i]) + sj[i];
+    y[i] = s;  // stash sol (each lane re-reads only what it wrote)
+    ss += (double)s * (double)s;
+  }
+  ss = warp_sum(ss);
+  const R snorm = (R)sqrt(ss);
+  const R alpha = jl_max(R(1) - sigma * lam / snorm, R(0));
+  double vv = 0.0;
+  for (long long i = b + lane; i < e; i += 32) {
+    const R xsi = xk[i] + sj[i];
+    const R o = (snorm == R(0) ? R(0) : alpha * y[i]) - xsi;
+    y[i] = o;
+    if (PSI) {
+      const double v = (double)(xsi + o);
+      vv += v * v;
+    }
+  }
+  if (PSI) vv = warp_sum(vv);
+  return vv;
+}
+
 template <class R, bool PSI>
 __global__ void __launch_bounds__(kGroupThreads)
     group_l2_kernel(R* y, const R* xk, const R* sj, const R* q, long long ngroups,
@@ -39,64 +168,50 @@ __global__ void __launch_bounds__(kGroupThreads)
   const int lane = threadIdx.x & 31;
   const long long warp = ((long long)blockIdx.x * kGroupThreads + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * kGroupThreads) >> 5;
+  const long long ntasks = (ngroups + kTask - 1) / kTask;
   double psi = 0.0;
-  for (long long g = warp; g < ngroups; g += nwarps) {
-    const long long b = offs[g], e = offs[g + 1], m = e - b;
-    const R lam = lambda_g[g];
-    double vv = 0.0;
-    if (m <= 32 * kEPL) {
-      R sol[kEPL], xs[kEPL];
+  for (long long task = warp; task < ntasks; task += nwarps) {
+    const long long g0 = task * kTask;
+    const TaskHead th = load_task(offs, g0, ngroups, lane);
+    const R lam_lane = lane < th.cnt ? lambda_g[g0 + lane] : R(0);
+    int pos = 0;
+    while (pos < th.cnt) {
+      const int k = plan_round(th.le, pos);
+      if (k < 0) {  // long group: the whole warp
+        const long long b = __shfl_sync(0xffffffffu, th.lo, pos), e = __shfl_sync(0xffffffffu, th.hi, pos);
+        const R lam = __shfl_sync(0xffffffffu, lam_lane, pos);
+        const double vv = l2_long_group<R, PSI>(y, xk, sj, q, b, e, lam, sigma, lane);
+        if (PSI && lane == 0) psi += (double)(lam * (R)sqrt(vv));  // λ_g ‖v_g‖  groupNormL2.jl:36
+        pos += 1;
+        continue;
+      }
+      Tile<R, true> t;
+      t.load(th, k, pos, lane, xk, sj, q);
+      const R lam = __shfl_sync(0xffffffffu, lam_lane, t.group_in_task(pos, k, lane) & 31);
       double ss = 0.0;
 #pragma unroll
-      for (int k = 0; k < kEPL; ++k) {
-        const long long i = b + k * 32 + lane;
-        sol[k] = R(0);
-        xs[k] = R(0);
-        if (i < e) {
-          const R xi = ldv(xk + i), si = ldv(sj + i), qi = ldv(q + i);
-          sol[k] = (qi + xi) + si;  // :65
-          xs[k] = xi + si;
-          ss += (double)sol[k] * (double)sol[k];
-        }
-      }
-      ss = warp_sum(ss);
-      const R snorm = (R)sqrt(ss);
+      for (int j = 0; j < kEPL; ++j) ss += (double)t.sol[j] * (double)t.sol[j];
+      ss = sub_sum(ss, t.L);
+      const R snorm = (R)sqrt_fast(ss);
       const R alpha = jl_max(R(1) - sigma * lam / snorm, R(0));
+      double vv = 0.0;
 #pragma unroll
-      for (int k = 0; k < kEPL; ++k) {
-        const long long i = b + k * 32 + lane;
-        if (i < e) {
-          const R o = (snorm == R(0) ? R(0) : alpha * sol[k]) - xs[k];  // :70-77
+      for (int j = 0; j < kEPL; ++j) {
+        const long long i = t.b + (long long)j * t.L + t.sub;
+        if (i < t.e) {
+          const R o = (snorm == R(0) ? R(0) : alpha * t.sol[j]) - t.xs[j];  // :70-77
           stv(y + i, o);
           if (PSI) {
-            const double v = (double)(xs[k] + o);
+            const double v = (double)(t.xs[j] + o);
             vv += v * v;
           }
         }
       }
-    } else {
-      double ss = 0.0;
-      for (long long i = b + lane; i < e; i += 32) {
-        const R s = (q[i] + xk[i]) + sj[i];
-        y[i] = s;  // stash sol (each lane re-reads only what it wrote)
-        ss += (double)s * (double)s;
+      if (PSI) {
+        vv = sub_sum(vv, t.L);
+        if (t.valid && t.sub == 0) psi += (double)(lam * (R)sqrt_fast(vv));
       }
-      ss = warp_sum(ss);
-      const R snorm = (R)sqrt(ss);
-      const R alpha = jl_max(R(1) - sigma * lam / snorm, R(0));
-      for (long long i = b + lane; i < e; i += 32) {
-        const R xsi = xk[i] + sj[i];
-        const R o = (snorm == R(0) ? R(0) : alpha * y[i]) - xsi;
-        y[i] = o;
-        if (PSI) {
-          const double v = (double)(xsi + o);
-          vv += v * v;
-        }
-      }
-    }
-    if (PSI) {
-      vv = warp_sum(vv);
-      if (lane == 0) psi += (double)(lam * (R)sqrt(vv));  // λ_g ‖v_g‖  groupNormL2.jl:36
+      pos += 32 >> k;
     }
   }
   if (PSI) {
@@ -110,32 +225,70 @@ __global__ void __launch_bounds__(kGroupThreads)
 }
 
 // --------------------------------------------------- ShiftedGroupNormL2Binf --
-// shiftedGroupNormL2Binf.jl:67-119.  Group data access: registers (REG) or the
-// stashed `sol` in y plus xk from memory.
-template <class R> struct GroupView {
-  bool reg;
-  R sol[kEPL], xkr[kEPL];
+// shiftedGroupNormL2Binf.jl:67-119.  The views give the root search Σ f(sol_i, sol_i/σ, xk_i)² over
+// the lane's group: from registers (a round of short groups) or from the stash (a long group).
+// One element of froot's sum: (σ softthres(u - c xk, Δc) - sol)², softthres written out so that the
+// thresholded case costs a select (fused multiply-adds are fine here: the search only needs the sign
+// change of froot, whose rounding noise differs between any two summation orders anyway).
+__device__ __forceinline__ double froot_term(double so, double u, double xg, double c, double dc, double sigma,
+                                             double ss) {
+  const double t = __fma_rn(-c, xg, u);
+  const double a = fabs(t) - dc;
+  const double z = __fma_rn(sigma, copysign(a, t), -so);
+  const double w = a > 0.0 ? z : so;
+  return __fma_rn(w, w, ss);
+}
+__device__ __forceinline__ double froot_term(float so, float u, float xg, float c, float dc, float sigma, double ss) {
+  const float t = fmaf(-c, xg, u);
+  const float a = fabsf(t) - dc;
+  const float z = fmaf(sigma, copysignf(a, t), -so);
+  const double w = (double)(a > 0.0f ? z : so);
+  return __fma_rn(w, w, ss);
+}
+
+template <class R> struct TileView {
+  const Tile<R, false>& t;
+  R u[kEPL];  // sol / σ
+  R sigma;
+  template <class F> __device__ __forceinline__ double sumsq(F f) const {
+    double ss = 0.0;
+#pragma unroll
+    for (int j = 0; j < kEPL; ++j) {
+      const double w = (double)f(t.sol[j], u[j], t.xkr[j]);
+      ss = __fma_rn(w, w, ss);
+    }
+    return sub_sum(ss, t.L);
+  }
+  __device__ __forceinline__ double froot_sum(R c, R dc) const {
+    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+    for (int j = 0; j < kEPL; j += 2) {
+      s0 = froot_term(t.sol[j], u[j], t.xkr[j], c, dc, sigma, s0);
+      s1 = froot_term(t.sol[j + 1], u[j + 1], t.xkr[j + 1], c, dc, sigma, s1);
+    }
+    return sub_sum(s0 + s1, t.L);
+  }
+};
+template <class R> struct LongView {
   const R* ysol;  // stashed sol (y)
   const R* xk;
   long long b, e;
   int lane;
-  // Σ f(sol_i, xk_i)^2 over the group, Float64 accumulate, all lanes get the sum
+  R sigma;
   template <class F> __device__ __forceinline__ double sumsq(F f) const {
     double ss = 0.0;
-    if (reg) {
-#pragma unroll
-      for (int k = 0; k < kEPL; ++k) {
-        const long long i = b + k * 32 + lane;
-        if (i < e) {
-          const double t = (double)f(sol[k], xkr[k]);
-          ss += t * t;
-        }
-      }
-    } else {
-      for (long long i = b + lane; i < e; i += 32) {
-        const double t = (double)f(ysol[i], xk[i]);
-        ss += t * t;
-      }
+    for (long long i = b + lane; i < e; i += 32) {
+      const R so = ysol[i];
+      const double w = (double)f(so, so / sigma, xk[i]);
+      ss = __fma_rn(w, w, ss);
+    }
+    return warp_sum(ss);
+  }
+  __device__ __forceinline__ double froot_sum(R c, R dc) const {
+    double ss = 0.0;
+    for (long long i = b + lane; i < e; i += 32) {
+      const R so = ysol[i];
+      ss = froot_term(so, so / sigma, xk[i], c, dc, sigma, ss);
     }
     return warp_sum(ss);
   }
@@ -143,136 +296,175 @@ template <class R> struct GroupView {
 
 template <class R> __device__ __forceinline__ bool adjacent_or_crossed(R a, R m, R b) { return !((a < m) && (m < b)); }
 
+// x moved by k units in the last place (positive finite x)
+__device__ __forceinline__ double ulp_step(double x, int k) {
+  return __longlong_as_double(__double_as_longlong(x) + (long long)k);
+}
+__device__ __forceinline__ float ulp_step(float x, int k) { return __int_as_float(__float_as_int(x) + k); }
+
+// Runs the bracket search of every group of the round in lockstep (lanes of one group hold identical
+// copies of its state).  Returns the step c(n*) and whether the group's prox is zero.
+//
+// fzero(froot, lmin, lmax) (Roots' bisection) ends on two adjacent floats around the sign change of
+// froot.  Same end state, an order of magnitude fewer evaluations: Illinois regula falsi (superlinear,
+// both ends move), and as soon as the interpolated point falls within a few ulps of an end of the
+// bracket the next evaluation is placed k ulps inside that end -- stepping over the root, which leaves a
+// bracket of k ulps that two or three midpoint steps close.  After 60 steps (never observed) it
+// degrades to plain bisection, which terminates by itself.
+template <class R, class View>
+__device__ __forceinline__ bool binf_solve(const View& gv, bool valid, R lam, R sigma, R delta, R& step_out) {
+  const R eps = Eps<R>::value;
+  const R sl = lam * sigma;  // σλ
+  auto froot = [&](R nn) -> R {  // :87-93
+    const R c = div_fast(nn, sigma * (nn - sl));
+    const double ss = gv.froot_sum(c, delta * c);
+#ifdef SPX_GROUP_STATS
+    if ((threadIdx.x & 31) == 0) atomicAdd(&g_stat_evals, 1ull);
+#endif
+    return nn - (R)sqrt_fast(ss);
+  };
+  const R lmin = sl * (R(1) + eps);
+  const R fl = froot(lmin);
+  const R ansatz = lmin + R(1);
+  R step = ansatz / (sigma * (ansatz - sl));
+  const R dstep = delta * step;
+  const R zlmax = (R)sqrt_fast(gv.sumsq([&](R, R u, R xg) -> R { return softthres_fast(u - step * xg, dstep); }));
+  const R nsol = (R)sqrt_fast(gv.sumsq([&](R so, R, R) -> R { return so; }));
+  const R nxk = (R)sqrt_fast(gv.sumsq([&](R, R, R xg) -> R { return xg; }));
+  const R lmax = nsol + sigma * (zlmax + R(1) * lam * nxk);  // |(ϵ-1)/ϵ + 1| = 1 for ϵ = 1  (:100)
+  const R fm = froot(lmax);
+  bool zero_out = fl * fm > R(0);
+  R a = lmin, fa = fl, bb = lmax, fb = fm;
+  bool done = !valid || zero_out || (fl != fl) || (fm != fm) || !(lmin > R(0));
+  if (!done && fa == R(0)) { bb = a; fb = R(0); done = true; }
+  if (!done && fb == R(0)) { a = bb; fa = R(0); done = true; }
+  // Interpolation runs on g(n) = froot(n) (n - σλ): c(n) has a pole at n = σλ, which froot inherits
+  // (it behaves like -K/(n - σλ) next to lmin); g has the same sign as froot on the bracket and no pole.
+  R ga = fa * (a - sl), gb = fb * (bb - sl);  // Illinois-damped copies
+  int side = 0, kulp = 4, slow = 0;
+  for (int it = 0; it < 400; ++it) {
+    const R mid = a + (bb - a) / R(2);
+    done = done || adjacent_or_crossed(a, mid, bb);
+    if (!__any_sync(0xffffffffu, !done)) break;
+    R x = mid;
+    bool probed = false;
+    if (it < 80 && slow < 2) {
+      const R xs_ = div_fast(a * gb - bb * ga, gb - ga);
+      if ((a < xs_) && (xs_ < bb)) x = xs_;
+      const R a_k = ulp_step(a, kulp), b_k = ulp_step(bb, -kulp);
+      if (x <= a_k) {
+        x = (a_k < mid) ? a_k : mid;
+        probed = true;
+      } else if (x >= b_k) {
+        x = (b_k > mid) ? b_k : mid;
+        probed = true;
+      }
+    }
+    const R width = bb - a;
+    const R fx = froot(x);
+    if (!done) {
+      const R gx = fx * (x - sl);
+      const bool same_as_a = (fx < R(0)) == (fa < R(0));
+      if (fx == R(0)) {
+        a = bb = x;
+        fa = fb = R(0);
+        done = true;
+      } else if (same_as_a) {
+        a = x; fa = fx; ga = gx;
+        if (side == -1) gb = gb / R(2);
+        side = -1;
+      } else {
+        bb = x; fb = fx; gb = gx;
+        if (side == 1) ga = ga / R(2);
+        side = 1;
+      }
+      slow = ((bb - a) <= width / R(2)) ? 0 : slow + 1;
+      if (probed) kulp = kulp < (1 << 20) ? kulp * 4 : kulp;
+    }
+  }
+  if (!zero_out) {
+    const R nroot = (jl_abs(fa) <= jl_abs(fb)) ? a : bb;
+    step = nroot / (sigma * (nroot - sl));
+    if (jl_abs(nroot - sl) == R(0)) zero_out = true;  // `abs(n - σλ) ≈ 0`  (:107)
+  }
+  step_out = step;
+  return zero_out;
+}
+
 template <class R>
-__global__ void __launch_bounds__(kGroupThreads)
+__global__ void __launch_bounds__(kGroupThreads, 2)
     group_l2binf_kernel(R* y, const R* xk, const R* sj, const R* q, long long ngroups,
-                        const long long* __restrict__ offs, const R* __restrict__ lambda_g, R sigma, R delta) {
+                        const long long* __restrict__ offs, const R* __restrict__ lambda_g, R sigma, R delta,
+                        UDiv<R> by_sigma) {
   const int lane = threadIdx.x & 31;
   const long long warp = ((long long)blockIdx.x * kGroupThreads + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * kGroupThreads) >> 5;
-  const R eps = Eps<R>::value;
-  for (long long g = warp; g < ngroups; g += nwarps) {
-    GroupView<R> gv;
-    gv.b = offs[g];
-    gv.e = offs[g + 1];
-    gv.lane = lane;
-    gv.ysol = y;
-    gv.xk = xk;
-    gv.reg = (gv.e - gv.b) <= 32 * kEPL;
-    const R lam = lambda_g[g];
-    R xs[kEPL];
-    if (gv.reg) {
-#pragma unroll
-      for (int k = 0; k < kEPL; ++k) {
-        const long long i = gv.b + k * 32 + lane;
-        gv.sol[k] = R(0);
-        gv.xkr[k] = R(0);
-        xs[k] = R(0);
-        if (i < gv.e) {
-          const R xi = ldv(xk + i), si = ldv(sj + i), qi = ldv(q + i);
-          gv.sol[k] = (qi + xi) + si;  // :80
-          gv.xkr[k] = xi;
-          xs[k] = xi + si;
+  const long long ntasks = (ngroups + kTask - 1) / kTask;
+  for (long long task = warp; task < ntasks; task += nwarps) {
+    const long long g0 = task * kTask;
+    const TaskHead th = load_task(offs, g0, ngroups, lane);
+    const R lam_lane = lane < th.cnt ? lambda_g[g0 + lane] : R(0);
+    int pos = 0;
+    while (pos < th.cnt) {
+      const int k = plan_round(th.le, pos);
+      if (k < 0) {  // long group: the whole warp, sol stashed in y
+        const long long b = __shfl_sync(0xffffffffu, th.lo, pos), e = __shfl_sync(0xffffffffu, th.hi, pos);
+        const R lam = __shfl_sync(0xffffffffu, lam_lane, pos);
+        for (long long i = b + lane; i < e; i += 32) y[i] = (q[i] + xk[i]) + sj[i];  // :80
+        LongView<R> gv{y, xk, b, e, lane, sigma};
+        R step;
+        const bool zero_out = binf_solve<R>(gv, true, lam, sigma, delta, step);
+        const R sl = lam * sigma, dstep2 = delta * step;
+        R alpha = R(0);
+        if (!zero_out) {
+          const double ss = gv.sumsq(
+              [&](R so, R u, R xg) -> R { return so - sigma * softthres(u - step * xg, dstep2); });
+          alpha = jl_max(R(0), R(1) - sl / (R)sqrt(ss));
         }
-      }
-    } else {
-      for (long long i = gv.b + lane; i < gv.e; i += 32) y[i] = (q[i] + xk[i]) + sj[i];
-    }
-    const R sl = lam * sigma;  // σλ
-    auto cstep = [&](R nn) -> R { return nn / (sigma * (nn - sl)); };
-    auto froot = [&](R nn) -> R {  // :87-93
-      const R c = cstep(nn);
-      const R dc = delta * c;
-      const double ss =
-          gv.sumsq([&](R so, R xg) -> R { return sigma * softthres(so / sigma - c * xg, dc) - so; });
-      return nn - (R)sqrt(ss);
-    };
-    const R lmin = sl * (R(1) + eps);
-    const R fl = froot(lmin);
-    const R ansatz = lmin + R(1);
-    R step = ansatz / (sigma * (ansatz - sl));
-    const R dstep = delta * step;
-    const R zlmax = (R)sqrt(gv.sumsq([&](R so, R xg) -> R { return softthres(so / sigma - step * xg, dstep); }));
-    const R nsol = (R)sqrt(gv.sumsq([&](R so, R) -> R { return so; }));
-    const R nxk = (R)sqrt(gv.sumsq([&](R, R xg) -> R { return xg; }));
-    const R lmax = nsol + sigma * (zlmax + R(1) * lam * nxk);  // |(ϵ-1)/ϵ + 1| = 1 for ϵ = 1  (:100)
-    const R fm = froot(lmax);
-    bool zero_out = false;
-    R nroot = R(0);
-    if (fl * fm > R(0)) {
-      zero_out = true;
-    } else {
-      // fzero(froot, lmin, lmax): Roots' bisection ends on two adjacent floats
-      // around the sign change.  Same end state, fewer evaluations: Illinois
-      // regula falsi steps while they at least halve the bracket, bisection
-      // otherwise, until lo and hi are adjacent.
-      R a = lmin, fa = fl, bb = lmax, fb = fm;
-      if (fa == R(0)) {
-        nroot = a;
-      } else if (fb == R(0)) {
-        nroot = bb;
-      } else {
-        R ga = fa, gb = fb;  // Illinois-damped copies
-        int side = 0;
-        bool force_bisect = false;
-        for (int it = 0; it < 200; ++it) {
-          const R mid = a + (bb - a) / R(2);
-          if (adjacent_or_crossed(a, mid, bb)) break;
-          R x = mid;
-          if (!force_bisect) {
-            const R xs_ = (a * gb - bb * ga) / (gb - ga);
-            if ((a < xs_) && (xs_ < bb)) x = xs_;
-          }
-          const R width = bb - a;
-          const R fx = froot(x);
-          if (fx == R(0)) {
-            a = bb = x;
-            fa = fb = R(0);
-            break;
-          }
-          if ((fx < R(0)) == (fa < R(0))) {
-            a = x; fa = fx; ga = fx;
-            if (side == -1) gb = gb / R(2);
-            side = -1;
-          } else {
-            bb = x; fb = fx; gb = fx;
-            if (side == 1) ga = ga / R(2);
-            side = 1;
-          }
-          force_bisect = !((bb - a) <= width / R(2));
-          if (force_bisect) { ga = fa; gb = fb; side = 0; }
-        }
-        nroot = (jl_abs(fa) <= jl_abs(fb)) ? a : bb;
-      }
-      step = cstep(nroot);
-      if (jl_abs(nroot - sl) == R(0)) zero_out = true;  // `abs(n - σλ) ≈ 0`  (:107)
-    }
-    // y_g = l2prox(sol - σ softthres(sol/σ - step xk, Δ step), σλ) - (xk + sj)   (:109-116)
-    const R dstep2 = delta * step;
-    R alpha = R(0);
-    if (!zero_out) {
-      const double ss =
-          gv.sumsq([&](R so, R xg) -> R { return so - sigma * softthres(so / sigma - step * xg, dstep2); });
-      alpha = jl_max(R(0), R(1) - sl / (R)sqrt(ss));
-    }
-    if (gv.reg) {
-#pragma unroll
-      for (int k = 0; k < kEPL; ++k) {
-        const long long i = gv.b + k * 32 + lane;
-        if (i < gv.e) {
+        for (long long i = b + lane; i < e; i += 32) {
           R o = R(0);
-          if (!zero_out) o = alpha * (gv.sol[k] - sigma * softthres(gv.sol[k] / sigma - step * gv.xkr[k], dstep2));
-          o = o - xs[k];
-          stv(y + i, o);
+          const R so = y[i], xg = xk[i];
+          if (!zero_out) o = alpha * (so - sigma * softthres(so / sigma - step * xg, dstep2));
+          y[i] = o - (xg + sj[i]);
+        }
+#ifdef SPX_GROUP_STATS
+        if (lane == 0) atomicAdd(&g_stat_groups, 1ull);
+#endif
+        pos += 1;
+        continue;
+      }
+      Tile<R, false> t;
+      t.load(th, k, pos, lane, xk, sj, q);
+      const R lam = __shfl_sync(0xffffffffu, lam_lane, t.group_in_task(pos, k, lane) & 31);
+      TileView<R> gv{t};
+      gv.sigma = sigma;
+#pragma unroll
+      for (int j = 0; j < kEPL; ++j) gv.u[j] = by_sigma(t.sol[j]);
+      R step;
+      const bool zero_out = binf_solve<R>(gv, t.valid, lam, sigma, delta, step);
+      // y_g = l2prox(sol - σ softthres(sol/σ - step xk, Δ step), σλ) - (xk + sj)   (:109-116)
+      const R sl = lam * sigma, dstep2 = delta * step;
+      R w[kEPL];
+      double ss = 0.0;
+#pragma unroll
+      for (int j = 0; j < kEPL; ++j) {
+        w[j] = t.sol[j] - sigma * softthres(gv.u[j] - step * t.xkr[j], dstep2);
+        ss += (double)w[j] * (double)w[j];
+      }
+      ss = sub_sum(ss, t.L);
+      const R alpha = zero_out ? R(0) : jl_max(R(0), R(1) - sl / (R)sqrt_fast(ss));
+#pragma unroll
+      for (int j = 0; j < kEPL; ++j) {
+        const long long i = t.b + (long long)j * t.L + t.sub;
+        if (i < t.e) {
+          const R o = zero_out ? R(0) : alpha * w[j];
+          stv(y + i, o - (t.xkr[j] + sj[i]));
         }
       }
-    } else {
-      for (long long i = gv.b + lane; i < gv.e; i += 32) {
-        R o = R(0);
-        const R so = y[i], xg = xk[i];
-        if (!zero_out) o = alpha * (so - sigma * softthres(so / sigma - step * xg, dstep2));
-        y[i] = o - (xg + sj[i]);
-      }
+#ifdef SPX_GROUP_STATS
+      if (t.valid && t.sub == 0) atomicAdd(&g_stat_groups, 1ull);
+#endif
+      pos += 32 >> k;
     }
   }
 }
@@ -318,7 +510,8 @@ static int group_grid(spx_ctx* ctx, int64_t ngroups, const void* kernel) {
   int per_sm = 1;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kGroupThreads, 0) != cudaSuccess || per_sm < 1)
     per_sm = 1;
-  long long want = (ngroups + (kGroupThreads / 32) - 1) / (kGroupThreads / 32);
+  const long long ntasks = (ngroups + kTask - 1) / kTask;
+  long long want = (ntasks + (kGroupThreads / 32) - 1) / (kGroupThreads / 32);
   long long cap = (long long)ctx->sm_count * per_sm;
   if (cap > kMaxPartials) cap = kMaxPartials;
   if (want < 1) want = 1;
@@ -381,8 +574,10 @@ static int32_t prox_group(spx_ctx* ctx, bool binf, int64_t n, R* y, const R* xk,
       return SPX_OK;
     }
     const int grid = group_grid(ctx, ngroups, (const void*)group_l2binf_kernel<R>);
+    UDiv<R> by_sigma;
+    by_sigma.set((R)sigma);
     group_l2binf_kernel<R><<<grid, kGroupThreads, 0, ctx->stream>>>(
-        y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, (R)sigma, (R)delta);
+        y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, (R)sigma, (R)delta, by_sigma);
     ctx->launches++;
     SPX_CUDA(cudaGetLastError());
   }
@@ -400,6 +595,19 @@ static int32_t prox_group(spx_ctx* ctx, bool binf, int64_t n, R* y, const R* xk,
 }  // namespace spx
 
 using namespace spx;
+
+#ifdef SPX_GROUP_STATS
+extern "C" int32_t spx_debug_group_stats(unsigned long long* out2, int reset) {
+  cudaMemcpyFromSymbol(out2, g_stat_evals, 8);
+  cudaMemcpyFromSymbol(out2 + 1, g_stat_groups, 8);
+  if (reset) {
+    unsigned long long z = 0;
+    cudaMemcpyToSymbol(g_stat_evals, &z, 8);
+    cudaMemcpyToSymbol(g_stat_groups, &z, 8);
+  }
+  return 0;
+}
+#endif
 
 #define SPX_DEFINE_GROUP(SUF, R)                                                                                 \
   extern "C" int32_t spx_prox_groupl2_##SUF(spx_ctx* ctx, int64_t n, R* y, const R* xk, const R* sj, const R* q, \
