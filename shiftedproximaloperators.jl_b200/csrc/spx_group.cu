@@ -227,45 +227,56 @@ __global__ void __launch_bounds__(kGroupThreads)
 // --------------------------------------------------- ShiftedGroupNormL2Binf --
 // shiftedGroupNormL2Binf.jl:67-119.  The views give the root search Σ f(sol_i, sol_i/σ, xk_i)² over
 // the lane's group: from registers (a round of short groups) or from the stash (a long group).
-// One element of froot's sum: (σ softthres(u - c xk, Δc) - sol)², softthres written out so that the
-// thresholded case costs a select (fused multiply-adds are fine here: the search only needs the sign
-// change of froot, whose rounding noise differs between any two summation orders anyway).
-__device__ __forceinline__ double froot_term(double so, double u, double xg, double c, double dc, double sigma,
-                                             double ss) {
-  const double t = __fma_rn(-c, xg, u);
-  const double a = fabs(t) - dc;
-  const double z = __fma_rn(sigma, copysign(a, t), -so);
-  const double w = a > 0.0 ? z : so;
-  return __fma_rn(w, w, ss);
+// One element of froot's sum, (σ softthres(sol/σ - c xk, Δc) - sol)², in the equivalent form
+// (S(sol - σc xk, σΔc) - sol)², S the soft threshold: no division, and the thresholded case is a
+// select.  Fused multiply-adds are fine here: the search only needs the sign change of froot, whose
+// rounding noise differs between any two summation orders anyway.
+// Also accumulates Σ w_i dw_i/d(σc) (dw/d(σc) = -xk - Δ sign(t) on the entries the threshold keeps, 0 on the
+// others), which gives froot'(n) for the Newton steps of the search.
+__device__ __forceinline__ void froot_term(double so, double xg, double sc, double sdc, double delta, double& ss,
+                                           double& dot) {
+  const double t = __fma_rn(-sc, xg, so);
+  const double a = fabs(t) - sdc;
+  const double z = copysign(a, t) - so;
+  const bool act = a > 0.0;
+  const double w = act ? z : so;
+  const double dw = act ? (-xg - copysign(delta, t)) : 0.0;
+  ss = __fma_rn(w, w, ss);
+  dot = __fma_rn(w, dw, dot);
 }
-__device__ __forceinline__ double froot_term(float so, float u, float xg, float c, float dc, float sigma, double ss) {
-  const float t = fmaf(-c, xg, u);
-  const float a = fabsf(t) - dc;
-  const float z = fmaf(sigma, copysignf(a, t), -so);
-  const double w = (double)(a > 0.0f ? z : so);
-  return __fma_rn(w, w, ss);
+__device__ __forceinline__ void froot_term(float so, float xg, float sc, float sdc, float delta, double& ss,
+                                           double& dot) {
+  const float t = fmaf(-sc, xg, so);
+  const float a = fabsf(t) - sdc;
+  const float z = copysignf(a, t) - so;
+  const bool act = a > 0.0f;
+  const double w = (double)(act ? z : so);
+  const double dw = (double)(act ? (-xg - copysignf(delta, t)) : 0.0f);
+  ss = __fma_rn(w, w, ss);
+  dot = __fma_rn(w, dw, dot);
 }
 
 template <class R> struct TileView {
   const Tile<R, false>& t;
-  R u[kEPL];  // sol / σ
-  R sigma;
+  UDiv<R> by_sigma;
+  // Σ f(sol_i, sol_i/σ, xk_i)² over the lane's group
   template <class F> __device__ __forceinline__ double sumsq(F f) const {
     double ss = 0.0;
 #pragma unroll
     for (int j = 0; j < kEPL; ++j) {
-      const double w = (double)f(t.sol[j], u[j], t.xkr[j]);
+      const double w = (double)f(t.sol[j], by_sigma(t.sol[j]), t.xkr[j]);
       ss = __fma_rn(w, w, ss);
     }
     return sub_sum(ss, t.L);
   }
-  __device__ __forceinline__ double froot_sum(R c, R dc) const {
-    double s0 = 0.0, s1 = 0.0;
+  __device__ __forceinline__ double froot_sum(R sc, R sdc, R delta, double& dot) const {
+    double s0 = 0.0, s1 = 0.0, d0 = 0.0, d1 = 0.0;
 #pragma unroll
     for (int j = 0; j < kEPL; j += 2) {
-      s0 = froot_term(t.sol[j], u[j], t.xkr[j], c, dc, sigma, s0);
-      s1 = froot_term(t.sol[j + 1], u[j + 1], t.xkr[j + 1], c, dc, sigma, s1);
+      froot_term(t.sol[j], t.xkr[j], sc, sdc, delta, s0, d0);
+      froot_term(t.sol[j + 1], t.xkr[j + 1], sc, sdc, delta, s1, d1);
     }
+    dot = sub_sum(d0 + d1, t.L);
     return sub_sum(s0 + s1, t.L);
   }
 };
@@ -274,23 +285,42 @@ template <class R> struct LongView {
   const R* xk;
   long long b, e;
   int lane;
-  R sigma;
+  UDiv<R> by_sigma;
   template <class F> __device__ __forceinline__ double sumsq(F f) const {
     double ss = 0.0;
-    for (long long i = b + lane; i < e; i += 32) {
-      const R so = ysol[i];
-      const double w = (double)f(so, so / sigma, xk[i]);
-      ss = __fma_rn(w, w, ss);
+    for (long long i0 = b + lane; i0 < e; i0 += 128) {
+      R so[4], xg[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long i = i0 + 32 * u;
+        so[u] = i < e ? ysol[i] : R(0);
+        xg[u] = i < e ? xk[i] : R(0);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const double w = (i0 + 32 * u < e) ? (double)f(so[u], by_sigma(so[u]), xg[u]) : 0.0;
+        ss = __fma_rn(w, w, ss);
+      }
     }
     return warp_sum(ss);
   }
-  __device__ __forceinline__ double froot_sum(R c, R dc) const {
-    double ss = 0.0;
-    for (long long i = b + lane; i < e; i += 32) {
-      const R so = ysol[i];
-      ss = froot_term(so, so / sigma, xk[i], c, dc, sigma, ss);
+  __device__ __forceinline__ double froot_sum(R sc, R sdc, R delta, double& dot) const {
+    double s0 = 0.0, s1 = 0.0, d0 = 0.0, d1 = 0.0;
+    for (long long i0 = b + lane; i0 < e; i0 += 128) {
+      R so[4], xg[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long i = i0 + 32 * u;
+        so[u] = i < e ? ysol[i] : R(0);  // zeros add nothing
+        xg[u] = i < e ? xk[i] : R(0);
+      }
+      froot_term(so[0], xg[0], sc, sdc, delta, s0, d0);
+      froot_term(so[1], xg[1], sc, sdc, delta, s1, d1);
+      froot_term(so[2], xg[2], sc, sdc, delta, s0, d0);
+      froot_term(so[3], xg[3], sc, sdc, delta, s1, d1);
     }
-    return warp_sum(ss);
+    dot = warp_sum(d0 + d1);
+    return warp_sum(s0 + s1);
   }
 };
 
@@ -306,22 +336,30 @@ __device__ __forceinline__ float ulp_step(float x, int k) { return __int_as_floa
 // copies of its state).  Returns the step c(n*) and whether the group's prox is zero.
 //
 // fzero(froot, lmin, lmax) (Roots' bisection) ends on two adjacent floats around the sign change of
-// froot.  Same end state, an order of magnitude fewer evaluations: Illinois regula falsi (superlinear,
-// both ends move), and as soon as the interpolated point falls within a few ulps of an end of the
-// bracket the next evaluation is placed k ulps inside that end -- stepping over the root, which leaves a
-// bracket of k ulps that two or three midpoint steps close.  After 60 steps (never observed) it
-// degrades to plain bisection, which terminates by itself.
+// froot.  Same end state, an order of magnitude fewer evaluations: froot is smooth between the kinks of
+// the soft threshold and nearly linear above the root, so safeguarded Newton steps from lmax (the
+// derivative comes out of the same pass over the group) converge in three or four evaluations; as soon
+// as a step lands within a few ulps of an end of the bracket the next evaluation is placed k ulps inside
+// that end -- stepping over the root, which leaves a bracket of k ulps that two or three midpoint steps
+// close.  A step that leaves the bracket is replaced by the midpoint, and after 40 steps (never
+// observed) the search degrades to plain bisection, which terminates by itself.
 template <class R, class View>
 __device__ __forceinline__ bool binf_solve(const View& gv, bool valid, R lam, R sigma, R delta, R& step_out) {
   const R eps = Eps<R>::value;
   const R sl = lam * sigma;  // σλ
+  R dfx;                     // froot'(n) of the last evaluation
   auto froot = [&](R nn) -> R {  // :87-93
-    const R c = div_fast(nn, sigma * (nn - sl));
-    const double ss = gv.froot_sum(c, delta * c);
+    const R gap = nn - sl;
+    const R sc = div_fast(nn, gap);  // σ c(n)
+    double dot;
+    const double ss = gv.froot_sum(sc, delta * sc, delta, dot);
 #ifdef SPX_GROUP_STATS
     if ((threadIdx.x & 31) == 0) atomicAdd(&g_stat_evals, 1ull);
 #endif
-    return nn - (R)sqrt_fast(ss);
+    const R nw = (R)sqrt_fast(ss);
+    // d‖w‖/dn = (w·dw/d(σc)) / ‖w‖ · d(σc)/dn,  d(σc)/dn = -σλ / (n - σλ)²
+    dfx = R(1) + div_fast((R)dot * sl, nw * (gap * gap));
+    return nn - nw;
   };
   const R lmin = sl * (R(1) + eps);
   const R fl = froot(lmin);
@@ -338,47 +376,42 @@ __device__ __forceinline__ bool binf_solve(const View& gv, bool valid, R lam, R 
   bool done = !valid || zero_out || (fl != fl) || (fm != fm) || !(lmin > R(0));
   if (!done && fa == R(0)) { bb = a; fb = R(0); done = true; }
   if (!done && fb == R(0)) { a = bb; fa = R(0); done = true; }
-  // Interpolation runs on g(n) = froot(n) (n - σλ): c(n) has a pole at n = σλ, which froot inherits
-  // (it behaves like -K/(n - σλ) next to lmin); g has the same sign as froot on the bracket and no pole.
-  R ga = fa * (a - sl), gb = fb * (bb - sl);  // Illinois-damped copies
-  int side = 0, kulp = 4, slow = 0;
+  R x = lmax, fx = fm, dx = dfx;  // Newton state
+  int kulp = 4;
   for (int it = 0; it < 400; ++it) {
     const R mid = a + (bb - a) / R(2);
     done = done || adjacent_or_crossed(a, mid, bb);
     if (!__any_sync(0xffffffffu, !done)) break;
-    R x = mid;
+    R xn = mid;
     bool probed = false;
-    if (it < 80 && slow < 2) {
-      const R xs_ = div_fast(a * gb - bb * ga, gb - ga);
-      if ((a < xs_) && (xs_ < bb)) x = xs_;
+    if (it < 40) {
+      const R xs_ = x - div_fast(fx, dx);
+      if ((a < xs_) && (xs_ < bb)) xn = xs_;
       const R a_k = ulp_step(a, kulp), b_k = ulp_step(bb, -kulp);
-      if (x <= a_k) {
-        x = (a_k < mid) ? a_k : mid;
+      if (xn <= a_k) {
+        xn = (a_k < mid) ? a_k : mid;
         probed = true;
-      } else if (x >= b_k) {
-        x = (b_k > mid) ? b_k : mid;
+      } else if (xn >= b_k) {
+        xn = (b_k > mid) ? b_k : mid;
         probed = true;
       }
     }
-    const R width = bb - a;
-    const R fx = froot(x);
+    const R fn = froot(xn);
     if (!done) {
-      const R gx = fx * (x - sl);
-      const bool same_as_a = (fx < R(0)) == (fa < R(0));
-      if (fx == R(0)) {
-        a = bb = x;
+      x = xn;
+      fx = fn;
+      dx = dfx;
+      if (fn == R(0)) {
+        a = bb = xn;
         fa = fb = R(0);
         done = true;
-      } else if (same_as_a) {
-        a = x; fa = fx; ga = gx;
-        if (side == -1) gb = gb / R(2);
-        side = -1;
+      } else if ((fn < R(0)) == (fa < R(0))) {
+        a = xn;
+        fa = fn;
       } else {
-        bb = x; fb = fx; gb = gx;
-        if (side == 1) ga = ga / R(2);
-        side = 1;
+        bb = xn;
+        fb = fn;
       }
-      slow = ((bb - a) <= width / R(2)) ? 0 : slow + 1;
       if (probed) kulp = kulp < (1 << 20) ? kulp * 4 : kulp;
     }
   }
@@ -410,8 +443,18 @@ __global__ void __launch_bounds__(kGroupThreads, 2)
       if (k < 0) {  // long group: the whole warp, sol stashed in y
         const long long b = __shfl_sync(0xffffffffu, th.lo, pos), e = __shfl_sync(0xffffffffu, th.hi, pos);
         const R lam = __shfl_sync(0xffffffffu, lam_lane, pos);
-        for (long long i = b + lane; i < e; i += 32) y[i] = (q[i] + xk[i]) + sj[i];  // :80
-        LongView<R> gv{y, xk, b, e, lane, sigma};
+        for (long long i0 = b + lane; i0 < e; i0 += 128) {  // :80, loads batched (y may alias q)
+          R s4[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const long long i = i0 + 32 * u;
+            if (i < e) s4[u] = (ldv(q + i) + ldv(xk + i)) + ldv(sj + i);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (i0 + 32 * u < e) y[i0 + 32 * u] = s4[u];
+        }
+        LongView<R> gv{y, xk, b, e, lane, by_sigma};
         R step;
         const bool zero_out = binf_solve<R>(gv, true, lam, sigma, delta, step);
         const R sl = lam * sigma, dstep2 = delta * step;
@@ -436,10 +479,7 @@ __global__ void __launch_bounds__(kGroupThreads, 2)
       Tile<R, false> t;
       t.load(th, k, pos, lane, xk, sj, q);
       const R lam = __shfl_sync(0xffffffffu, lam_lane, t.group_in_task(pos, k, lane) & 31);
-      TileView<R> gv{t};
-      gv.sigma = sigma;
-#pragma unroll
-      for (int j = 0; j < kEPL; ++j) gv.u[j] = by_sigma(t.sol[j]);
+      TileView<R> gv{t, by_sigma};
       R step;
       const bool zero_out = binf_solve<R>(gv, t.valid, lam, sigma, delta, step);
       // y_g = l2prox(sol - σ softthres(sol/σ - step xk, Δ step), σλ) - (xk + sj)   (:109-116)
@@ -448,7 +488,7 @@ __global__ void __launch_bounds__(kGroupThreads, 2)
       double ss = 0.0;
 #pragma unroll
       for (int j = 0; j < kEPL; ++j) {
-        w[j] = t.sol[j] - sigma * softthres(gv.u[j] - step * t.xkr[j], dstep2);
+        w[j] = t.sol[j] - sigma * softthres(by_sigma(t.sol[j]) - step * t.xkr[j], dstep2);
         ss += (double)w[j] * (double)w[j];
       }
       ss = sub_sum(ss, t.L);
