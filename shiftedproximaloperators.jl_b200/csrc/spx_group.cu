@@ -37,6 +37,16 @@ template <class R> __device__ __forceinline__ void stv(R* p, R v) {
 template <class R> __device__ __forceinline__ R softthres(R x, R a) {
   return jl_sign(x) * jl_max(R(0), jl_abs(x) - a);
 }
+// bit-identical to the reference form, NaNs included (`!(a <= 0)` keeps a NaN threshold excess):
+// sign(±0) max(0, -a) = ±0 = copysign(0, ±0), sign(NaN) = NaN = copysign(NaN, NaN)
+__device__ __forceinline__ double softthres_sel(double x, double a) {
+  const double ex = fabs(x) - a;
+  return copysign(!(ex <= 0.0) ? ex : 0.0, x);
+}
+__device__ __forceinline__ float softthres_sel(float x, float a) {
+  const float ex = fabsf(x) - a;
+  return copysignf(!(ex <= 0.0f) ? ex : 0.0f, x);
+}
 // same value for non-NaN operands, three instructions (used inside the root search only)
 __device__ __forceinline__ double softthres_fast(double x, double a) { return copysign(fmax(fabs(x) - a, 0.0), x); }
 __device__ __forceinline__ float softthres_fast(float x, float a) { return copysignf(fmaxf(fabsf(x) - a, 0.0f), x); }
@@ -56,7 +66,25 @@ __device__ __forceinline__ double div_fast(double a, double b) {
 }
 __device__ __forceinline__ float div_fast(float a, float b) { return a / b; }
 
-// sum over the L lanes of a group (L a power of two, lanes aligned); every lane gets the total
+// sum over the L lanes of a group (L a power of two, lanes aligned); every lane gets the total.
+// L is uniform over the warp: the switch is a uniform branch into a fully unrolled butterfly.
+template <int L> __device__ __forceinline__ void sub_sum_t(double& v, double& w) {
+#pragma unroll
+  for (int o = L >> 1; o > 0; o >>= 1) {
+    v += __shfl_xor_sync(0xffffffffu, v, o);
+    w += __shfl_xor_sync(0xffffffffu, w, o);
+  }
+}
+__device__ __forceinline__ void sub_sum2(double& v, double& w, int L) {
+  switch (L) {
+    case 32: sub_sum_t<32>(v, w); break;
+    case 16: sub_sum_t<16>(v, w); break;
+    case 8: sub_sum_t<8>(v, w); break;
+    case 4: sub_sum_t<4>(v, w); break;
+    case 2: sub_sum_t<2>(v, w); break;
+    default: break;
+  }
+}
 __device__ __forceinline__ double sub_sum(double v, int L) {
   for (int o = L >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
@@ -269,6 +297,18 @@ template <class R> struct TileView {
     }
     return sub_sum(ss, t.L);
   }
+  // Σ softthres(sol/σ - step xk, Δ step)², Σ sol², Σ xk²
+  __device__ __forceinline__ void norms(R step, R dstep, double& z2, double& s2, double& x2) const {
+#pragma unroll
+    for (int j = 0; j < kEPL; ++j) {
+      const double z = (double)softthres_fast(by_sigma(t.sol[j]) - step * t.xkr[j], dstep);
+      z2 = __fma_rn(z, z, z2);
+      s2 = __fma_rn((double)t.sol[j], (double)t.sol[j], s2);
+      x2 = __fma_rn((double)t.xkr[j], (double)t.xkr[j], x2);
+    }
+    sub_sum2(z2, s2, t.L);
+    x2 = sub_sum(x2, t.L);
+  }
   __device__ __forceinline__ double froot_sum(R sc, R sdc, R delta, double& dot) const {
     double s0 = 0.0, s1 = 0.0, d0 = 0.0, d1 = 0.0;
 #pragma unroll
@@ -276,8 +316,10 @@ template <class R> struct TileView {
       froot_term(t.sol[j], t.xkr[j], sc, sdc, delta, s0, d0);
       froot_term(t.sol[j + 1], t.xkr[j + 1], sc, sdc, delta, s1, d1);
     }
-    dot = sub_sum(d0 + d1, t.L);
-    return sub_sum(s0 + s1, t.L);
+    double ss = s0 + s1;
+    dot = d0 + d1;
+    sub_sum2(ss, dot, t.L);
+    return ss;
   }
 };
 template <class R> struct LongView {
@@ -303,6 +345,11 @@ template <class R> struct LongView {
       }
     }
     return warp_sum(ss);
+  }
+  __device__ __forceinline__ void norms(R step, R dstep, double& z2, double& s2, double& x2) const {
+    z2 = sumsq([&](R, R u, R xg) -> R { return softthres_fast(u - step * xg, dstep); });
+    s2 = sumsq([&](R so, R, R) -> R { return so; });
+    x2 = sumsq([&](R, R, R xg) -> R { return xg; });
   }
   __device__ __forceinline__ double froot_sum(R sc, R sdc, R delta, double& dot) const {
     double s0 = 0.0, s1 = 0.0, d0 = 0.0, d1 = 0.0;
@@ -362,42 +409,55 @@ __device__ __forceinline__ bool binf_solve(const View& gv, bool valid, R lam, R 
     return nn - nw;
   };
   const R lmin = sl * (R(1) + eps);
-  const R fl = froot(lmin);
   const R ansatz = lmin + R(1);
   R step = ansatz / (sigma * (ansatz - sl));
   const R dstep = delta * step;
-  const R zlmax = (R)sqrt_fast(gv.sumsq([&](R, R u, R xg) -> R { return softthres_fast(u - step * xg, dstep); }));
-  const R nsol = (R)sqrt_fast(gv.sumsq([&](R so, R, R) -> R { return so; }));
-  const R nxk = (R)sqrt_fast(gv.sumsq([&](R, R, R xg) -> R { return xg; }));
+  // the three norms of :97-100 in one pass
+  double z2 = 0.0, s2 = 0.0, x2 = 0.0;
+  gv.norms(step, dstep, z2, s2, x2);
+  const R zlmax = (R)sqrt_fast(z2), nsol = (R)sqrt_fast(s2), nxk = (R)sqrt_fast(x2);
   const R lmax = nsol + sigma * (zlmax + R(1) * lam * nxk);  // |(ϵ-1)/ϵ + 1| = 1 for ϵ = 1  (:100)
-  const R fm = froot(lmax);
-  bool zero_out = fl * fm > R(0);
-  R a = lmin, fa = fl, bb = lmax, fb = fm;
-  bool done = !valid || zero_out || (fl != fl) || (fm != fm) || !(lmin > R(0));
-  if (!done && fa == R(0)) { bb = a; fb = R(0); done = true; }
-  if (!done && fb == R(0)) { a = bb; fa = R(0); done = true; }
-  R x = lmax, fx = fm, dx = dfx;  // Newton state
+  // One froot call site (the kernel is instruction-cache bound otherwise): trips 0 and 1 evaluate the two
+  // ends of the bracket, the following ones are the search.
+  R a = lmin, fa = R(0), bb = lmax, fb = R(0);
+  R x = lmax, fx = R(0), dx = R(1);  // Newton state
+  bool zero_out = false, done = !valid || !(lmin > R(0));
   int kulp = 4;
-  for (int it = 0; it < 400; ++it) {
-    const R mid = a + (bb - a) / R(2);
-    done = done || adjacent_or_crossed(a, mid, bb);
-    if (!__any_sync(0xffffffffu, !done)) break;
-    R xn = mid;
+  for (int it = -2; it < 400; ++it) {
+    R xn;
     bool probed = false;
-    if (it < 40) {
-      const R xs_ = x - div_fast(fx, dx);
-      if ((a < xs_) && (xs_ < bb)) xn = xs_;
-      const R a_k = ulp_step(a, kulp), b_k = ulp_step(bb, -kulp);
-      if (xn <= a_k) {
-        xn = (a_k < mid) ? a_k : mid;
-        probed = true;
-      } else if (xn >= b_k) {
-        xn = (b_k > mid) ? b_k : mid;
-        probed = true;
+    if (it < 0) {
+      xn = (it == -2) ? lmin : lmax;
+    } else {
+      const R mid = a + (bb - a) / R(2);
+      done = done || adjacent_or_crossed(a, mid, bb);
+      if (!__any_sync(0xffffffffu, !done)) break;
+      xn = mid;
+      if (it < 40) {
+        const R xs_ = x - div_fast(fx, dx);
+        if ((a < xs_) && (xs_ < bb)) xn = xs_;
+        const R a_k = ulp_step(a, kulp), b_k = ulp_step(bb, -kulp);
+        if (xn <= a_k) {
+          xn = (a_k < mid) ? a_k : mid;
+          probed = true;
+        } else if (xn >= b_k) {
+          xn = (b_k > mid) ? b_k : mid;
+          probed = true;
+        }
       }
     }
     const R fn = froot(xn);
-    if (!done) {
+    if (it == -2) {
+      fa = fn;
+    } else if (it == -1) {
+      fb = fn;
+      fx = fn;
+      dx = dfx;
+      zero_out = fa * fb > R(0);
+      done = done || zero_out || (fa != fa) || (fb != fb);
+      if (!done && fa == R(0)) { bb = a; fb = R(0); done = true; }
+      if (!done && fb == R(0)) { a = bb; fa = R(0); done = true; }
+    } else if (!done) {
       x = xn;
       fx = fn;
       dx = dfx;
@@ -424,8 +484,11 @@ __device__ __forceinline__ bool binf_solve(const View& gv, bool valid, R lam, R 
   return zero_out;
 }
 
+#ifndef SPX_GB_MINB
+#define SPX_GB_MINB 3
+#endif
 template <class R>
-__global__ void __launch_bounds__(kGroupThreads, 2)
+__global__ void __launch_bounds__(kGroupThreads, SPX_GB_MINB)
     group_l2binf_kernel(R* y, const R* xk, const R* sj, const R* q, long long ngroups,
                         const long long* __restrict__ offs, const R* __restrict__ lambda_g, R sigma, R delta,
                         UDiv<R> by_sigma) {
@@ -488,7 +551,7 @@ __global__ void __launch_bounds__(kGroupThreads, 2)
       double ss = 0.0;
 #pragma unroll
       for (int j = 0; j < kEPL; ++j) {
-        w[j] = t.sol[j] - sigma * softthres(by_sigma(t.sol[j]) - step * t.xkr[j], dstep2);
+        w[j] = t.sol[j] - sigma * softthres_sel(by_sigma(t.sol[j]) - step * t.xkr[j], dstep2);
         ss += (double)w[j] * (double)w[j];
       }
       ss = sub_sum(ss, t.L);
