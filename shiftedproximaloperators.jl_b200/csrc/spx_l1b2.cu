@@ -4,15 +4,18 @@
 //   if Δ <= χ(y):  η = root of η - χ(ProjB(-xk η/Δ));  y = ProjB(-xk η/Δ) Δ/η
 //   y -= sj
 //
-// Every evaluation of the residual is a full streaming pass over xk, sj, q (3R
-// per element, nothing written), so the pass count is what matters.  One pass
-// evaluates up to 16 trial values of η at once (the pass is HBM-bound; the
-// extra clamps and squares are free), which turns Roots' one-point-per-pass
-// iteration into a 17-section / secant-clustered search: the bracket reaches
-// two adjacent floats in a handful of passes.  When the vector is sharded over
-// several GPUs the K partial sums are all-reduced by the caller's callback
-// between passes; the scalar search itself is replicated on every rank.
+// Every evaluation of the residual is a full streaming pass over xk, sj, q (3R per element, nothing
+// written), so the pass count is what matters.  A pass evaluates up to 8 trial values of η at once and
+// returns, next to Σw², the sum Σ w dw/dη that gives the derivative of the residual (the pass stays
+// HBM-bound: ~12 instructions per trial).  Roots' one-point-per-pass iteration becomes a safeguarded
+// Newton / secant search whose bracket closes superlinearly from both sides: the residual at η = Δ comes
+// from the very pass that decides whether the ball is active, a Newton step from there brackets the
+// root, each further pass evaluates the secant point and the Newton points of both ends, and the last
+// pass evaluates every float left inside the bracket.  End state as Roots' bisection: two adjacent floats
+// around the sign change.  When the vector is sharded over several GPUs the partial sums are all-reduced
+// by the caller's callback between passes; the scalar search itself is replicated on every rank.
 #include <algorithm>
+#include <cstring>
 #include <vector>
 
 #include "spx_elementwise.cuh"
@@ -22,27 +25,61 @@ namespace spx {
 
 template <int K> struct ScaleSet { double s[K]; };
 
-// Σ_i ProjB(z_i(k))^2 for K scalings in one pass
+// Σ_i ProjB(z_i(k))² and Σ_i ProjB(z_i(k)) dProjB/dscale (= Σ over the unclamped entries of z_i (-xk_i))
+// for K scalings in one pass.  The clamp is two compares and selects (a NaN z stays NaN; a NaN bound is
+// caught by the `mid - mid` poison term, so a NaN anywhere still makes every norm NaN like Base.min/max).
 template <class R, int K, int VEC>
 __global__ void __launch_bounds__(kEwThreads)
     l1b2_norm_kernel(const R* xk, const R* sj, const R* q, long long n, R ls, bool use_scale, ScaleSet<K> sc,
                      int nblocks_stride, Partial* __restrict__ partials) {
-  double acc[K];
+  double acc[K], dot[K];
 #pragma unroll
-  for (int k = 0; k < K; ++k) acc[k] = 0.0;
+  for (int k = 0; k < K; ++k) { acc[k] = 0.0; dot[k] = 0.0; }
+  double poison = 0.0;
   R scale[K];
 #pragma unroll
   for (int k = 0; k < K; ++k) scale[k] = (R)sc.s[k];
   const long long nvec = n / VEC;
-  auto body = [&](R x, R s, R qq) {
-    const R mid = s + qq;
-    const R lo = mid - ls, hi = mid + ls;
-    const R nx = -x;
+  // one packet of VEC elements: products summed in R over the packet (4 terms for Float32: conversions to
+  // Float64 are quarter-rate, one per packet and trial instead of two per element), then added in Float64
+  auto packet = [&](const R* x, const R* s, const R* qq, int m) {
+    R lo[VEC], hi[VEC], nx[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      const bool on = e < m;
+      const R mid = on ? s[e] + qq[e] : R(0);
+      lo[e] = mid - ls;
+      hi[e] = mid + ls;
+      nx[e] = on ? -x[e] : R(0);
+      poison += (double)(mid - mid);
+      if (!on) { lo[e] = R(0); hi[e] = R(0); }
+    }
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-      const R z = use_scale ? nx * scale[k] : nx;
-      const double w = (double)jl_min(jl_max(z, lo), hi);
-      acc[k] += w * w;
+      if (sizeof(R) == 8) {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+          const R z = use_scale ? nx[e] * scale[k] : nx[e];
+          const bool below = z < lo[e], above = z > hi[e];
+          const R w = below ? lo[e] : (above ? hi[e] : z);
+          const R dw = (below || above) ? R(0) : nx[e];
+          acc[k] = __fma_rn((double)w, (double)w, acc[k]);
+          dot[k] = __fma_rn((double)w, (double)dw, dot[k]);
+        }
+      } else {
+        float pa = 0.0f, pd = 0.0f;
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+          const float z = use_scale ? (float)nx[e] * (float)scale[k] : (float)nx[e];
+          const bool below = z < (float)lo[e], above = z > (float)hi[e];
+          const float w = below ? (float)lo[e] : (above ? (float)hi[e] : z);
+          const float dw = (below || above) ? 0.0f : (float)nx[e];
+          pa = fmaf(w, w, pa);
+          pd = fmaf(w, dw, pd);
+        }
+        acc[k] += (double)pa;
+        dot[k] += (double)pd;
+      }
     }
   };
   for (long long v = (long long)blockIdx.x * kEwThreads + threadIdx.x; v < nvec; v += (long long)gridDim.x * kEwThreads) {
@@ -50,18 +87,20 @@ __global__ void __launch_bounds__(kEwThreads)
     ld_stream(xk + v * VEC, a);
     ld_stream(sj + v * VEC, b);
     ld_stream(q + v * VEC, c);
-#pragma unroll
-    for (int e = 0; e < VEC; ++e) body(a.v[e], b.v[e], c.v[e]);
+    packet(a.v, b.v, c.v, VEC);
   }
   if (VEC > 1 && blockIdx.x == gridDim.x - 1) {
     const long long i = nvec * VEC + threadIdx.x;
-    if (i < n) body(xk[i], sj[i], q[i]);
+    if (i < n) {
+      R x1[VEC] = {xk[i]}, s1[VEC] = {sj[i]}, q1[VEC] = {q[i]};
+      packet(x1, s1, q1, 1);
+    }
   }
 #pragma unroll
   for (int k = 0; k < K; ++k) {
     Partial p;
-    p.s = 0.0;
-    p.s2 = acc[k];
+    p.s = dot[k];
+    p.s2 = acc[k] + poison;
     p.bad = -1;
     p = block_fold<kEwThreads>(p);
     if (threadIdx.x == 0) partials[(size_t)k * nblocks_stride + blockIdx.x] = p;
@@ -70,7 +109,7 @@ __global__ void __launch_bounds__(kEwThreads)
 
 template <class R, int K>
 static int32_t norm_pass_k(spx_ctx* ctx, int64_t n, const R* xk, const R* sj, const R* q, R ls, const double* scale,
-                           int nscale, double* out) {
+                           int nscale, double* out, double* dot_out) {
   ScaleSet<K> sc;
   for (int k = 0; k < K; ++k) sc.s[k] = scale ? scale[k < nscale ? k : nscale - 1] : 1.0;
   const uintptr_t bits = (uintptr_t)xk | (uintptr_t)sj | (uintptr_t)q;
@@ -79,7 +118,7 @@ static int32_t norm_pass_k(spx_ctx* ctx, int64_t n, const R* xk, const R* sj, co
   const long long nv = vec ? n / VECW : n;
   long long want = (nv + kEwThreads - 1) / kEwThreads;
   if (want < 1) want = 1;
-  long long cap = (long long)ctx->sm_count * 4;
+  long long cap = (long long)ctx->sm_count * 8;
   const int grid = (int)(want < cap ? want : cap);
   if (vec)
     l1b2_norm_kernel<R, K, VECW><<<grid, kEwThreads, 0, ctx->stream>>>(xk, sj, q, n, ls, scale != nullptr, sc, grid,
@@ -92,19 +131,24 @@ static int32_t norm_pass_k(spx_ctx* ctx, int64_t n, const R* xk, const R* sj, co
   int32_t st = finalize_partials(ctx, grid, K, false);
   if (st != SPX_OK) return st;
   for (int k = 0; k < nscale; ++k) out[k] = ctx->h_result[k].s2;
+  if (dot_out)
+    for (int k = 0; k < nscale; ++k) dot_out[k] = ctx->h_result[k].s;
   return SPX_OK;
 }
 
 template <class R>
 static int32_t norm_pass(spx_ctx* ctx, int64_t n, const R* xk, const R* sj, const R* q, R ls, const double* scale,
-                         int nscale, double* out) {
+                         int nscale, double* out, double* dot_out = nullptr) {
   if (n == 0) {
     for (int k = 0; k < nscale; ++k) out[k] = 0.0;
+    if (dot_out)
+      for (int k = 0; k < nscale; ++k) dot_out[k] = 0.0;
     return SPX_OK;
   }
-  if (nscale <= 1) return norm_pass_k<R, 1>(ctx, n, xk, sj, q, ls, scale, nscale, out);
-  if (nscale <= 8) return norm_pass_k<R, 8>(ctx, n, xk, sj, q, ls, scale, nscale, out);
-  return norm_pass_k<R, 16>(ctx, n, xk, sj, q, ls, scale, nscale, out);
+  if (nscale <= 1) return norm_pass_k<R, 1>(ctx, n, xk, sj, q, ls, scale, nscale, out, dot_out);
+  if (nscale <= 4) return norm_pass_k<R, 4>(ctx, n, xk, sj, q, ls, scale, nscale, out, dot_out);
+  if (nscale <= 8) return norm_pass_k<R, 8>(ctx, n, xk, sj, q, ls, scale, nscale, out, dot_out);
+  return norm_pass_k<R, 16>(ctx, n, xk, sj, q, ls, scale, nscale, out, dot_out);
 }
 
 // y = ProjB(-xk scale) post - sj, with Σ|xk+sj+y| and Σ(sj+y)² for ψ(y)
@@ -179,23 +223,29 @@ static int32_t prox_l1b2(spx_ctx* ctx, int64_t n, R* y, const R* xk, const R* sj
   const R lam = (R)lambda_, sig = (R)sigma_, delta = (R)delta_, chil = (R)chi_lambda_;
   const R ls = lam * sig;
   int passes = 0;
-  // K residuals per pass: f_k = η_k - χ(ProjB(-xk η_k/Δ))
-  auto eval = [&](const std::vector<R>& etas, bool use_scale, std::vector<R>& f) -> int32_t {
+  // K residuals per pass: f_k = η_k - χ(ProjB(-xk η_k/Δ)) and their derivatives
+  // f'_k = 1 - χ (Σ w dw/dscale) / (‖w‖ Δ)
+  auto eval = [&](const std::vector<R>& etas, bool use_scale, std::vector<R>& f, std::vector<R>& df) -> int32_t {
     const int m = (int)etas.size();
-    double scale[kMaxScale], ss[kMaxScale];
+    double scale[kMaxScale], ss[2 * kMaxScale];
     for (int k = 0; k < m; ++k) scale[k] = (double)(etas[k] / delta);
-    int32_t st = norm_pass<R>(ctx, n, xk, sj, q, ls, use_scale ? scale : nullptr, m, ss);
+    int32_t st = norm_pass<R>(ctx, n, xk, sj, q, ls, use_scale ? scale : nullptr, m, ss, ss + m);
     if (st != SPX_OK) return st;
     ++passes;
     if (reduce) {
-      st = reduce(user, ss, m);
+      st = reduce(user, ss, 2 * m);
       if (st != SPX_OK) {
         set_error("spx_prox_l1b2: all-reduce callback failed (%d)", (int)st);
         return st;
       }
     }
     f.resize(m);
-    for (int k = 0; k < m; ++k) f[k] = etas[k] - chil * (R)std::sqrt(ss[k]);
+    df.resize(m);
+    for (int k = 0; k < m; ++k) {
+      const double nw = std::sqrt(ss[k]);
+      f[k] = etas[k] - chil * (R)nw;
+      df[k] = (R)(1.0 - (double)chil * ss[m + k] / (nw * (double)delta));
+    }
     return SPX_OK;
   };
   auto finish = [&](bool use_scale, R scale, R post) -> int32_t {
@@ -217,82 +267,108 @@ static int32_t prox_l1b2(spx_ctx* ctx, int64_t n, R* y, const R* xk, const R* sj
     return SPX_OK;
   };
 
-  std::vector<R> f, pts(1, delta);
-  int32_t st = eval(pts, false, f);  // ‖ProjB(-xk)‖  (:56-58)
+  std::vector<R> f, df, pts(1, delta);
+  int32_t st = eval(pts, false, f, df);  // ‖ProjB(-xk)‖  (:56-58); also the residual and slope at η = Δ
   if (st != SPX_OK) return st;
   // f[0] = Δ - χ(y); the reference tests Δ <= χ(y)  (:58) -- the sign of a difference is exact
   if (!(f[0] <= R(0))) return finish(false, R(1), R(1));
-  R a = delta, fa = f[0], b = a, fb = fa;
+  R a = delta, fa = f[0], da = df[0], b = a, fb = fa, db = da;
   R eta = a;
+  auto ulps_between = [](R lo, R hi) -> long long {  // representable numbers strictly inside (lo, hi), 0 < lo < hi
+    if (sizeof(R) == 8) {
+      long long x, y;
+      double l = (double)lo, h = (double)hi;
+      memcpy(&x, &l, 8);
+      memcpy(&y, &h, 8);
+      return y - x - 1;
+    }
+    int x, y;
+    float l = (float)lo, h = (float)hi;
+    memcpy(&x, &l, 4);
+    memcpy(&y, &h, 4);
+    return (long long)y - x - 1;
+  };
+  // scan evaluated points (ascending, strictly inside the bracket): the residual is increasing, so the
+  // bracket becomes the first sign change
+  auto absorb = [&](const std::vector<R>& p, bool& have_b, bool& exact) {
+    for (size_t k = 0; k < p.size(); ++k) {
+      if (f[k] == R(0)) { eta = p[k]; exact = true; return; }
+      if (f[k] < R(0)) { a = p[k]; fa = f[k]; da = df[k]; }
+      else { b = p[k]; fb = f[k]; db = df[k]; have_b = true; return; }
+    }
+  };
   if (fa != R(0)) {
-    // bracket: b0 = max(2a, a+1), doubled until the residual is non-negative
-    bool have = false;
+    bool have_b = false, exact = false;
+    // bracket: a Newton step from a (the residual is convex there in practice, so it lands just past the
+    // root) next to the reference's own guesses max(2a, a+1) 2^k
     R b0 = std::max(R(2) * a, a + R(1));
-    while (!have) {
+    while (!have_b && !exact) {
       pts.clear();
-      for (int k = 0; k < 8; ++k) pts.push_back(b0 * (R)std::ldexp(1.0, k));
-      st = eval(pts, true, f);
-      if (st != SPX_OK) return st;
-      for (int k = 0; k < 8; ++k) {
-        if (f[k] < R(0)) {
-          a = pts[k];
-          fa = f[k];
-        } else {
-          b = pts[k];
-          fb = f[k];
-          have = true;
-          break;
-        }
+      const R xn = (da > R(0)) ? a - fa / da : std::numeric_limits<R>::infinity();
+      if (std::isfinite(xn) && xn > a) {
+        pts.push_back(xn);
+        pts.push_back(xn + (xn - a) / R(16));
+        pts.push_back(xn + (xn - a));
       }
-      if (!have) {
+      for (int k = 0; k < 4; ++k) pts.push_back(b0 * (R)std::ldexp(1.0, 2 * k));
+      std::sort(pts.begin(), pts.end());
+      pts.erase(std::unique(pts.begin(), pts.end()), pts.end());
+      while (!pts.empty() && !std::isfinite(pts.back())) pts.pop_back();
+      if (pts.empty()) {
+        set_error("spx_prox_l1b2: no sign change of the trust-region residual");
+        return SPX_E_NOROOT;
+      }
+      st = eval(pts, true, f, df);
+      if (st != SPX_OK) return st;
+      absorb(pts, have_b, exact);
+      if (!have_b && !exact) {
         b0 = R(2) * a;
-        if (!std::isfinite(b0)) {
+        if (!std::isfinite(b0) || passes > 200) {
           set_error("spx_prox_l1b2: no sign change of the trust-region residual");
           return SPX_E_NOROOT;
         }
       }
     }
-    eta = b;
-    bool exact = (fb == R(0));
-    bool uniform = true;
+    if (!exact) eta = b;
+    exact = exact || (fb == R(0));
+    bool slow = false;
     while (!exact) {
       const R mid = a + (b - a) / R(2);
       if (!(a < mid && mid < b)) break;
       const R w = b - a;
+      const long long inside = ulps_between(a, b);
       pts.clear();
-      if (uniform) {
-        for (int k = 1; k <= kMaxScale; ++k) pts.push_back(a + w * ((R)k / (R)(kMaxScale + 1)));
+      if (inside <= 8) {  // last pass: every float left in the bracket
+        R x = a;
+        for (long long k = 0; k < inside; ++k) {
+          x = std::nextafter(x, b);
+          pts.push_back(x);
+        }
+      } else if (slow) {  // poor shrink: section uniformly
+        for (int k = 1; k <= 8; ++k) pts.push_back(a + w * ((R)k / (R)9));
       } else {
-        R xs = a - fa * (w / (fb - fa));
-        if (!(xs > a && xs < b)) xs = mid;
-        for (int j = 3; j >= 0; --j) pts.push_back(xs - w * (R)std::ldexp(1.0, -(3 + 4 * j) - 0));
-        for (int j = 0; j <= 3; ++j) pts.push_back(xs + w * (R)std::ldexp(1.0, -(15 - 4 * j)));
-        pts.push_back(mid);
+        // secant point and the Newton points of both ends, each with a neighbour one estimated error
+        // further out, so that the next bracket is as tight as the estimates agree
+        const R xs = a - fa * (w / (fb - fa));
+        const R xa = (da > R(0)) ? a - fa / da : mid;
+        const R xb = (db > R(0)) ? b - fb / db : mid;
+        const R best = (std::fabs(fa) <= std::fabs(fb)) ? xa : xb;
+        R err = std::max(std::fabs(best - xs), std::fabs(xa - xb));
+        err = std::max(err, R(4) * (std::nextafter(best, b) - best));
+        const R c[8] = {xs, xa, xb, best - err, best + err, best - err / R(16), best + err / R(16), best};
+        for (R x : c) pts.push_back(x);
       }
       std::sort(pts.begin(), pts.end());
       std::vector<R> in;
       for (R x : pts)
         if (x > a && x < b && (in.empty() || x > in.back())) in.push_back(x);
       if (in.empty()) in.push_back(mid);
-      if ((int)in.size() > kMaxScale) in.resize(kMaxScale);
-      st = eval(in, true, f);
+      if ((int)in.size() > 8) in.resize(8);
+      st = eval(in, true, f, df);
       if (st != SPX_OK) return st;
-      for (size_t k = 0; k < in.size(); ++k) {
-        if (f[k] == R(0)) {
-          eta = in[k];
-          exact = true;
-          break;
-        }
-        if (f[k] < R(0)) {
-          a = in[k];
-          fa = f[k];
-        } else {
-          b = in[k];
-          fb = f[k];
-          break;
-        }
-      }
-      uniform = !((b - a) <= w / R(8));  // poor shrink -> next pass sections uniformly
+      bool hb = true;
+      absorb(in, hb, exact);
+      slow = !((b - a) <= w / R(8));
       if (passes > 200) break;
     }
     if (!exact) eta = (std::fabs(fa) <= std::fabs(fb)) ? a : b;

@@ -24,11 +24,16 @@ namespace cg = cooperative_groups;
 
 namespace spx {
 
-constexpr int kTrThreads = 1024;
+#ifndef SPX_TR_THREADS
+#define SPX_TR_THREADS 1024
+#endif
+constexpr int kTrThreads = SPX_TR_THREADS;     // 1024 x 64 registers: one CTA per SM (512 x 2 measured slower: 8-CTA clusters)
 constexpr int kTrE = 16;                       // elements per thread (registers)
 constexpr int kTrChunk = kTrThreads * kTrE;    // 16384 elements per CTA
 constexpr int kTrBins = 2048;                  // 11-bit digits
+constexpr int kTrBpt = kTrBins / kTrThreads;   // bins per thread when a digit is picked
 constexpr int kTrMaxCluster = 8;
+constexpr int kPickThreads = 1024;             // single-block digit pick of the global path
 
 template <class R> struct KeyTraits;
 template <> struct KeyTraits<double> {
@@ -56,7 +61,7 @@ __host__ __device__ constexpr int digit_bits(int BITS, int pass) {
 
 // exclusive prefix sum of one int per thread over the block (ascending thread id);
 // `ws` holds 33 ints.  Returns the exclusive prefix; *total = block sum.
-__device__ __forceinline__ int block_excl_scan(int v, int* ws, int* total) {
+template <int THREADS> __device__ __forceinline__ int block_excl_scan(int v, int* ws, int* total) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   int inc = v;
 #pragma unroll
@@ -68,7 +73,7 @@ __device__ __forceinline__ int block_excl_scan(int v, int* ws, int* total) {
   if (lane == 31) ws[w] = inc;
   __syncthreads();
   if (w == 0) {
-    int s = lane < (kTrThreads / 32) ? ws[lane] : 0;
+    int s = lane < (THREADS / 32) ? ws[lane] : 0;
     int sinc = s;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -94,7 +99,7 @@ struct TrShared {
 };
 
 template <class R, bool BINF, bool VECLD>
-__global__ void __launch_bounds__(kTrThreads, 1)
+__global__ void __launch_bounds__(kTrThreads, 65536 / (64 * kTrThreads))
     topr_cluster_kernel(R* y, const R* xk, const R* sj, const R* q, long long n, long long r, R delta,
                         long long nprob) {
   using KT = KeyTraits<R>;
@@ -151,20 +156,23 @@ __global__ void __launch_bounds__(kTrThreads, 1)
     const bool select = (r > 0) && (r < n);
     if (select) {
       keep_all_bin = false;
+      unsigned cand = valid;  // slots whose key still carries the selected prefix
 #pragma unroll 1
       for (int pass = 0; pass < KT::NPASS; ++pass) {
         const int width = digit_bits(KT::BITS, pass);
-        const int hi_shift = shift;  // prefix = key >> hi_shift
         shift -= width;
         for (int b = t; b < kTrBins; b += kTrThreads) sh->hist[b] = 0;
         __syncthreads();
+        const K dmask = (K)((1u << width) - 1u);
+        if (__any_sync(0xffffffffu, cand != 0u)) {  // after the first digits most warps hold no candidate
 #pragma unroll
-        for (int s = 0; s < kTrE; ++s) {
-          const K key = KT::key(z[s]);
-          const bool in = ((valid >> s) & 1u) && (pass == 0 || (key >> hi_shift) == prefix);
-          const unsigned d = in ? (unsigned)((key >> shift) & (K)((1u << width) - 1u)) : 0xffffffffu;
-          const unsigned peers = __match_any_sync(0xffffffffu, d);
-          if (in && lane == (__ffs(peers) - 1)) atomicAdd(&sh->hist[d], (unsigned)__popc(peers));
+          for (int s = 0; s < kTrE; ++s) {
+            const bool in = (cand >> s) & 1u;
+            if (pass > 0 && !__any_sync(0xffffffffu, in)) continue;
+            const unsigned d = in ? (unsigned)((KT::key(z[s]) >> shift) & dmask) : 0xffffffffu;
+            const unsigned peers = __match_any_sync(0xffffffffu, d);
+            if (in && lane == (__ffs(peers) - 1)) atomicAdd(&sh->hist[d], (unsigned)__popc(peers));
+          }
         }
         cluster.sync();  // every CTA's histogram is complete
         for (int b = t; b < kTrBins; b += kTrThreads) {
@@ -173,21 +181,35 @@ __global__ void __launch_bounds__(kTrThreads, 1)
           sh->tot[b] = s;
         }
         cluster.sync();  // remote reads done before anyone clears its histogram again
-        // bins in descending order: thread t owns bins 2047-2t and 2046-2t
-        const int b0 = kTrBins - 1 - 2 * t, b1 = b0 - 1;
-        const int c0 = (int)sh->tot[b0], c1 = (int)sh->tot[b1];
+        // bins in descending order: thread t owns bins 2047 - kTrBpt t ... 2048 - kTrBpt (t + 1)
+        int c[kTrBpt], mine = 0;
+#pragma unroll
+        for (int j = 0; j < kTrBpt; ++j) {
+          c[j] = (int)sh->tot[kTrBins - 1 - kTrBpt * t - j];
+          mine += c[j];
+        }
         int total;
-        const int above = block_excl_scan(c0 + c1, sh->ws, &total);
-        if ((long long)above < need && need <= (long long)above + c0) {
-          sh->sel_bin = b0; sh->sel_above = above; sh->sel_count = c0;
-        } else if ((long long)above + c0 < need && need <= (long long)above + c0 + c1) {
-          sh->sel_bin = b1; sh->sel_above = above + c0; sh->sel_count = c1;
+        long long above = block_excl_scan<kTrThreads>(mine, sh->ws, &total);
+#pragma unroll
+        for (int j = 0; j < kTrBpt; ++j) {
+          if (above < need && need <= above + c[j]) {
+            sh->sel_bin = kTrBins - 1 - kTrBpt * t - j;
+            sh->sel_above = above;
+            sh->sel_count = c[j];
+          }
+          above += c[j];
         }
         __syncthreads();
-        prefix = (prefix << width) | (K)sh->sel_bin;
+        const unsigned sel = (unsigned)sh->sel_bin;
+        prefix = (prefix << width) | (K)sel;
         need -= sh->sel_above;
         const long long bin_count = sh->sel_count;
         __syncthreads();
+        unsigned keepc = 0;
+#pragma unroll
+        for (int s = 0; s < kTrE; ++s)
+          if (((cand >> s) & 1u) && (unsigned)((KT::key(z[s]) >> shift) & dmask) == sel) keepc |= 1u << s;
+        cand = keepc;
         if (need == bin_count) {  // the whole bin is kept: no finer digit needed
           keep_all_bin = true;
           break;
@@ -218,7 +240,7 @@ __global__ void __launch_bounds__(kTrThreads, 1)
         // ordered tie resolution: equal elements ranked by global index
         int total;
         int mine = __popc(eqmask);
-        (void)block_excl_scan(mine, sh->ws, &total);
+        (void)block_excl_scan<kTrThreads>(mine, sh->ws, &total);
         if (t == 0) sh->eq_count = total;
         cluster.sync();
         long long offset = 0;
@@ -228,7 +250,7 @@ __global__ void __launch_bounds__(kTrThreads, 1)
         for (int k = 0; k < ROUNDS; ++k) {
           const unsigned m = (eqmask >> (k * VEC)) & ((1u << VEC) - 1u);
           int rtotal;
-          long long rank = offset + block_excl_scan(__popc(m), sh->ws, &rtotal);
+          long long rank = offset + block_excl_scan<kTrThreads>(__popc(m), sh->ws, &rtotal);
 #pragma unroll
           for (int e = 0; e < VEC; ++e) {
             if ((m >> e) & 1u) {
@@ -316,7 +338,7 @@ __global__ void __launch_bounds__(256) topr_g_hist(const R* y, long long n, int 
 
 // single block: pick the digit, update the selection state, clear the histogram
 template <class R>
-__global__ void __launch_bounds__(kTrThreads) topr_g_pick(int pass, GlobalSel* st) {
+__global__ void __launch_bounds__(kPickThreads) topr_g_pick(int pass, GlobalSel* st) {
   using KT = KeyTraits<R>;
   __shared__ int ws[40];
   __shared__ int sel_bin;
@@ -331,8 +353,8 @@ __global__ void __launch_bounds__(kTrThreads) topr_g_pick(int pass, GlobalSel* s
   int total_lo, total_hi;
   const long long s = c0 + c1;
   const int lo = (int)(s & 0x3fffffff), hi = (int)(s >> 30);
-  const long long above_lo = block_excl_scan(lo, ws, &total_lo);
-  const long long above_hi = block_excl_scan(hi, ws, &total_hi);
+  const long long above_lo = block_excl_scan<kPickThreads>(lo, ws, &total_lo);
+  const long long above_hi = block_excl_scan<kPickThreads>(hi, ws, &total_hi);
   const long long above = above_lo + (above_hi << 30);
   const long long need = st->need;
   if (above < need && need <= above + c0) {
@@ -468,7 +490,7 @@ static int32_t topr_global(spx_ctx* ctx, int64_t n, R* y, const R* xk, const R* 
         topr_g_hist<R><<<nblk, 256, 0, ctx->stream>>>(y, n, pass, st);
         ctx->launches++;
       }
-      topr_g_pick<R><<<1, kTrThreads, 0, ctx->stream>>>(pass, st);
+      topr_g_pick<R><<<1, kPickThreads, 0, ctx->stream>>>(pass, st);
       ctx->launches++;
     }
     topr_g_eqcount<R><<<nblk, 256, 0, ctx->stream>>>(y, n, per_block, st, block_eq);
