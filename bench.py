@@ -148,7 +148,7 @@ def workload_config(log2n, **extra):
 
 # -------------------------------------------------------------------- clocks ---
 class ClockSampler(threading.Thread):
-    def __init__(self, index: int, period=0.02):
+    def __init__(self, index: int, period=0.005):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons = [], set()

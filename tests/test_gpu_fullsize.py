@@ -1,0 +1,217 @@
+"""BASELINE.json's configurations at FULL size (n = 2^28 Float64, 2^30 Float32, 10^7 groups of 64,
+4096 x 65536 top-r problems), checked through size-independent properties:
+
+* a position-sensitive 64-bit checksum of the whole output against the oracle streamed chunk by chunk
+  (bit-exact operators), or oracle comparison on windows spread over the vector (first, last, random);
+* feasibility of every element, fused ψ(y) == stand-alone ψ(y), support counts, threshold ordering,
+  `BInf == clamp(plain)`, ‖sj + y‖ = Δ on an active L2 ball.
+
+Inputs are the hash-generated vectors of SURVEY.md §8d (device generator == oracle generator, any window
+can be regenerated on the host).  Set SPX_FULLSIZE=0 to run the same tests at 1/64 of the size.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from gpu_util import DEV, N, orc, sp
+from shiftedprox import _lib as L
+
+pytestmark = pytest.mark.gpu
+
+FULL = os.environ.get("SPX_FULLSIZE", "1") != "0"
+SHRINK = 0 if FULL else 6
+SEED = orc.SEED
+M64 = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+def dev_uniform(n, stream, dtype=torch.float64, scale=1.0, shift=0.0, i0=0):
+    t = torch.empty(n, dtype=dtype, device=DEV)
+    suf, ct = ("f64", C.c_double) if dtype == torch.float64 else ("f32", C.c_float)
+    L.call(f"spx_fill_uniform_{suf}", sp.context(DEV), C.c_void_p(t.data_ptr()), C.c_int64(n), C.c_int64(i0),
+           C.c_uint64(SEED), C.c_uint64(stream), ct(scale), ct(shift))
+    return t
+
+
+def splitmix64(x):
+    with np.errstate(over="ignore"):
+        x = (x + np.uint64(0x9E3779B97F4A7C15)) & M64
+        x = ((x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)) & M64
+        x = ((x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)) & M64
+        return x ^ (x >> np.uint64(31))
+
+
+def host_checksum(words, i0):
+    """Σ_i mix(word_i ^ mix(i)) mod 2^64 with global positions i0 .. (csrc/spx_context.cu checksum_kernel)"""
+    idx = np.arange(i0, i0 + words.size, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        return int(np.sum(splitmix64(words.view(np.uint64) ^ splitmix64(idx)), dtype=np.uint64))
+
+
+def dev_checksum(t):
+    out = C.c_uint64()
+    L.call("spx_checksum", sp.context(DEV), C.c_void_p(t.data_ptr()), C.c_int64(t.numel() * t.element_size() // 8),
+           C.byref(out))
+    return out.value
+
+
+def c2_host_inputs(i0, m):
+    u = lambda k, **kw: orc.uniform(m, k, np.float64, i0=i0, **kw)  # noqa: E731
+    xk, sj, q = u(0, scale=4.0, shift=-2.0), u(1, shift=-0.5), u(2, scale=4.0, shift=-2.0)
+    l, ub = -(0.25 + u(3)), 0.25 + u(4)
+    d, b = 0.5 + u(5), u(6)
+    d = np.where(b < 0.1, -d, d)
+    d = np.where((b >= 0.1) & (b < 0.2), 0.0, d)
+    return xk, sj, q, l, ub, d
+
+
+def windows(n, w, count, rng):
+    offs = [0, n - w] + [int(o) for o in rng.integers(0, n - w, size=count)]
+    return sorted(set(offs))
+
+
+def test_c2_box_prox_iprox_at_2p28():
+    """C2: L0Box prox!/iprox! (bit-exact: whole-vector checksum against the streamed oracle) and
+    RootNormLhalfBox prox! (windows, 4 ulp of the value scale), vector bounds, n = 2^28 Float64."""
+    n = 1 << (28 - SHRINK)
+    lam, sigma = 1.0, 0.1
+    xk, sj, q = dev_uniform(n, 0, scale=4.0, shift=-2.0), dev_uniform(n, 1, shift=-0.5), dev_uniform(n, 2, scale=4.0, shift=-2.0)
+    l = dev_uniform(n, 3).add_(0.25).neg_()
+    u = dev_uniform(n, 4).add_(0.25)
+    d = dev_uniform(n, 5).add_(0.5)
+    b = dev_uniform(n, 6)
+    d = torch.where(b < 0.1, -d, d)
+    d = torch.where((b >= 0.1) & (b < 0.2), torch.zeros_like(d), d)
+    del b
+    psi0 = sp.shifted(sp.shifted(sp.NormL0(lam), xk, l, u), sj)
+    psih = sp.shifted(sp.shifted(sp.RootNormLhalf(lam), xk, l, u), sj)
+    yp, yi, yh = (torch.empty_like(q) for _ in range(3))
+    _, vfused = sp.prox_(yp, psi0, q, sigma, want_value=True)
+    sp.iprox_(yi, psi0, q, d)
+    sp.prox_(yh, psih, q, sigma)
+    got = {"prox": dev_checksum(yp), "iprox": dev_checksum(yi)}
+    # properties on the device, every element
+    eps = 1.4901161193847656e-8
+    for y in (yp, yh, yi):
+        w = sj + y
+        assert bool(((w >= l - eps) & (w <= u + eps)).all())
+    assert vfused == pytest.approx(psi0(yp), rel=1e-12)
+    assert vfused == float(torch.count_nonzero((xk + sj) + yp).item()) * lam
+    # streamed oracle
+    chunk = 1 << 22
+    want = {"prox": 0, "iprox": 0}
+    rng = np.random.default_rng(11)
+    lh_windows = set(int(o) for o in rng.integers(0, n // chunk, size=3)) | {0, n // chunk - 1}
+    for c in range(n // chunk):
+        i0 = c * chunk
+        hxk, hsj, hq, hl, hu, hd = c2_host_inputs(i0, chunk)
+        want["prox"] = (want["prox"] + host_checksum(orc.prox_box("l0", hxk, hsj, hq, hl, hu, lam, sigma), i0)) % (1 << 64)
+        want["iprox"] = (want["iprox"] + host_checksum(orc.iprox_box("l0", hxk, hsj, hq, hd, hl, hu, lam), i0)) % (1 << 64)
+        if c in lh_windows:
+            m = 1 << 16
+            ref = orc.prox_box("lhalf", hxk[:m], hsj[:m], hq[:m], hl[:m], hu[:m], lam, sigma)
+            tol = 4 * np.finfo(np.float64).eps * (np.abs(hxk[:m]) + np.abs(hsj[:m]) + np.abs(hq[:m]) + 1.0)
+            bad = np.abs(N(yh[i0:i0 + m]) - ref) > tol
+            assert bad.mean() <= 1e-4, (c, int(bad.sum()))
+    assert got == want
+
+
+def test_c3_l1_binf_and_l1b2_at_2p30_f32():
+    """C3: ShiftedNormL1 with a BInf trust region (= L1Box with scalar bounds ±Δ) and ShiftedNormL1B2 with an
+    active ball, n = 2^30 Float32."""
+    n = 1 << (30 - SHRINK)
+    f32 = torch.float32
+    lam, sigma = 1.0, 0.1
+    xk, sj, q = dev_uniform(n, 0, f32, 4.0, -2.0), dev_uniform(n, 1, f32, 1.0, -0.5), dev_uniform(n, 2, f32, 4.0, -2.0)
+    y = torch.empty_like(q)
+    # L1 BInf: bit-exact on windows, feasible everywhere, fused ψ == stand-alone ψ
+    delta = 0.75
+    box = sp.shifted(sp.shifted(sp.NormL1(lam), xk, -delta, delta), sj)
+    _, v = sp.prox_(y, box, q, sigma, want_value=True)
+    assert v == pytest.approx(box(y), rel=1e-6)
+    w = sj + y
+    assert bool((w.abs() <= delta + 0.00034526698).all())
+    del w
+    rng = np.random.default_rng(5)
+    for i0 in windows(n, 1 << 16, 6, rng):
+        m = 1 << 16
+        u = lambda k, **kw: orc.uniform(m, k, np.float32, i0=i0, **kw)  # noqa: E731
+        hxk, hsj, hq = u(0, scale=4.0, shift=-2.0), u(1, shift=-0.5), u(2, scale=4.0, shift=-2.0)
+        ref = orc.prox_box("l1", hxk, hsj, hq, np.float32(-delta), np.float32(delta), lam, sigma)
+        assert np.array_equal(N(y[i0:i0 + m]), ref)
+    # L1B2, ball active: ‖sj + y‖₂ = Δ
+    pb = sp.shifted(sp.shifted(sp.NormL1(lam), xk, 1.0e9, sp.NormL2(1.0)), sj)
+    sp.prox_(y, pb, q, sigma)  # inactive ball: y = ProjB(-xk) - sj
+    full = float(torch.linalg.vector_norm((sj + y).double()))
+    pb = sp.shifted(sp.shifted(sp.NormL1(lam), xk, 0.5 * full, sp.NormL2(1.0)), sj)
+    _, v = sp.prox_(y, pb, q, sigma, want_value=True)
+    assert np.isfinite(v)
+    assert pb.last_passes <= 12
+    nrm = float(torch.linalg.vector_norm((sj + y).double()))
+    assert nrm == pytest.approx(0.5 * full, rel=1e-5)
+
+
+def test_c4_group_l2_and_binf_10m_groups_of_64():
+    """C4: 10^7 groups of 64 Float64: ShiftedGroupNormL2 and ShiftedGroupNormL2Binf against the oracle on
+    windows of whole groups; fused ψ(y) == stand-alone ψ(y)."""
+    ng = 10_000_000 >> SHRINK
+    gs = 64
+    n = ng * gs
+    sigma, delta = 0.3, 0.5
+    xk, sj, q = dev_uniform(n, 0, scale=4.0, shift=-2.0), dev_uniform(n, 1, shift=-0.5), dev_uniform(n, 2, scale=4.0, shift=-2.0)
+    lam_g = dev_uniform(ng, 12, shift=0.5)
+    offs = torch.arange(0, n + 1, gs, dtype=torch.int64, device=DEV)
+    h = sp.GroupNormL2(lam_g, None, offsets=offs)
+    y = torch.empty_like(q)
+    psi = sp.shifted(sp.shifted(h, xk), sj)
+    _, v = sp.prox_(y, psi, q, sigma, want_value=True)
+    assert v == pytest.approx(psi(y), rel=1e-12)
+    yb = torch.empty_like(q)
+    psib = sp.shifted(sp.shifted(h, xk, delta, sp.NormLinf(1.0)), sj)
+    sp.prox_(yb, psib, q, sigma)
+    assert bool(((sj + yb).abs() <= 1.1 * delta).all())
+    rng = np.random.default_rng(9)
+    wg = 2000  # groups per window
+    for g0 in windows(ng, wg, 4, rng):
+        i0, m = g0 * gs, wg * gs
+        u = lambda k, **kw: orc.uniform(m, k, np.float64, i0=i0, **kw)  # noqa: E731
+        hxk, hsj, hq = u(0, scale=4.0, shift=-2.0), u(1, shift=-0.5), u(2, scale=4.0, shift=-2.0)
+        hlam = orc.uniform(wg, 12, np.float64, shift=0.5, i0=g0)
+        ho = np.arange(0, m + 1, gs)
+        scale = np.abs(hxk) + np.abs(hsj) + np.abs(hq) + 1
+        ref = orc.prox_groupl2(hxk, hsj, hq, ho, hlam, sigma)
+        assert np.all(np.abs(N(y[i0:i0 + m]) - ref) <= 8 * np.finfo(np.float64).eps * scale)
+        refb = orc.prox_groupl2binf(hxk, hsj, hq, ho, hlam, sigma, delta)
+        assert np.all(np.abs(N(yb[i0:i0 + m]) - refb) <= 1e-9 * scale)
+
+
+def test_c5_topr_batch_4096_problems():
+    """C5: 4096 independent problems of 65536 Float64, r = 1024: exactly r survivors per problem, every
+    survivor at least as large as every dropped entry, BInf == clamp(plain), whole problems against the oracle."""
+    nprob, pn, r = 4096 >> SHRINK, 65536, 1024
+    n = nprob * pn
+    delta = 1.0
+    xk, sj, q = dev_uniform(n, 0, scale=4.0, shift=-2.0), dev_uniform(n, 1, shift=-0.5), dev_uniform(n, 2, scale=4.0, shift=-2.0)
+    y, yb = torch.empty_like(q), torch.empty_like(q)
+    L.call("spx_prox_indballl0_f64", sp.context(DEV), C.c_int64(nprob), C.c_int64(pn), C.c_void_p(y.data_ptr()),
+           C.c_void_p(xk.data_ptr()), C.c_void_p(sj.data_ptr()), C.c_void_p(q.data_ptr()), C.c_int64(r), C.c_int32(0),
+           C.c_double(0.0))
+    L.call("spx_prox_indballl0_f64", sp.context(DEV), C.c_int64(nprob), C.c_int64(pn), C.c_void_p(yb.data_ptr()),
+           C.c_void_p(xk.data_ptr()), C.c_void_p(sj.data_ptr()), C.c_void_p(q.data_ptr()), C.c_int64(r), C.c_int32(1),
+           C.c_double(delta))
+    xs = xk + sj
+    z = (xs + q).abs().view(nprob, pn)
+    kept = (y != -xs).view(nprob, pn)  # a dropped entry is written as 0 - xs
+    assert bool((kept.sum(1) == r).all())
+    big = torch.where(kept, z, torch.full_like(z, float("inf"))).amin(1)
+    small = torch.where(kept, torch.zeros_like(z), z).amax(1)
+    assert bool((big >= small).all())
+    assert torch.equal(yb, y.clamp(-delta, delta))
+    for p in (0, nprob // 2, nprob - 1):
+        i0 = p * pn
+        u = lambda k, **kw: orc.uniform(pn, k, np.float64, i0=i0, **kw)  # noqa: E731
+        hxk, hsj, hq = u(0, scale=4.0, shift=-2.0), u(1, shift=-0.5), u(2, scale=4.0, shift=-2.0)
+        assert np.array_equal(N(y[i0:i0 + pn]), orc.prox_indballl0(hxk, hsj, hq, r))
+        assert np.array_equal(N(yb[i0:i0 + pn]), orc.prox_indballl0(hxk, hsj, hq, r, delta=delta))
