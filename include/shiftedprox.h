@@ -243,6 +243,13 @@ typedef struct spx_box_job_f32 {
   int32_t spx_prox_indballl0_##SUF(spx_ctx* ctx, int64_t nprob, int64_t n, R* y, const R* xk,    \
                                    const R* sj, const R* q, int64_t r, int32_t binf,             \
                                    double delta);                                                \
+  /* one vector spread over `world` GPUs in rank order (this rank holds n_local contiguous elements of */ \
+  /* the n_global): the 2048-bin histogram of every radix digit goes through `reduce` (sum over ranks), */ \
+  /* then one vector of `world` tie counts; lowest global index wins ties, as on one GPU */             \
+  int32_t spx_prox_indballl0_sharded_##SUF(spx_ctx* ctx, int64_t n_local, int64_t n_global, R* y,       \
+                                           const R* xk, const R* sj, const R* q, int64_t r,            \
+                                           int32_t binf, double delta, int32_t rank, int32_t world,    \
+                                           spx_allreduce_sum_fn reduce, void* user);                   \
   /* ------------------------------------------------------ ψ(y) (a18-a20) */                    \
   /* generic ψ(y) = h(xk + sj + y), ShiftedProximalOperators.jl:51-54; kind = SPX_H_L1, */      \
   /* _L0, _LHALF, _INDBALLL0 (param r) */                                                        \

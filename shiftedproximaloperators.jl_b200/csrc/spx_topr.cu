@@ -18,6 +18,9 @@
 // the end of this file (z stashed in y, one histogram pass per digit).
 #include <cooperative_groups.h>
 
+#include <cstring>
+#include <vector>
+
 #include "spx_common.cuh"
 
 namespace cg = cooperative_groups;
@@ -288,12 +291,13 @@ __global__ void __launch_bounds__(kTrThreads, 65536 / (64 * kTrThreads))
 // For one long vector: z is stashed in y (3R + 1W), every further digit costs
 // one read of y, the last pass reads y, xk, sj and writes y.
 struct GlobalSel {
-  unsigned hist[kTrBins];
+  unsigned long long hist[kTrBins];  // 64-bit: the sharded form sums the histograms of every GPU
   unsigned long long prefix;
   long long need;
   int shift;
   int done;          // keep_all_bin reached
   long long eq_total;
+  long long eq_base;  // threshold-equal elements on lower-ranked shards (sharded form)
 };
 
 template <class R>
@@ -312,7 +316,7 @@ __global__ void __launch_bounds__(256) topr_g_stash(R* y, const R* xk, const R* 
   }
   __syncthreads();
   for (int b = threadIdx.x; b < kTrBins; b += 256)
-    if (h[b]) atomicAdd(&st->hist[b], h[b]);
+    if (h[b]) atomicAdd(&st->hist[b], (unsigned long long)h[b]);
 }
 
 template <class R>
@@ -333,7 +337,7 @@ __global__ void __launch_bounds__(256) topr_g_hist(const R* y, long long n, int 
   }
   __syncthreads();
   for (int b = threadIdx.x; b < kTrBins; b += 256)
-    if (h[b]) atomicAdd(&st->hist[b], h[b]);
+    if (h[b]) atomicAdd(&st->hist[b], (unsigned long long)h[b]);
 }
 
 // single block: pick the digit, update the selection state, clear the histogram
@@ -347,7 +351,7 @@ __global__ void __launch_bounds__(kPickThreads) topr_g_pick(int pass, GlobalSel*
   const int t = threadIdx.x;
   const int width = digit_bits(KT::BITS, pass);
   const int b0 = kTrBins - 1 - 2 * t, b1 = b0 - 1;
-  const long long c0 = st->hist[b0], c1 = st->hist[b1];
+  const long long c0 = (long long)st->hist[b0], c1 = (long long)st->hist[b1];
   // counts can exceed int for huge n: scan in two 31-bit halves is overkill; clamp-free 64-bit scan
   // via two int scans of the low / high parts
   int total_lo, total_hi;
@@ -399,7 +403,7 @@ __global__ void __launch_bounds__(256) topr_g_eqcount(const R* y, long long n, l
     block_eq[blockIdx.x] = s;
   }
 }
-__global__ void topr_g_scan(long long* block_eq, int nblocks) {
+__global__ void topr_g_scan(long long* block_eq, int nblocks, GlobalSel* st) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     long long run = 0;
     for (int i = 0; i < nblocks; ++i) {
@@ -407,6 +411,7 @@ __global__ void topr_g_scan(long long* block_eq, int nblocks) {
       block_eq[i] = run;
       run += c;
     }
+    st->eq_total = run;
   }
 }
 
@@ -423,7 +428,7 @@ __global__ void __launch_bounds__(256) topr_g_final(R* y, const R* xk, const R* 
   const int shift = st->shift;
   const bool all_bin = st->done != 0;
   const long long need = st->need;
-  long long run = mode == 0 ? block_eq[blockIdx.x] : 0;
+  long long run = mode == 0 ? st->eq_base + block_eq[blockIdx.x] : 0;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   for (long long base = b; base < e; base += 256) {
     const long long i = base + threadIdx.x;
@@ -466,10 +471,17 @@ __global__ void __launch_bounds__(256) topr_g_final(R* y, const R* xk, const R* 
   }
 }
 
+// One vector on one GPU (reduce == nullptr), or this GPU's contiguous shard of a vector spread over
+// `world` GPUs in rank order: the histogram of every digit is summed over the shards through the caller's
+// all-reduce (one exchange per radix digit), every rank picks the same digit, and the
+// lowest-index tie rule continues across shards through the count of threshold-equal elements on the
+// lower-ranked shards.
 template <class R>
 static int32_t topr_global(spx_ctx* ctx, int64_t n, R* y, const R* xk, const R* sj, const R* q, int64_t r, bool binf,
-                           R delta) {
+                           R delta, int64_t n_global = -1, int rank = 0, int world = 1,
+                           spx_allreduce_sum_fn reduce = nullptr, void* user = nullptr) {
   using KT = KeyTraits<R>;
+  if (n_global < 0) n_global = n;
   const int nblk = ctx->sm_count * 8;
   int32_t stt = ensure_scratch(ctx, sizeof(GlobalSel) + sizeof(long long) * (size_t)(nblk + 1));
   if (stt != SPX_OK) return stt;
@@ -480,28 +492,72 @@ static int32_t topr_global(spx_ctx* ctx, int64_t n, R* y, const R* xk, const R* 
   init.need = r;
   init.shift = KT::BITS;
   SPX_CUDA(cudaMemcpyAsync(st, &init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
-  const int mode = (r >= n) ? 1 : (r <= 0 ? 2 : 0);
-  topr_g_stash<R><<<nblk, 256, 0, ctx->stream>>>(y, xk, sj, q, n, st);
-  ctx->launches++;
+  const int mode = (r >= n_global) ? 1 : (r <= 0 ? 2 : 0);
+  // sum the histogram over the shards (counts are exact in Float64 up to 2^53)
+  std::vector<unsigned long long> hh;
+  std::vector<double> hd;
+  auto reduce_hist = [&]() -> int32_t {
+    if (!reduce) return SPX_OK;
+    hh.resize(kTrBins);
+    hd.resize(kTrBins);
+    SPX_CUDA(cudaMemcpyAsync(hh.data(), st->hist, sizeof(unsigned long long) * kTrBins, cudaMemcpyDeviceToHost,
+                             ctx->stream));
+    SPX_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int b = 0; b < kTrBins; ++b) hd[b] = (double)hh[b];
+    int32_t st2 = reduce(user, hd.data(), kTrBins);
+    if (st2 != SPX_OK) {
+      set_error("spx_prox_indballl0_sharded: all-reduce callback failed (%d)", (int)st2);
+      return st2;
+    }
+    for (int b = 0; b < kTrBins; ++b) hh[b] = (unsigned long long)hd[b];
+    SPX_CUDA(cudaMemcpyAsync(st->hist, hh.data(), sizeof(unsigned long long) * kTrBins, cudaMemcpyHostToDevice,
+                             ctx->stream));
+    return SPX_OK;
+  };
+  if (n > 0) {
+    topr_g_stash<R><<<nblk, 256, 0, ctx->stream>>>(y, xk, sj, q, n, st);
+    ctx->launches++;
+  }
   const long long per_block = (n + nblk - 1) / nblk;
   if (mode == 0) {
     for (int pass = 0; pass < KT::NPASS; ++pass) {
-      if (pass > 0) {
+      if (pass > 0 && n > 0) {
         topr_g_hist<R><<<nblk, 256, 0, ctx->stream>>>(y, n, pass, st);
         ctx->launches++;
       }
+      stt = reduce_hist();
+      if (stt != SPX_OK) return stt;
       topr_g_pick<R><<<1, kPickThreads, 0, ctx->stream>>>(pass, st);
       ctx->launches++;
     }
     topr_g_eqcount<R><<<nblk, 256, 0, ctx->stream>>>(y, n, per_block, st, block_eq);
-    topr_g_scan<<<1, 32, 0, ctx->stream>>>(block_eq, nblk);
+    topr_g_scan<<<1, 32, 0, ctx->stream>>>(block_eq, nblk, st);
     ctx->launches += 2;
+    if (reduce && world > 1) {
+      // exclusive prefix over ranks of the threshold-equal counts: all-reduce a vector with one slot per rank
+      long long eq_total = 0;
+      SPX_CUDA(cudaMemcpyAsync(&eq_total, &st->eq_total, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+      SPX_CUDA(cudaStreamSynchronize(ctx->stream));
+      std::vector<double> slots((size_t)world, 0.0);
+      slots[(size_t)rank] = (double)eq_total;
+      int32_t st2 = reduce(user, slots.data(), world);
+      if (st2 != SPX_OK) {
+        set_error("spx_prox_indballl0_sharded: all-reduce callback failed (%d)", (int)st2);
+        return st2;
+      }
+      long long base = 0;
+      for (int rr = 0; rr < rank; ++rr) base += (long long)slots[(size_t)rr];
+      SPX_CUDA(cudaMemcpyAsync(&st->eq_base, &base, sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+      SPX_CUDA(cudaStreamSynchronize(ctx->stream));  // `base` lives on this stack frame
+    }
   }
-  if (binf)
-    topr_g_final<R, true><<<nblk, 256, 0, ctx->stream>>>(y, xk, sj, n, per_block, st, block_eq, delta, mode);
-  else
-    topr_g_final<R, false><<<nblk, 256, 0, ctx->stream>>>(y, xk, sj, n, per_block, st, block_eq, delta, mode);
-  ctx->launches++;
+  if (n > 0) {
+    if (binf)
+      topr_g_final<R, true><<<nblk, 256, 0, ctx->stream>>>(y, xk, sj, n, per_block, st, block_eq, delta, mode);
+    else
+      topr_g_final<R, false><<<nblk, 256, 0, ctx->stream>>>(y, xk, sj, n, per_block, st, block_eq, delta, mode);
+    ctx->launches++;
+  }
   SPX_CUDA(cudaGetLastError());
   return SPX_OK;
 }
@@ -569,6 +625,29 @@ using namespace spx;
 extern "C" int32_t spx_prox_indballl0_f64(spx_ctx* ctx, int64_t nprob, int64_t n, double* y, const double* xk,
                                           const double* sj, const double* q, int64_t r, int32_t binf, double delta) {
   return prox_indballl0<double>(ctx, nprob, n, y, xk, sj, q, r, binf, delta);
+}
+extern "C" int32_t spx_prox_indballl0_sharded_f64(spx_ctx* ctx, int64_t n_local, int64_t n_global, double* y,
+                                                  const double* xk, const double* sj, const double* q, int64_t r,
+                                                  int32_t binf, double delta, int32_t rank, int32_t world,
+                                                  spx_allreduce_sum_fn reduce, void* user) {
+  SPX_REQUIRE(ctx != nullptr, "null context");
+  SPX_REQUIRE(n_local >= 0 && n_global >= n_local && world >= 1 && rank >= 0 && rank < world, "bad shard description");
+  SPX_REQUIRE(n_local == 0 || (y && xk && sj && q), "null device vector");
+  SPX_REQUIRE(world == 1 || reduce != nullptr, "a sharded vector needs the all-reduce callback");
+  DeviceGuard g(ctx->device);
+  return topr_global<double>(ctx, n_local, y, xk, sj, q, r, binf != 0, delta, n_global, rank, world, reduce, user);
+}
+extern "C" int32_t spx_prox_indballl0_sharded_f32(spx_ctx* ctx, int64_t n_local, int64_t n_global, float* y,
+                                                  const float* xk, const float* sj, const float* q, int64_t r,
+                                                  int32_t binf, double delta, int32_t rank, int32_t world,
+                                                  spx_allreduce_sum_fn reduce, void* user) {
+  SPX_REQUIRE(ctx != nullptr, "null context");
+  SPX_REQUIRE(n_local >= 0 && n_global >= n_local && world >= 1 && rank >= 0 && rank < world, "bad shard description");
+  SPX_REQUIRE(n_local == 0 || (y && xk && sj && q), "null device vector");
+  SPX_REQUIRE(world == 1 || reduce != nullptr, "a sharded vector needs the all-reduce callback");
+  DeviceGuard g(ctx->device);
+  return topr_global<float>(ctx, n_local, y, xk, sj, q, r, binf != 0, (float)delta, n_global, rank, world, reduce,
+                            user);
 }
 extern "C" int32_t spx_prox_indballl0_f32(spx_ctx* ctx, int64_t nprob, int64_t n, float* y, const float* xk,
                                           const float* sj, const float* q, int64_t r, int32_t binf, double delta) {

@@ -126,3 +126,34 @@ def prox_l1b2_sharded_(y_local, psi, q_local, sigma, group=None, want_value=Fals
               C.byref(passes), C.byref(out) if want_value else None)
     psi.last_passes = passes.value
     return (y_local, out.value) if want_value else y_local
+
+
+# ----------------------------------------------------- single-vector top-r sharded ---
+def prox_indballl0_sharded_(y_local, psi, q_local, n_global: int, group=None):
+    """ShiftedIndBallL0(BInf) prox! of ONE vector spread over the ranks in rank order (this rank holds
+    psi.n contiguous elements): each radix digit's 2048-bin histogram is all-reduced (SUM), every rank picks
+    the same digit, and ties at the threshold go to the lowest global index."""
+    from . import _lib as L, _p, ShiftedIndBallL0BInf
+
+    dev = psi.xk.device
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+
+    def _reduce(_user, vals, count):
+        try:
+            buf = torch.tensor([vals[i] for i in range(count)], dtype=torch.float64, device=dev)
+            dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+            host = buf.cpu()
+            for i in range(count):
+                vals[i] = float(host[i])
+            return 0
+        except Exception:  # never let an exception cross the C boundary
+            return -1
+
+    cb = L.ALLREDUCE_FN(_reduce)
+    binf = isinstance(psi, ShiftedIndBallL0BInf)
+    psi._call("prox_indballl0_sharded", C.c_int64(psi.n), C.c_int64(n_global), _p(y_local), _p(psi.xk), _p(psi.sj),
+              _p(q_local), C.c_int64(psi.h.r), C.c_int32(1 if binf else 0),
+              C.c_double(psi.Delta if binf else 0.0), C.c_int32(rank), C.c_int32(world),
+              cb if world > 1 else L.ALLREDUCE_FN(lambda u, v, c: 0), None)
+    return y_local

@@ -68,3 +68,66 @@ def test_l1b2_sharded_callback_matches_single_device(dt):
     assert np.array_equal(N(y1), N(y2))
     assert len(calls) == passes.value  # one all-reduce per norm pass + one for the ψ sums
     assert val.value == pytest.approx(psi(y2), rel=1e-12 if dt == np.float64 else 1e-5)
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("n,r,quant", [(300_001, 1234, False), (200_000, 50_000, True), (70_000, 69_999, False)])
+@pytest.mark.parametrize("binf", [False, True])
+def test_topr_single_vector_over_two_shards(dt, n, r, quant, binf):
+    """One vector cut into two shards (two contexts with their own streams, two host threads standing in for two
+    ranks; the all-reduce callback meets at a barrier): histogram exchange per radix digit + cross-shard tie
+    rule give exactly the single-device / oracle result, ties included (magnitudes quantised to 1/64)."""
+    import ctypes as C
+    import threading
+
+    from shiftedprox import _lib as L
+
+    xk, sj, q = inputs(n, dt)
+    if quant:
+        xk, sj, q = (np.round(a * 64) / 64 for a in (xk, sj, q))
+        xk, sj, q = xk.astype(dt), sj.astype(dt), q.astype(dt)
+    delta = 1.0
+    ref = orc.prox_indballl0(xk, sj, q, r, delta=delta if binf else None)
+    world = 2
+    cut = (n // 2 + 3) & ~3
+    bounds_ = [(0, cut), (cut, n)]
+    suf = "f64" if dt == np.float64 else "f32"
+    barrier = threading.Barrier(world)
+    slots = [None] * world
+    outs = [None] * world
+    errs = []
+
+    def worker(rank):
+        try:
+            lo, hi = bounds_[rank]
+            ctx = C.c_void_p()
+            L.call("spx_ctx_create", C.byref(ctx), C.c_int32(0), C.c_void_p(0), C.c_int32(1))
+            txk, tsj, tq = T(xk[lo:hi]), T(sj[lo:hi]), T(q[lo:hi])
+            y = torch.empty_like(tq)
+            torch.cuda.synchronize()
+
+            def reduce(_user, vals, count):
+                slots[rank] = [vals[i] for i in range(count)]
+                barrier.wait()
+                tot = [sum(s[i] for s in slots) for i in range(count)]
+                barrier.wait()
+                for i in range(count):
+                    vals[i] = tot[i]
+                return 0
+
+            cb = L.ALLREDUCE_FN(reduce)
+            L.call(f"spx_prox_indballl0_sharded_{suf}", ctx, C.c_int64(hi - lo), C.c_int64(n), C.c_void_p(y.data_ptr()),
+                   C.c_void_p(txk.data_ptr()), C.c_void_p(tsj.data_ptr()), C.c_void_p(tq.data_ptr()), C.c_int64(r),
+                   C.c_int32(1 if binf else 0), C.c_double(delta), C.c_int32(rank), C.c_int32(world), cb, None)
+            L.call("spx_ctx_synchronize", ctx)
+            outs[rank] = N(y)
+            L.call("spx_ctx_destroy", ctx)
+        except Exception as e:  # pragma: no cover
+            errs.append(e)
+            barrier.abort()
+
+    th = [threading.Thread(target=worker, args=(k,)) for k in range(world)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs, errs
+    assert np.array_equal(np.concatenate(outs), ref)
