@@ -23,7 +23,13 @@ constexpr int kEwThreads = 256;
 template <class Op, class = void> struct MinBlocks { static constexpr int value = 1; };
 template <class Op> struct MinBlocks<Op, std::void_t<decltype(Op::MINB)>> { static constexpr int value = Op::MINB; };
 
-template <int VEC, int UNROLL, class Op>
+// NPTR: number of leading operands known to be vectors, the others being scalars (fill) -- resolved at
+// compile time so the streaming loop carries no null tests, no fill moves and no predicated address
+// arithmetic (~10 % of the instructions of a Box kernel); NPTR < 0 keeps the run-time tests.
+template <class Op, class = void> struct SplitNull { static constexpr bool value = false; };
+template <class Op> struct SplitNull<Op, std::void_t<decltype(Op::SPLIT_NULL)>> { static constexpr bool value = Op::SPLIT_NULL; };
+
+template <int VEC, int UNROLL, class Op, int NPTR = -1>
 __global__ void __launch_bounds__(kEwThreads, MinBlocks<Op>::value)
     ew_kernel(const Op op, const long long n, const long long index_base, Partial* __restrict__ partials) {
   using R = typename Op::Real;
@@ -42,7 +48,8 @@ __global__ void __launch_bounds__(kEwThreads, MinBlocks<Op>::value)
       const long long v = base + (long long)u * kEwThreads + threadIdx.x;
 #pragma unroll
       for (int k = 0; k < NIN; ++k) {
-        if (op.in[k] != nullptr && v < nvec) {
+        const bool is_vec = NPTR < 0 ? (op.in[k] != nullptr) : (k < NPTR);
+        if (is_vec && v < nvec) {
           ld_stream(op.in[k] + v * VEC, reg[k][u]);
         } else {
 #pragma unroll
@@ -207,15 +214,26 @@ template <class Op> inline bool aligned16(const Op& op) {
   return (bits & 15u) == 0;
 }
 
-template <int VEC, int UNROLL, class Op> inline int ew_blocks_per_sm() {
+template <int VEC, int UNROLL, class Op, int NPTR = -1> inline int ew_blocks_per_sm() {
   static int cached = 0;  // per instantiation
   if (cached == 0) {
     int nb = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ew_kernel<VEC, UNROLL, Op>, kEwThreads, 0) != cudaSuccess || nb < 1)
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ew_kernel<VEC, UNROLL, Op, NPTR>, kEwThreads, 0) !=
+            cudaSuccess ||
+        nb < 1)
       nb = 1;
     cached = nb;
   }
   return cached;
+}
+
+// how many leading operands are vectors, or -1 if a scalar operand precedes a vector
+template <class Op> inline int leading_vectors(const Op& op) {
+  int k = 0;
+  while (k < Op::NIN && op.in[k] != nullptr) ++k;
+  for (int j = k; j < Op::NIN; ++j)
+    if (op.in[j] != nullptr) return -1;
+  return k;
 }
 
 // Launch `op` over n elements on `stream`.  Returns the number of blocks (=
@@ -250,14 +268,27 @@ int32_t ew_launch(spx_ctx* ctx, cudaStream_t stream, const Op& op, int64_t n, in
   const long long tile = (long long)kEwThreads * UNROLL;
   long long want = (nvec + tile - 1) / tile;
   if (want < 1) want = 1;
-  int per_sm = vec ? ew_blocks_per_sm<VECW, UNROLL, Op>() : ew_blocks_per_sm<1, UNROLL, Op>();
+  // operators with nullable trailing operands (the Box bounds): all vectors, or exactly the last two scalar
+  int nptr = -1;
+  if constexpr (SplitNull<Op>::value) {
+    const int lead = leading_vectors(op);
+    if (vec && (lead == Op::NIN || lead == Op::NIN - 2)) nptr = lead;
+  }
+  int per_sm = !vec ? ew_blocks_per_sm<1, UNROLL, Op>()
+                    : (nptr < 0 ? ew_blocks_per_sm<VECW, UNROLL, Op>()
+                                : (nptr == Op::NIN ? ew_blocks_per_sm<VECW, UNROLL, Op, Op::NIN>()
+                                                   : ew_blocks_per_sm<VECW, UNROLL, Op, Op::NIN - 2>()));
   long long cap = (long long)ctx->sm_count * per_sm;
   if (cap > kMaxPartials) cap = kMaxPartials;
   int grid = (int)(want < cap ? want : cap);
-  if (vec)
-    ew_kernel<VECW, UNROLL, Op><<<grid, kEwThreads, 0, stream>>>(op, n, index_base, partials);
-  else
+  if (!vec)
     ew_kernel<1, UNROLL, Op><<<grid, kEwThreads, 0, stream>>>(op, n, index_base, partials);
+  else if (nptr < 0)
+    ew_kernel<VECW, UNROLL, Op><<<grid, kEwThreads, 0, stream>>>(op, n, index_base, partials);
+  else if (nptr == Op::NIN)
+    ew_kernel<VECW, UNROLL, Op, Op::NIN><<<grid, kEwThreads, 0, stream>>>(op, n, index_base, partials);
+  else
+    ew_kernel<VECW, UNROLL, Op, Op::NIN - 2><<<grid, kEwThreads, 0, stream>>>(op, n, index_base, partials);
   ctx->launches++;
   if (nblocks_out) *nblocks_out = grid;
   cudaError_t e = cudaGetLastError();

@@ -436,6 +436,7 @@ template <class R, bool PSI> struct ProxL1Box {
   using Real = R;
   static constexpr int NIN = 5, UNROLL = 2, MINB = 4;
   static constexpr bool OUT = true, ACC = PSI;
+  static constexpr bool SPLIT_NULL = true;  // l, u: both vectors or both scalars at compile time
   const R* in[NIN];  // xk, sj, q, l, u
   R fill[NIN];
   R* y;
@@ -498,6 +499,7 @@ template <class R, bool PSI> struct IproxL1Box {
   using Real = R;
   static constexpr int NIN = 6, UNROLL = 1, MINB = 3;
   static constexpr bool OUT = true, ACC = PSI;
+  static constexpr bool SPLIT_NULL = true;  // l, u: both vectors or both scalars at compile time
   const R* in[NIN];  // xk, sj, g, d, l, u
   R fill[NIN];
   R* y;
@@ -556,6 +558,7 @@ template <class R, bool PSI> struct ProxL0Box {
   using Real = R;
   static constexpr int NIN = 5, UNROLL = 2, MINB = 4;
   static constexpr bool OUT = true, ACC = PSI;
+  static constexpr bool SPLIT_NULL = true;  // l, u: both vectors or both scalars at compile time
   const R* in[NIN];  // xk, sj, q, l, u
   R fill[NIN];
   R* y;
@@ -598,6 +601,7 @@ template <class R, bool PSI> struct IproxL0Box {
   using Real = R;
   static constexpr int NIN = 6, UNROLL = 1, MINB = 3;
   static constexpr bool OUT = true, ACC = PSI;
+  static constexpr bool SPLIT_NULL = true;  // l, u: both vectors or both scalars at compile time
   const R* in[NIN];  // xk, sj, g, d, l, u
   R fill[NIN];
   R* y;
@@ -739,6 +743,7 @@ template <class R, bool PSI> struct ProxLhalfBox {
 #endif
   static constexpr int NIN = 5, UNROLL = SPX_LHB_UNROLL, MINB = SPX_LHB_MINB, STAGES = SPX_LHB_STAGES;
   static constexpr bool OUT = true, ACC = PSI;
+  static constexpr bool SPLIT_NULL = true;  // l, u: both vectors or both scalars at compile time
   const R* in[NIN];  // xk, sj, q, l, u
   R fill[NIN];
   R* y;
@@ -819,6 +824,7 @@ template <class R> struct ValueBox {
   using Real = R;
   static constexpr int NIN = 5, UNROLL = 2, MINB = 4;
   static constexpr bool OUT = false, ACC = true;
+  static constexpr bool SPLIT_NULL = true;  // l, u: both vectors or both scalars at compile time
   const R* in[NIN];  // xk, sj, y, l, u
   R fill[NIN];
   R* y;
