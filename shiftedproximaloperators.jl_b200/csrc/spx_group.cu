@@ -584,26 +584,56 @@ __global__ void __launch_bounds__(kGroupThreads)
   const int lane = threadIdx.x & 31;
   const long long warp = ((long long)blockIdx.x * kGroupThreads + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * kGroupThreads) >> 5;
+  const long long ntasks = (ngroups + kTask - 1) / kTask;
   Partial p;
   p.s = 0.0;
   p.s2 = 0.0;
   p.bad = -1;
-  for (long long g = warp; g < ngroups; g += nwarps) {
-    const long long b = offs[g], e = offs[g + 1];
-    double ss = 0.0;
-    for (long long i = b + lane; i < e; i += 32) {
-      R v;
-      if (binf) {
-        const R w = sj[i] + y[i];
-        if ((double)w < -rad || (double)w > rad) p.bad = 1;
-        v = w + xk[i];
-      } else {
-        v = (xk[i] + sj[i]) + y[i];
-      }
-      ss += (double)v * (double)v;
+  // v = (xk + sj) + y, or for the Binf form w = sj + y (checked against the ball) and v = w + xk
+  auto term = [&](R xi, R si, R yi) -> double {
+    R v;
+    if (binf) {
+      const R w = si + yi;
+      if ((double)w < -rad || (double)w > rad) p.bad = 1;
+      v = w + xi;
+    } else {
+      v = (xi + si) + yi;
     }
-    ss = warp_sum(ss);
-    if (lane == 0) p.s += (double)(lambda_g[g] * (R)sqrt(ss));
+    return (double)v * (double)v;
+  };
+  for (long long task = warp; task < ntasks; task += nwarps) {
+    const long long g0 = task * kTask;
+    const TaskHead th = load_task(offs, g0, ngroups, lane);
+    const R lam_lane = lane < th.cnt ? lambda_g[g0 + lane] : R(0);
+    int pos = 0;
+    while (pos < th.cnt) {
+      const int k = plan_round(th.le, pos);
+      if (k < 0) {  // long group: the whole warp
+        const long long b = __shfl_sync(0xffffffffu, th.lo, pos), e = __shfl_sync(0xffffffffu, th.hi, pos);
+        double ss = 0.0;
+#pragma unroll 4
+        for (long long i = b + lane; i < e; i += 32) ss += term(xk[i], sj[i], y[i]);
+        ss = warp_sum(ss);
+        const R lam = __shfl_sync(0xffffffffu, lam_lane, pos);
+        if (lane == 0) p.s += (double)(lam * (R)sqrt(ss));
+        pos += 1;
+        continue;
+      }
+      const int L = 1 << k, sub = lane & (L - 1), gi = pos + (lane >> k);
+      const long long lo = __shfl_sync(0xffffffffu, th.lo, gi & 31), hi = __shfl_sync(0xffffffffu, th.hi, gi & 31);
+      const R lam = __shfl_sync(0xffffffffu, lam_lane, gi & 31);
+      const bool valid = gi < th.cnt;
+      const long long b = valid ? lo : 0, e = valid ? hi : 0;
+      double ss = 0.0;
+#pragma unroll
+      for (int j = 0; j < kEPL; ++j) {
+        const long long i = b + (long long)j * L + sub;
+        if (i < e) ss += term(ldv(xk + i), ldv(sj + i), ldv(y + i));
+      }
+      ss = sub_sum(ss, L);
+      if (valid && sub == 0) p.s += (double)(lam * (R)sqrt_fast(ss));
+      pos += 32 >> k;
+    }
   }
   p = block_fold<kGroupThreads>(p);
   if (threadIdx.x == 0) partials[blockIdx.x] = p;
