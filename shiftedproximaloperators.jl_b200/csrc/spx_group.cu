@@ -7,7 +7,8 @@
 // thirty-two to a warp, so the per-group scalar work -- the norm, and for the Binf form the whole root
 // search -- is shared by the groups of a round instead of being repeated on 32 idle lanes.  Groups of
 // more than 256 elements take the whole warp, stash `sol` in the output vector and re-read it through
-// L1/L2.  Sums of squares are accumulated in Float64 whatever R is; the butterfly order is fixed, so
+// L1/L2; they run in a second launch of the same kernel (PART = 1) so that the register-resident rounds
+// and the deeply batched loads a lone warp needs to hide latency do not share one register budget.  Sums of squares are accumulated in Float64 whatever R is; the butterfly order is fixed, so
 // results are deterministic.
 #include "spx_common.cuh"
 #include "spx_ops.cuh"
@@ -162,33 +163,67 @@ template <class R, bool KEEP_XS> struct Tile {
 
 // ------------------------------------------------------- ShiftedGroupNormL2 --
 // shiftedGroupNormL2.jl:52-79
+// Loads are batched four iterations deep before anything is stored: y may alias q, so the compiler
+// cannot hoist them itself, and a warp that owns a long group is alone in hiding its latency.
 template <class R, bool PSI>
 __device__ __forceinline__ double l2_long_group(R* y, const R* xk, const R* sj, const R* q, long long b, long long e,
                                                 R lam, R sigma, int lane) {
   double ss = 0.0;
-  for (long long i = b + lane; i < e; i += 32) {
-    const R s = (q[i] + xk[i]) + sj[i];
-    y[i] = s;  // stash sol (each lane re-reads only what it wrote)
-    ss += (double)s * (double)s;
+  for (long long i0 = b + lane; i0 < e; i0 += 128) {
+    R xv[4], sv[4], qv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long i = i0 + 32 * u;
+      if (i < e) {
+        xv[u] = ldv(xk + i);
+        sv[u] = ldv(sj + i);
+        qv[u] = ldv(q + i);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long i = i0 + 32 * u;
+      if (i < e) {
+        const R s = (qv[u] + xv[u]) + sv[u];
+        y[i] = s;  // stash sol (each lane re-reads only what it wrote)
+        ss += (double)s * (double)s;
+      }
+    }
   }
   ss = warp_sum(ss);
   const R snorm = (R)sqrt(ss);
   const R alpha = jl_max(R(1) - sigma * lam / snorm, R(0));
   double vv = 0.0;
-  for (long long i = b + lane; i < e; i += 32) {
-    const R xsi = xk[i] + sj[i];
-    const R o = (snorm == R(0) ? R(0) : alpha * y[i]) - xsi;
-    y[i] = o;
-    if (PSI) {
-      const double v = (double)(xsi + o);
-      vv += v * v;
+  for (long long i0 = b + lane; i0 < e; i0 += 128) {
+    R xv[4], sv[4], yv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long i = i0 + 32 * u;
+      if (i < e) {
+        xv[u] = xk[i];
+        sv[u] = sj[i];
+        yv[u] = y[i];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long i = i0 + 32 * u;
+      if (i < e) {
+        const R xsi = xv[u] + sv[u];
+        const R o = (snorm == R(0) ? R(0) : alpha * yv[u]) - xsi;
+        stv(y + i, o);
+        if (PSI) {
+          const double v = (double)(xsi + o);
+          vv += v * v;
+        }
+      }
     }
   }
   if (PSI) vv = warp_sum(vv);
   return vv;
 }
 
-template <class R, bool PSI>
+template <class R, bool PSI, int PART>  // PART 0: groups of <= 256 elements, 1: the longer ones
 __global__ void __launch_bounds__(kGroupThreads)
     group_l2_kernel(R* y, const R* xk, const R* sj, const R* q, long long ngroups,
                     const long long* __restrict__ offs, const R* __restrict__ lambda_g, R sigma,
@@ -201,16 +236,24 @@ __global__ void __launch_bounds__(kGroupThreads)
   for (long long task = warp; task < ntasks; task += nwarps) {
     const long long g0 = task * kTask;
     const TaskHead th = load_task(offs, g0, ngroups, lane);
+    // le[5]: groups of <= 256 elements (lanes beyond the task count as such)
+    if (PART == 1 ? (th.le[5] == 0xffffffffu) : (th.le[5] == 0u)) continue;
     const R lam_lane = lane < th.cnt ? lambda_g[g0 + lane] : R(0);
     int pos = 0;
     while (pos < th.cnt) {
       const int k = plan_round(th.le, pos);
       if (k < 0) {  // long group: the whole warp
-        const long long b = __shfl_sync(0xffffffffu, th.lo, pos), e = __shfl_sync(0xffffffffu, th.hi, pos);
-        const R lam = __shfl_sync(0xffffffffu, lam_lane, pos);
-        const double vv = l2_long_group<R, PSI>(y, xk, sj, q, b, e, lam, sigma, lane);
-        if (PSI && lane == 0) psi += (double)(lam * (R)sqrt(vv));  // λ_g ‖v_g‖  groupNormL2.jl:36
+        if (PART == 1) {
+          const long long b = __shfl_sync(0xffffffffu, th.lo, pos), e = __shfl_sync(0xffffffffu, th.hi, pos);
+          const R lam = __shfl_sync(0xffffffffu, lam_lane, pos);
+          const double vv = l2_long_group<R, PSI>(y, xk, sj, q, b, e, lam, sigma, lane);
+          if (PSI && lane == 0) psi += (double)(lam * (R)sqrt(vv));  // λ_g ‖v_g‖  groupNormL2.jl:36
+        }
         pos += 1;
+        continue;
+      }
+      if (PART == 1) {
+        pos += 32 >> k;
         continue;
       }
       Tile<R, true> t;
@@ -487,8 +530,8 @@ __device__ __forceinline__ bool binf_solve(const View& gv, bool valid, R lam, R 
 #ifndef SPX_GB_MINB
 #define SPX_GB_MINB 3
 #endif
-template <class R>
-__global__ void __launch_bounds__(kGroupThreads, SPX_GB_MINB)
+template <class R, int PART>
+__global__ void __launch_bounds__(kGroupThreads, PART == 0 ? SPX_GB_MINB : 2)
     group_l2binf_kernel(R* y, const R* xk, const R* sj, const R* q, long long ngroups,
                         const long long* __restrict__ offs, const R* __restrict__ lambda_g, R sigma, R delta,
                         UDiv<R> by_sigma) {
@@ -499,10 +542,20 @@ __global__ void __launch_bounds__(kGroupThreads, SPX_GB_MINB)
   for (long long task = warp; task < ntasks; task += nwarps) {
     const long long g0 = task * kTask;
     const TaskHead th = load_task(offs, g0, ngroups, lane);
+    // le[5]: groups of <= 256 elements (lanes beyond the task count as such)
+    if (PART == 1 ? (th.le[5] == 0xffffffffu) : (th.le[5] == 0u)) continue;
     const R lam_lane = lane < th.cnt ? lambda_g[g0 + lane] : R(0);
     int pos = 0;
     while (pos < th.cnt) {
       const int k = plan_round(th.le, pos);
+      if (k < 0 && PART == 0) {
+        pos += 1;
+        continue;
+      }
+      if (k >= 0 && PART == 1) {
+        pos += 32 >> k;
+        continue;
+      }
       if (k < 0) {  // long group: the whole warp, sol stashed in y
         const long long b = __shfl_sync(0xffffffffu, th.lo, pos), e = __shfl_sync(0xffffffffu, th.hi, pos);
         const R lam = __shfl_sync(0xffffffffu, lam_lane, pos);
@@ -576,7 +629,7 @@ __global__ void __launch_bounds__(kGroupThreads, SPX_GB_MINB)
 // ShiftedGroupNormL2: v = (xk + sj) + y  (ShiftedProximalOperators.jl:51-54)
 // ShiftedGroupNormL2Binf: w = sj + y, IndBallLinf(1.1Δ)(w), v = w + xk
 // (shiftedGroupNormL2Binf.jl:34-39); value Σ_g λ_g ‖v_g‖  (groupNormL2.jl:33-39)
-template <class R>
+template <class R, int PART>
 __global__ void __launch_bounds__(kGroupThreads)
     group_value_kernel(const R* __restrict__ xk, const R* __restrict__ sj, const R* __restrict__ y, long long ngroups,
                        const long long* __restrict__ offs, const R* __restrict__ lambda_g, bool binf, double rad,
@@ -604,19 +657,27 @@ __global__ void __launch_bounds__(kGroupThreads)
   for (long long task = warp; task < ntasks; task += nwarps) {
     const long long g0 = task * kTask;
     const TaskHead th = load_task(offs, g0, ngroups, lane);
+    // le[5]: groups of <= 256 elements (lanes beyond the task count as such)
+    if (PART == 1 ? (th.le[5] == 0xffffffffu) : (th.le[5] == 0u)) continue;
     const R lam_lane = lane < th.cnt ? lambda_g[g0 + lane] : R(0);
     int pos = 0;
     while (pos < th.cnt) {
       const int k = plan_round(th.le, pos);
       if (k < 0) {  // long group: the whole warp
-        const long long b = __shfl_sync(0xffffffffu, th.lo, pos), e = __shfl_sync(0xffffffffu, th.hi, pos);
-        double ss = 0.0;
+        if (PART == 1) {
+          const long long b = __shfl_sync(0xffffffffu, th.lo, pos), e = __shfl_sync(0xffffffffu, th.hi, pos);
+          double ss = 0.0;
 #pragma unroll 4
-        for (long long i = b + lane; i < e; i += 32) ss += term(xk[i], sj[i], y[i]);
-        ss = warp_sum(ss);
-        const R lam = __shfl_sync(0xffffffffu, lam_lane, pos);
-        if (lane == 0) p.s += (double)(lam * (R)sqrt(ss));
+          for (long long i = b + lane; i < e; i += 32) ss += term(xk[i], sj[i], y[i]);
+          ss = warp_sum(ss);
+          const R lam = __shfl_sync(0xffffffffu, lam_lane, pos);
+          if (lane == 0) p.s += (double)(lam * (R)sqrt(ss));
+        }
         pos += 1;
+        continue;
+      }
+      if (PART == 1) {
+        pos += 32 >> k;
         continue;
       }
       const int L = 1 << k, sub = lane & (L - 1), gi = pos + (lane >> k);
@@ -662,11 +723,15 @@ int32_t value_group_binf(spx_ctx* ctx, int64_t n, const R* xk, const R* sj, cons
     *out = 0.0;
     return SPX_OK;
   }
-  const int grid = group_grid(ctx, ngroups, (const void*)group_value_kernel<R>);
-  group_value_kernel<R><<<grid, kGroupThreads, 0, ctx->stream>>>(xk, sj, y, ngroups, (const long long*)offs, lambda_g,
-                                                                binf, 1.1 * (double)(R)delta, ctx->d_partials);
-  ctx->launches++;
+  const int grid0 = group_grid(ctx, ngroups, (const void*)group_value_kernel<R, 0>);
+  const int grid1 = group_grid(ctx, ngroups, (const void*)group_value_kernel<R, 1>);
+  group_value_kernel<R, 0><<<grid0, kGroupThreads, 0, ctx->stream>>>(
+      xk, sj, y, ngroups, (const long long*)offs, lambda_g, binf, 1.1 * (double)(R)delta, ctx->d_partials);
+  group_value_kernel<R, 1><<<grid1, kGroupThreads, 0, ctx->stream>>>(
+      xk, sj, y, ngroups, (const long long*)offs, lambda_g, binf, 1.1 * (double)(R)delta, ctx->d_partials + grid0);
+  ctx->launches += 2;
   SPX_CUDA(cudaGetLastError());
+  const int grid = grid0 + grid1;
   int32_t st = finalize_partials(ctx, grid, 1, false);
   if (st != SPX_OK) return st;
   // the reference accumulates sum_c in R; one rounding to R here
@@ -689,29 +754,38 @@ static int32_t prox_group(spx_ctx* ctx, bool binf, int64_t n, R* y, const R* xk,
   if (ngroups > 0) {
     if (!binf) {
       if (psi_out) {
-        const int grid = group_grid(ctx, ngroups, (const void*)group_l2_kernel<R, true>);
-        group_l2_kernel<R, true><<<grid, kGroupThreads, 0, ctx->stream>>>(
+        const int grid0 = group_grid(ctx, ngroups, (const void*)group_l2_kernel<R, true, 0>);
+        const int grid1 = group_grid(ctx, ngroups, (const void*)group_l2_kernel<R, true, 1>);
+        group_l2_kernel<R, true, 0><<<grid0, kGroupThreads, 0, ctx->stream>>>(
             y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, (R)sigma, ctx->d_partials);
-        ctx->launches++;
+        group_l2_kernel<R, true, 1><<<grid1, kGroupThreads, 0, ctx->stream>>>(
+            y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, (R)sigma, ctx->d_partials + grid0);
+        ctx->launches += 2;
         SPX_CUDA(cudaGetLastError());
-        int32_t st = finalize_partials(ctx, grid, 1, false);
+        int32_t st = finalize_partials(ctx, grid0 + grid1, 1, false);
         if (st != SPX_OK) return st;
         *psi_out = (double)(R)ctx->h_result[0].s;
         return SPX_OK;
       }
-      const int grid = group_grid(ctx, ngroups, (const void*)group_l2_kernel<R, false>);
-      group_l2_kernel<R, false><<<grid, kGroupThreads, 0, ctx->stream>>>(
+      const int grid0 = group_grid(ctx, ngroups, (const void*)group_l2_kernel<R, false, 0>);
+      const int grid1 = group_grid(ctx, ngroups, (const void*)group_l2_kernel<R, false, 1>);
+      group_l2_kernel<R, false, 0><<<grid0, kGroupThreads, 0, ctx->stream>>>(
           y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, (R)sigma, ctx->d_partials);
-      ctx->launches++;
+      group_l2_kernel<R, false, 1><<<grid1, kGroupThreads, 0, ctx->stream>>>(
+          y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, (R)sigma, ctx->d_partials);
+      ctx->launches += 2;
       SPX_CUDA(cudaGetLastError());
       return SPX_OK;
     }
-    const int grid = group_grid(ctx, ngroups, (const void*)group_l2binf_kernel<R>);
     UDiv<R> by_sigma;
     by_sigma.set((R)sigma);
-    group_l2binf_kernel<R><<<grid, kGroupThreads, 0, ctx->stream>>>(
+    const int grid0 = group_grid(ctx, ngroups, (const void*)group_l2binf_kernel<R, 0>);
+    const int grid1 = group_grid(ctx, ngroups, (const void*)group_l2binf_kernel<R, 1>);
+    group_l2binf_kernel<R, 0><<<grid0, kGroupThreads, 0, ctx->stream>>>(
         y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, (R)sigma, (R)delta, by_sigma);
-    ctx->launches++;
+    group_l2binf_kernel<R, 1><<<grid1, kGroupThreads, 0, ctx->stream>>>(
+        y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, (R)sigma, (R)delta, by_sigma);
+    ctx->launches += 2;
     SPX_CUDA(cudaGetLastError());
   }
   if (psi_out) {
