@@ -10,7 +10,7 @@
 // L1/L2; they run in a second launch of the same kernel (PART = 1) so that the register-resident rounds
 // and the deeply batched loads a lone warp needs to hide latency do not share one register budget.  Sums of squares are accumulated in Float64 whatever R is; the butterfly order is fixed, so
 // results are deterministic.
-#include "spx_common.cuh"
+#include "spx_elementwise.cuh"
 #include "spx_ops.cuh"
 
 namespace spx {
@@ -700,6 +700,104 @@ __global__ void __launch_bounds__(kGroupThreads)
   if (threadIdx.x == 0) partials[blockIdx.x] = p;
 }
 
+// ---- a single group spanning the whole vector (ShiftedGroupNormL2 built from NormL2, runtests.jl:244) ----
+// One warp cannot stream a vector: the norm is a grid-wide reduction pass (3R), the scaling a second
+// streaming pass (3R + 1W) on the elementwise kernel.
+template <class R> struct SolSumSq {
+  using Real = R;
+  static constexpr int NIN = 3, UNROLL = 4;
+  static constexpr bool OUT = false, ACC = true;
+  const R* in[NIN];  // xk, sj, q
+  R fill[NIN];
+  R* y;
+  __device__ __forceinline__ R apply(const R (&x)[NIN], long long, Partial& acc) const {
+    const double s = (double)((x[2] + x[0]) + x[1]);
+    acc.s2 += s * s;
+    return R(0);
+  }
+};
+template <class R, bool PSI> struct SolScale {
+  using Real = R;
+  static constexpr int NIN = 3, UNROLL = 2;
+  static constexpr bool OUT = true, ACC = PSI;
+  const R* in[NIN];  // xk, sj, q
+  R fill[NIN];
+  R* y;
+  R alpha;
+  bool zero;
+  __device__ __forceinline__ R apply(const R (&x)[NIN], long long, Partial& acc) const {
+    const R sol = (x[2] + x[0]) + x[1];
+    const R xs = x[0] + x[1];
+    const R o = (zero ? R(0) : alpha * sol) - xs;
+    if (PSI) {
+      const double v = (double)(xs + o);
+      acc.s2 += v * v;
+    }
+    return o;
+  }
+};
+template <class R> struct VSumSq {
+  using Real = R;
+  static constexpr int NIN = 3, UNROLL = 4;
+  static constexpr bool OUT = false, ACC = true;
+  const R* in[NIN];  // xk, sj, y
+  R fill[NIN];
+  R* y;
+  bool binf;
+  double rad;
+  __device__ __forceinline__ R apply(const R (&x)[NIN], long long, Partial& acc) const {
+    R v;
+    if (binf) {
+      const R w = x[1] + x[2];
+      if ((double)w < -rad || (double)w > rad) acc.bad = 1;
+      v = w + x[0];
+    } else {
+      v = (x[0] + x[1]) + x[2];
+    }
+    acc.s2 += (double)v * (double)v;
+    return R(0);
+  }
+};
+constexpr int64_t kSingleGroupMin = 1 << 15;  // below this one warp is quick enough
+
+template <class Op, class R> static void set_in3(Op& op, const R* a, const R* b, const R* c) {
+  op.in[0] = a; op.in[1] = b; op.in[2] = c;
+  op.fill[0] = op.fill[1] = op.fill[2] = R(0);
+  op.y = nullptr;
+}
+
+template <class R>
+static int32_t prox_single_group(spx_ctx* ctx, int64_t n, R* y, const R* xk, const R* sj, const R* q,
+                                 const R* lambda_g, R sigma, double* psi_out) {
+  R lam;
+  SPX_CUDA(cudaMemcpyAsync(&lam, lambda_g, sizeof(R), cudaMemcpyDeviceToHost, ctx->stream));
+  SolSumSq<R> ss;
+  set_in3(ss, xk, sj, q);
+  int nb = 0;
+  int32_t st = ew_launch(ctx, ctx->stream, ss, n, 0, ctx->d_partials, &nb);
+  if (st != SPX_OK) return st;
+  st = finalize_partials(ctx, nb, 1, false);  // synchronises: lam has arrived as well
+  if (st != SPX_OK) return st;
+  const R snorm = (R)std::sqrt(ctx->h_result[0].s2);
+  R alpha = R(1) - sigma * lam / snorm;  // shiftedGroupNormL2.jl:70-77
+  alpha = (alpha != alpha) ? alpha : (alpha > R(0) ? alpha : R(0));
+  if (psi_out) {
+    SolScale<R, true> sc;
+    set_in3(sc, xk, sj, q);
+    sc.y = y; sc.alpha = alpha; sc.zero = snorm == R(0);
+    st = ew_launch(ctx, ctx->stream, sc, n, 0, ctx->d_partials, &nb);
+    if (st != SPX_OK) return st;
+    st = finalize_partials(ctx, nb, 1, false);
+    if (st != SPX_OK) return st;
+    *psi_out = (double)(R)(double)(lam * (R)std::sqrt(ctx->h_result[0].s2));
+    return SPX_OK;
+  }
+  SolScale<R, false> sc;
+  set_in3(sc, xk, sj, q);
+  sc.y = y; sc.alpha = alpha; sc.zero = snorm == R(0);
+  return ew_launch(ctx, ctx->stream, sc, n, 0, ctx->d_partials, &nb);
+}
+
 static int group_grid(spx_ctx* ctx, int64_t ngroups, const void* kernel) {
   int per_sm = 1;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kGroupThreads, 0) != cudaSuccess || per_sm < 1)
@@ -721,6 +819,22 @@ int32_t value_group_binf(spx_ctx* ctx, int64_t n, const R* xk, const R* sj, cons
   DeviceGuard g(ctx->device);
   if (ngroups == 0) {
     *out = 0.0;
+    return SPX_OK;
+  }
+  if (ngroups == 1 && n >= kSingleGroupMin) {  // one group spanning the vector: grid-wide reduction
+    R lam;
+    SPX_CUDA(cudaMemcpyAsync(&lam, lambda_g, sizeof(R), cudaMemcpyDeviceToHost, ctx->stream));
+    VSumSq<R> op;
+    set_in3(op, xk, sj, y);
+    op.binf = binf;
+    op.rad = 1.1 * (double)(R)delta;
+    int nb = 0;
+    int32_t st1 = ew_launch(ctx, ctx->stream, op, n, 0, ctx->d_partials, &nb);
+    if (st1 != SPX_OK) return st1;
+    st1 = finalize_partials(ctx, nb, 1, false);
+    if (st1 != SPX_OK) return st1;
+    *out = ctx->h_result[0].bad > 0 ? std::numeric_limits<double>::infinity()
+                                    : (double)(R)(double)(lam * (R)std::sqrt(ctx->h_result[0].s2));
     return SPX_OK;
   }
   const int grid0 = group_grid(ctx, ngroups, (const void*)group_value_kernel<R, 0>);
@@ -751,6 +865,7 @@ static int32_t prox_group(spx_ctx* ctx, bool binf, int64_t n, R* y, const R* xk,
   SPX_REQUIRE(n >= 0 && ngroups >= 0, "negative size");
   SPX_REQUIRE(ngroups == 0 || (y && xk && sj && q && offs && lambda_g), "null device vector");
   DeviceGuard g(ctx->device);
+  if (ngroups == 1 && !binf && n >= kSingleGroupMin) return prox_single_group<R>(ctx, n, y, xk, sj, q, lambda_g, (R)sigma, psi_out);
   if (ngroups > 0) {
     if (!binf) {
       if (psi_out) {

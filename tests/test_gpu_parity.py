@@ -365,10 +365,11 @@ def ragged_offsets(ngroups, maxlen, seed=3):
 
 
 @pytest.mark.parametrize("dt", DT)
-@pytest.mark.parametrize("layout", ["one", "two", "g64", "ragged"])
+@pytest.mark.parametrize("layout", ["one", "one_big", "two", "g64", "ragged"])
 def test_group_l2_prox_and_value(dt, layout):
-    offs = {"one": np.array([0, 777]), "two": np.array([0, 3, 6]), "g64": np.arange(0, 64 * 501, 64),
-            "ragged": ragged_offsets(300, 4096)}[layout]
+    # "one_big": a single group spanning a long vector (ShiftedGroupNormL2 from NormL2) -> grid-wide path
+    offs = {"one": np.array([0, 777]), "one_big": np.array([0, 100_003]), "two": np.array([0, 3, 6]),
+            "g64": np.arange(0, 64 * 501, 64), "ragged": ragged_offsets(300, 4096)}[layout]
     n = int(offs[-1]); ng = len(offs) - 1
     xk, sj, q = inputs(n, dt)
     lam_g = (dt(0.5) + orc.uniform(ng, 12, dt)).astype(dt)
