@@ -36,7 +36,22 @@ constexpr int kTrChunk = kTrThreads * kTrE;    // 16384 elements per CTA
 constexpr int kTrBins = 2048;                  // 11-bit digits
 constexpr int kTrBpt = kTrBins / kTrThreads;   // bins per thread when a digit is picked
 constexpr int kTrMaxCluster = 8;
+constexpr int kTrCandMax = 1024;               // candidates of the threshold bin resolved by direct ranking
 constexpr int kPickThreads = 1024;             // single-block digit pick of the global path
+
+#ifdef SPX_TR_TIMING
+__device__ unsigned long long g_tr_t[8];
+#define TR_T(i)                                          \
+  do {                                                   \
+    if (threadIdx.x == 0 && blockIdx.x == 0) {           \
+      const long long now__ = clock64();                 \
+      atomicAdd(&g_tr_t[i], (unsigned long long)(now__ - tr_last)); \
+      tr_last = now__;                                   \
+    }                                                    \
+  } while (0)
+#else
+#define TR_T(i)
+#endif
 
 template <class R> struct KeyTraits;
 template <> struct KeyTraits<double> {
@@ -99,12 +114,19 @@ struct TrShared {
   long long sel_above;
   long long sel_count;
   long long eq_count;  // equal-to-threshold elements in this CTA
+  // linear-bin form
+  unsigned long long kmax_slot[kTrMaxCluster];  // every CTA's largest key, replicated in every CTA
+  unsigned long long cand_key[kTrCandMax];      // CTA 0: keys of the threshold bin
+  int cand_idx[kTrCandMax];                     //        and their positions in the problem
+  int cand_count;                               // CTA 0
+  unsigned long long thr_key;                   // replicated: the r-th largest key ...
+  int thr_idx;                                  // ... and the last position kept among its equals
 };
 
 template <class R, bool BINF, bool VECLD>
 __global__ void __launch_bounds__(kTrThreads, 65536 / (64 * kTrThreads))
     topr_cluster_kernel(R* y, const R* xk, const R* sj, const R* q, long long n, long long r, R delta,
-                        long long nprob) {
+                        long long nprob, const unsigned char* __restrict__ only_flagged) {
   using KT = KeyTraits<R>;
   using K = typename KT::K;
   constexpr int VEC = VECLD ? 16 / (int)sizeof(R) : 1;
@@ -122,11 +144,15 @@ __global__ void __launch_bounds__(kTrThreads, 65536 / (64 * kTrThreads))
   const int lane = t & 31;
 
   for (long long prob = cid; prob < nprob; prob += ncluster) {
+    if (only_flagged != nullptr && only_flagged[prob] == 0) continue;  // cluster-uniform
     const long long pbase = prob * n;
     const long long cbase = (long long)crank * kTrChunk;  // this CTA's slice of the problem
     long long cnt = n - cbase;
     cnt = cnt < 0 ? 0 : (cnt > kTrChunk ? kTrChunk : cnt);
 
+#ifdef SPX_TR_TIMING
+    long long tr_last = clock64();
+#endif
     // ---- load: z in registers, xs in shared memory --------------------------
     R z[kTrE];
     unsigned valid = 0;
@@ -151,6 +177,8 @@ __global__ void __launch_bounds__(kTrThreads, 65536 / (64 * kTrThreads))
       }
     }
 
+    __syncthreads();
+    TR_T(0);  // load
     // ---- radix select of the r-th largest key ------------------------------
     bool keep_all_bin = true;   // every key whose prefix equals `prefix` is kept
     K prefix = 0;               // selected digits so far
@@ -177,13 +205,17 @@ __global__ void __launch_bounds__(kTrThreads, 65536 / (64 * kTrThreads))
             if (in && lane == (__ffs(peers) - 1)) atomicAdd(&sh->hist[d], (unsigned)__popc(peers));
           }
         }
+        __syncthreads();
+        TR_T(1);  // local histogram
         cluster.sync();  // every CTA's histogram is complete
+        TR_T(2);  // cluster sync
         for (int b = t; b < kTrBins; b += kTrThreads) {
           unsigned s = 0;
           for (unsigned rr = 0; rr < csize; ++rr) s += cluster.map_shared_rank(sh->hist, rr)[b];
           sh->tot[b] = s;
         }
         cluster.sync();  // remote reads done before anyone clears its histogram again
+        TR_T(3);  // remote sum + sync
         // bins in descending order: thread t owns bins 2047 - kTrBpt t ... 2048 - kTrBpt (t + 1)
         int c[kTrBpt], mine = 0;
 #pragma unroll
@@ -213,6 +245,7 @@ __global__ void __launch_bounds__(kTrThreads, 65536 / (64 * kTrThreads))
         for (int s = 0; s < kTrE; ++s)
           if (((cand >> s) & 1u) && (unsigned)((KT::key(z[s]) >> shift) & dmask) == sel) keepc |= 1u << s;
         cand = keepc;
+        TR_T(4);  // scan + pick
         if (need == bin_count) {  // the whole bin is kept: no finer digit needed
           keep_all_bin = true;
           break;
@@ -266,6 +299,8 @@ __global__ void __launch_bounds__(kTrThreads, 65536 / (64 * kTrThreads))
       }
     }
 
+    __syncthreads();
+    TR_T(5);  // keep masks / ties
     // ---- write y once -------------------------------------------------------
 #pragma unroll
     for (int k = 0; k < ROUNDS; ++k) {
@@ -281,6 +316,229 @@ __global__ void __launch_bounds__(kTrThreads, 65536 / (64 * kTrThreads))
           o.v[e] = v;
         }
         st_stream(y + pbase + cbase + li, o);
+      }
+    }
+    cluster.sync();  // shared state is reused by the next problem
+    TR_T(6);  // write + final sync
+  }
+}
+
+// ------------------------------------------------------ linear-bin form ---
+// The radix digits of an IEEE key are a poor first cut: the top 11 bits are the exponent, which a whole
+// problem shares up to a handful of values, so the first pass separates nothing and the select needs ~3
+// passes of warp-matched histogram atomics and ~8 cluster barriers.  This form bins |z| LINEARLY between 0
+// and the problem's largest magnitude (2048 bins, monotone in |z|, spread over the whole range, so plain
+// shared-memory atomics rarely collide): one histogram pass locates the bin holding the r-th largest
+// element; that bin holds ~n/2048 elements, which are gathered into CTA 0 and ranked directly (key
+// descending, position ascending -- the reference's tie order), giving the exact threshold (key, position).
+// Problems it cannot decide cheaply -- a NaN or Inf, all zeros, more than 1024 candidates in the threshold
+// bin -- are flagged and left to the radix kernel above, which runs afterwards on the flagged problems only.
+template <class R, bool BINF, bool VECLD>
+__global__ void __launch_bounds__(kTrThreads, 1)
+    topr_cluster_lin_kernel(R* y, const R* xk, const R* sj, const R* q, long long n, long long r, R delta,
+                            long long nprob, unsigned char* __restrict__ fallback) {
+  using KT = KeyTraits<R>;
+  using K = typename KT::K;
+  constexpr int VEC = VECLD ? 16 / (int)sizeof(R) : 1;
+  constexpr int ROUNDS = kTrE / VEC;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  TrShared* sh = reinterpret_cast<TrShared*>(smem_raw);
+  R* xs_sm = reinterpret_cast<R*>(smem_raw + ((sizeof(TrShared) + 15) / 16) * 16);
+
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned csize = cluster.num_blocks();
+  const unsigned crank = cluster.block_rank();
+  const long long ncluster = gridDim.x / csize;
+  const long long cid = blockIdx.x / csize;
+  const int t = threadIdx.x;
+  const int lane = t & 31;
+  const bool select = (r > 0) && (r < n);
+  TrShared* sh0 = cluster.map_shared_rank(sh, 0);
+
+  for (long long prob = cid; prob < nprob; prob += ncluster) {
+    const long long pbase = prob * n;
+    const long long cbase = (long long)crank * kTrChunk;  // this CTA's slice of the problem
+    long long cnt = n - cbase;
+    cnt = cnt < 0 ? 0 : (cnt > kTrChunk ? kTrChunk : cnt);
+
+    // ---- load: z in registers, xs in shared memory --------------------------
+    R z[kTrE];
+    unsigned valid = 0;
+    K kmax = 0;
+#pragma unroll
+    for (int k = 0; k < ROUNDS; ++k) {
+      const long long li = ((long long)k * kTrThreads + t) * VEC;
+      if (li < cnt) {  // VECLD => cnt is a multiple of VEC
+        Pack<R, VEC> a, b, c;
+        ld_stream(xk + pbase + cbase + li, a);
+        ld_stream(sj + pbase + cbase + li, b);
+        ld_stream(q + pbase + cbase + li, c);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+          const R xs = a.v[e] + b.v[e];
+          z[k * VEC + e] = xs + c.v[e];  // (xk + sj) + q   shiftedIndBallL0.jl:66
+          xs_sm[li + e] = xs;
+          valid |= 1u << (k * VEC + e);
+          const K key = KT::key(z[k * VEC + e]);
+          kmax = key > kmax ? key : kmax;
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) z[k * VEC + e] = R(0);
+      }
+    }
+    bool hard = false;
+    unsigned keepmask = 0;
+    if (!select) {
+      keepmask = (r >= n) ? valid : 0u;
+    } else {
+      // ---- largest magnitude of the problem ---------------------------------
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const K other = __shfl_xor_sync(0xffffffffu, kmax, o);
+        kmax = other > kmax ? other : kmax;
+      }
+      for (int b = t; b < kTrBins; b += kTrThreads) sh->hist[b] = 0;
+      if (t == 0) {
+        sh->cand_count = 0;
+        sh->kmax_slot[crank] = 0;
+      }
+      __syncthreads();  // also: ws free for reuse
+      if (lane == 0) atomicMax(&sh->kmax_slot[crank], (unsigned long long)kmax);
+      __syncthreads();
+      if (t < (int)csize) cluster.map_shared_rank(sh, t)->kmax_slot[crank] = sh->kmax_slot[crank];
+      cluster.sync();
+      K gmax = 0;
+      for (unsigned rr = 0; rr < csize; ++rr) {
+        const K v = (K)sh->kmax_slot[rr];
+        gmax = v > gmax ? v : gmax;
+      }
+      // the keys are the bit patterns of |z|: gmax back to a number
+      double zmax;
+      if (sizeof(R) == 8) zmax = __longlong_as_double((long long)gmax);
+      else zmax = (double)__int_as_float((int)gmax);
+      const double scale = (double)kTrBins / zmax;
+      hard = !(zmax > 0.0) || !(zmax < 1e300) || !(scale < 1e300);  // NaN, Inf, all zero, denormal range
+      auto bin_of = [&](R v) -> unsigned {
+        const double b = fabs((double)v) * scale;
+        const unsigned ub = (unsigned)b;  // b in [0, 2048 (1 + eps)]
+        return ub < (unsigned)kTrBins ? ub : (unsigned)kTrBins - 1u;
+      };
+      long long need = r;
+      unsigned sel = 0;
+      if (!hard) {
+        // ---- one histogram pass ----------------------------------------------
+#pragma unroll
+        for (int s = 0; s < kTrE; ++s)
+          if ((valid >> s) & 1u) atomicAdd(&sh->hist[bin_of(z[s])], 1u);
+      }
+      cluster.sync();  // every CTA's histogram is complete (a hard problem still keeps the barriers aligned)
+      if (!hard) {
+        for (int b = t; b < kTrBins; b += kTrThreads) {
+          unsigned s = 0;
+          for (unsigned rr = 0; rr < csize; ++rr) s += cluster.map_shared_rank(sh->hist, rr)[b];
+          sh->tot[b] = s;
+        }
+      }
+      cluster.sync();  // remote reads done
+      long long bin_count = 0;
+      if (!hard) {
+        int c[kTrBpt], mine = 0;
+#pragma unroll
+        for (int j = 0; j < kTrBpt; ++j) {
+          c[j] = (int)sh->tot[kTrBins - 1 - kTrBpt * t - j];
+          mine += c[j];
+        }
+        int total;
+        long long above = block_excl_scan<kTrThreads>(mine, sh->ws, &total);
+#pragma unroll
+        for (int j = 0; j < kTrBpt; ++j) {
+          if (above < need && need <= above + c[j]) {
+            sh->sel_bin = kTrBins - 1 - kTrBpt * t - j;
+            sh->sel_above = above;
+            sh->sel_count = c[j];
+          }
+          above += c[j];
+        }
+        __syncthreads();
+        sel = (unsigned)sh->sel_bin;
+        need -= sh->sel_above;  // rank inside the threshold bin, 1-based
+        bin_count = sh->sel_count;
+        hard = bin_count > kTrCandMax;
+      }
+      // ---- gather the threshold bin into CTA 0 --------------------------------
+      if (!hard) {
+#pragma unroll
+        for (int k = 0; k < ROUNDS; ++k) {
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) {
+            const int s = k * VEC + e;
+            if (((valid >> s) & 1u) && bin_of(z[s]) == sel) {
+              const int pos = atomicAdd(&sh0->cand_count, 1);
+              sh0->cand_key[pos] = (unsigned long long)KT::key(z[s]);
+              sh0->cand_idx[pos] = (int)(cbase + ((long long)k * kTrThreads + t) * VEC + e);
+            }
+          }
+        }
+      }
+      cluster.sync();
+      if (!hard && crank == 0) {
+        // direct ranking: key descending, position ascending; the element of rank `need` is the threshold
+        const int C = sh->cand_count;
+        if (t < C) {
+          const unsigned long long mk = sh->cand_key[t];
+          const int mi = sh->cand_idx[t];
+          int rank = 1;
+          for (int j = 0; j < C; ++j) {
+            const unsigned long long kj = sh->cand_key[j];
+            rank += (kj > mk) || (kj == mk && sh->cand_idx[j] < mi);
+          }
+          if ((long long)rank == need) {
+            for (unsigned rr = 0; rr < csize; ++rr) {
+              TrShared* dst = cluster.map_shared_rank(sh, rr);
+              dst->thr_key = mk;
+              dst->thr_idx = mi;
+            }
+          }
+        }
+      }
+      cluster.sync();
+      if (!hard) {
+        const K tk = (K)sh->thr_key;
+        const int ti = sh->thr_idx;
+#pragma unroll
+        for (int k = 0; k < ROUNDS; ++k) {
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) {
+            const int s = k * VEC + e;
+            if ((valid >> s) & 1u) {
+              const K key = KT::key(z[s]);
+              const int gi = (int)(cbase + ((long long)k * kTrThreads + t) * VEC + e);
+              if (key > tk || (key == tk && gi <= ti)) keepmask |= 1u << s;
+            }
+          }
+        }
+      }
+    }
+    if (t == 0 && crank == 0) fallback[prob] = hard ? 1 : 0;
+
+    // ---- write y once (a flagged problem is written by the radix kernel) ------
+    if (!hard) {
+#pragma unroll
+      for (int k = 0; k < ROUNDS; ++k) {
+        const long long li = ((long long)k * kTrThreads + t) * VEC;
+        if (li < cnt) {
+          Pack<R, VEC> o;
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) {
+            const int s = k * VEC + e;
+            const R zz = ((keepmask >> s) & 1u) ? z[s] : R(0);
+            R v = zz - xs_sm[li + e];  // y .-= xk .+ sj   (:70)
+            if (BINF) v = jl_min(jl_max(v, -delta), delta);  // shiftedIndBallL0BInf.jl:91
+            o.v[e] = v;
+          }
+          st_stream(y + pbase + cbase + li, o);
+        }
       }
     }
     cluster.sync();  // shared state is reused by the next problem
@@ -562,34 +820,55 @@ static int32_t topr_global(spx_ctx* ctx, int64_t n, R* y, const R* xk, const R* 
   return SPX_OK;
 }
 
-template <class R, bool BINF, bool VECLD>
-static int32_t topr_cluster_launch(spx_ctx* ctx, int64_t nprob, int64_t n, R* y, const R* xk, const R* sj, const R* q,
-                                   int64_t r, R delta) {
-  auto kern = topr_cluster_kernel<R, BINF, VECLD>;
-  int csize = 1;
-  while ((long long)csize * kTrChunk < n) csize <<= 1;
-  const size_t smem = ((sizeof(TrShared) + 15) / 16) * 16 + sizeof(R) * (size_t)kTrChunk;
+template <class Kern>
+static int32_t cluster_grid(spx_ctx* ctx, Kern kern, int csize, size_t smem, int64_t nprob, cudaLaunchConfig_t* cfg,
+                            cudaLaunchAttribute* attr) {
   SPX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  cudaLaunchConfig_t cfg = {};
-  cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = csize;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
-  cfg.blockDim = dim3(kTrThreads);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = ctx->stream;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  cfg.gridDim = dim3(csize);
+  cfg->blockDim = dim3(kTrThreads);
+  cfg->dynamicSmemBytes = smem;
+  cfg->stream = ctx->stream;
+  cfg->attrs = attr;
+  cfg->numAttrs = 1;
+  cfg->gridDim = dim3(csize);
   int max_clusters = 0;
-  cudaError_t e = cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg);
+  cudaError_t e = cudaOccupancyMaxActiveClusters(&max_clusters, kern, cfg);
   if (e != cudaSuccess || max_clusters < 1) max_clusters = ctx->sm_count / csize;
   if (max_clusters < 1) max_clusters = 1;
   long long nclusters = nprob < max_clusters ? nprob : max_clusters;
-  cfg.gridDim = dim3((unsigned)(nclusters * csize));
-  SPX_CUDA(cudaLaunchKernelEx(&cfg, kern, y, xk, sj, q, (long long)n, (long long)r, delta, (long long)nprob));
-  ctx->launches++;
+  cfg->gridDim = dim3((unsigned)(nclusters * csize));
+  return SPX_OK;
+}
+
+template <class R, bool BINF, bool VECLD>
+static int32_t topr_cluster_launch(spx_ctx* ctx, int64_t nprob, int64_t n, R* y, const R* xk, const R* sj, const R* q,
+                                   int64_t r, R delta) {
+  int csize = 1;
+  while ((long long)csize * kTrChunk < n) csize <<= 1;
+  const size_t smem = ((sizeof(TrShared) + 15) / 16) * 16 + sizeof(R) * (size_t)kTrChunk;
+  int32_t st = ensure_scratch(ctx, (size_t)nprob + 4096);
+  if (st != SPX_OK) return st;
+  unsigned char* flags = (unsigned char*)ctx->d_scratch + 4096;  // the first 4 KiB belong to the reductions
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  {  // linear-bin select: decides every ordinary problem
+    auto kern = topr_cluster_lin_kernel<R, BINF, VECLD>;
+    st = cluster_grid(ctx, kern, csize, smem, nprob, &cfg, attr);
+    if (st != SPX_OK) return st;
+    SPX_CUDA(cudaLaunchKernelEx(&cfg, kern, y, xk, sj, q, (long long)n, (long long)r, delta, (long long)nprob, flags));
+    ctx->launches++;
+  }
+  {  // radix select on the problems it flagged (NaN / Inf / all-zero / crowded threshold bin)
+    auto kern = topr_cluster_kernel<R, BINF, VECLD>;
+    st = cluster_grid(ctx, kern, csize, smem, nprob, &cfg, attr);
+    if (st != SPX_OK) return st;
+    SPX_CUDA(cudaLaunchKernelEx(&cfg, kern, y, xk, sj, q, (long long)n, (long long)r, delta, (long long)nprob,
+                                (const unsigned char*)flags));
+    ctx->launches++;
+  }
   return SPX_OK;
 }
 
@@ -622,6 +901,16 @@ static int32_t prox_indballl0(spx_ctx* ctx, int64_t nprob, int64_t n, R* y, cons
 
 using namespace spx;
 
+#ifdef SPX_TR_TIMING
+extern "C" int32_t spx_debug_topr_timing(unsigned long long* out8, int reset) {
+  cudaMemcpyFromSymbol(out8, g_tr_t, 64);
+  if (reset) {
+    unsigned long long z[8] = {0};
+    cudaMemcpyToSymbol(g_tr_t, z, 64);
+  }
+  return 0;
+}
+#endif
 extern "C" int32_t spx_prox_indballl0_f64(spx_ctx* ctx, int64_t nprob, int64_t n, double* y, const double* xk,
                                           const double* sj, const double* q, int64_t r, int32_t binf, double delta) {
   return prox_indballl0<double>(ctx, nprob, n, y, xk, sj, q, r, binf, delta);

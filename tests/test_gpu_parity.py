@@ -496,3 +496,26 @@ def test_indballl0_batched(dt):
     for p in range(nprob):
         sl = slice(p * n, (p + 1) * n)
         assert np.array_equal(got[sl], orc.prox_indballl0(xk[sl], sj[sl], q[sl], r, delta=1.0)), p
+
+
+@pytest.mark.parametrize("dt", DT)
+def test_indballl0_batch_mixing_ordinary_and_flagged_problems(dt):
+    """The linear-bin select flags what it cannot decide cheaply (crowded threshold bin, Inf/NaN, all zeros)
+    and the radix kernel finishes exactly those problems: a batch mixing both kinds must match the oracle."""
+    nprob, n, r = 9, 20_000, 700
+    xk, sj, q = inputs(nprob * n, dt)
+    xk = xk.copy(); sj = sj.copy(); q = q.copy()
+    sl = lambda p: slice(p * n, (p + 1) * n)  # noqa: E731
+    xk[sl(1)] = 0; sj[sl(1)] = 0; q[sl(1)] = dt(1.5)                      # all equal: 20000 ties in one bin
+    xk[sl(3)] = 0; sj[sl(3)] = 0; q[sl(3)] = 0                             # all zeros
+    q[3 * n + 17] = 0
+    q[4 * n + 5] = np.inf                                                  # an infinity
+    q[5 * n + 123] = np.nan                                                # a NaN (sorts largest)
+    q[sl(7)] = (np.round(q[sl(7)] * 4) / 4).astype(dt); xk[sl(7)] = 0; sj[sl(7)] = 0   # ~20 distinct magnitudes
+    psi = sp.shifted(sp.shifted(sp.IndBallL0(r), T(xk), nprob=nprob), T(sj))
+    y = torch.empty(nprob * n, dtype=T(q).dtype, device=DEV)
+    sp.prox_(y, psi, T(q), 1.0)
+    got = N(y)
+    for p in range(nprob):
+        ref = orc.prox_indballl0(xk[sl(p)], sj[sl(p)], q[sl(p)], r)
+        assert np.array_equal(got[sl(p)], ref, equal_nan=True), p
