@@ -485,9 +485,9 @@ __global__ void __launch_bounds__(kTrThreads, 1)
       if (!hard && crank == 0) {
         // direct ranking: key descending, position ascending; the element of rank `need` is the threshold
         const int C = sh->cand_count;
-        if (t < C) {
-          const unsigned long long mk = sh->cand_key[t];
-          const int mi = sh->cand_idx[t];
+        for (int ci = t; ci < C; ci += kTrThreads) {
+          const unsigned long long mk = sh->cand_key[ci];
+          const int mi = sh->cand_idx[ci];
           int rank = 1;
           for (int j = 0; j < C; ++j) {
             const unsigned long long kj = sh->cand_key[j];
