@@ -203,12 +203,26 @@ __device__ __forceinline__ LhalfStart lhalf_start(float zf, float c4f) {
 }
 // s² for the largest root s; a = σλ/2.  NEAR1: t may approach 1 (Box form), where the slope
 // az(4d² - 1) shrinks: one more step and a compensated last residual (s² = p + e, p - az by Fast2Sum).
-template <bool NEAR1> __device__ __forceinline__ double lhalf_newton(double az, double a, const LhalfStart& st) {
+// SINGLE: the result is rounded to Float32 (R = Float32): one Float64 step already leaves an error of
+// ~1e-11, far below a Float32 ulp (two where the slope shrinks).
+template <bool NEAR1, bool SINGLE = false>
+__device__ __forceinline__ double lhalf_newton(double az, double a, const LhalfStart& st) {
   const double inv = (double)st.inv;
   double s = (double)st.s0;
   double u = __fma_rn(s, s, -az);
   double f = __fma_rn(s, u, a);
   s = __fma_rn(-f, inv, s);
+  if (SINGLE) {
+    if (NEAR1 && st.t32 > 0.9f) {
+      u = __fma_rn(s, s, -az);
+      f = __fma_rn(s, u, a);
+      s = __fma_rn(-f, inv, s);
+      u = __fma_rn(s, s, -az);
+      f = __fma_rn(s, u, a);
+      s = __fma_rn(-f, inv, s);
+    }
+    return s * s;
+  }
   if (NEAR1 && st.t32 > 0.9f) {
     u = __fma_rn(s, s, -az);
     f = __fma_rn(s, u, a);
@@ -353,7 +367,7 @@ template <class R, bool PSI> struct ProxLhalf {
     // runs the straight-line Newton (nearly every warp holds an element above the threshold).
     const bool above = !((double)az <= p);
     const float zf = (float)az;
-    double mag = lhalf_newton<false>((double)az, c4 + c4, lhalf_start(zf, c4f));
+    double mag = lhalf_newton<false, sizeof(R) == 4>((double)az, c4 + c4, lhalf_start(zf, c4f));
     if (above && !(fast && lhalf_f32_range(zf))) mag = lhalf_mag_ref<R>(az, c4);
     R o = above ? (R)copysign(mag, (double)z) : R(0);
     o = o - xs;
@@ -763,7 +777,7 @@ template <class R, bool PSI> struct ProxLhalfBox {
     // stationary point (candidate 4)
     const float zf = (float)axsq;
     const LhalfStart st = lhalf_start(zf, c4f);
-    const double mag = lhalf_newton<true>((double)axsq, k.c4 + k.c4, st);
+    const double mag = lhalf_newton<true, sizeof(R) == 4>((double)axsq, k.c4 + k.c4, st);
     const double val = copysign(mag, (double)xsq);
     const bool real_branch = st.t32 <= 0.998f;
     bool hard = !(fast && lhalf_f32_range(zf)) || !(st.t32 <= 0.998f || st.t32 >= 1.002f);
