@@ -6,7 +6,8 @@
 
 Every rank holds a contiguous shard of the same synthetic vectors.  Checks that (1) the all-reduced ψ(y)
 equals the single-device value, (2) the sharded ShiftedNormL1B2 prox! (K partial sums all-reduced per pass,
-root search replicated) reproduces the single-device result bit for bit on every shard."""
+root search replicated) reproduces the single-device result bit for bit on every shard, (3) the top-r projection
+of one vector spread over the ranks (histogram all-reduce per radix digit) is identical to the single-device one."""
 import ctypes as C
 import os
 import sys
@@ -66,6 +67,19 @@ def main():
         diff = float((ys - yf[lo:hi]).abs().max())
         ok &= diff <= tol * 4.0
         ok &= abs(vs - vf) <= 1e-9 * abs(vf) if dtype == torch.float64 else abs(vs - vf) <= 1e-4 * abs(vf)
+        # (3) one vector's top-r across the ranks: histogram all-reduce per radix digit, cross-shard tie rule
+        r_top = 100_003
+        qq = (full[2] * 64).round() / 64  # quantised: many ties at the threshold
+        pf = sp.shifted(sp.shifted(sp.IndBallL0(r_top), full[0], 1.0, sp.NormLinf(1.0)), full[1])
+        sp.prox_(yf, pf, qq, 1.0)
+        ps = sp.shifted(sp.shifted(sp.IndBallL0(r_top), xk, 1.0, sp.NormLinf(1.0)), sj)
+        yt = torch.empty_like(q)
+        sharded.prox_indballl0_sharded_(yt, ps, qq[lo:hi].clone(), n)
+        top_ok = bool(torch.equal(yt, yf[lo:hi]))
+        ok &= top_ok
+        if rank == 0:
+            print(f"[{dtype}] world={world} sharded top-r (r={r_top}, quantised ties) identical to single device: {top_ok}",
+                  flush=True)
         if rank == 0:
             print(f"[{dtype}] world={world} psi rel err {rel:.2e}; l1b2 passes {bs.last_passes} (single {bf.last_passes}), "
                   f"max |y_sharded - y_single| {diff:.3e}, psi {vs:.12g} vs {vf:.12g}", flush=True)
