@@ -4,10 +4,11 @@
 //   if Δ <= χ(y):  η = root of η - χ(ProjB(-xk η/Δ));  y = ProjB(-xk η/Δ) Δ/η
 //   y -= sj
 //
-// Every evaluation of the residual is a full streaming pass over xk, sj, q (3R per element, nothing
-// written), so the pass count is what matters.  A pass evaluates up to 8 trial values of η at once and
-// returns, next to Σw², the sum Σ w dw/dη that gives the derivative of the residual (the pass stays
-// HBM-bound: ~12 instructions per trial).  Roots' one-point-per-pass iteration becomes a safeguarded
+// Every evaluation of the residual is a full streaming pass over xk, sj, q (3R per element; 2R once
+// mid = sj + q has been stashed in the output vector, which the search is free to use as scratch when it
+// aliases no input), so the pass count is what matters.  A pass evaluates up to 4 (last pass: 8) trial values
+// of η at once and returns, next to Σw², the sum Σ w dw/dη that gives the derivative of the residual (~12
+// instructions per trial: four trials keep the pass HBM-bound, eight are FP64-issue bound).  Roots' one-point-per-pass iteration becomes a safeguarded
 // Newton / secant search whose bracket closes superlinearly from both sides: the residual at η = Δ comes
 // from the very pass that decides whether the ball is active, a Newton step from there brackets the
 // root, each further pass evaluates the secant point and the Newton points of both ends, and the last
@@ -28,10 +29,13 @@ template <int K> struct ScaleSet { double s[K]; };
 // Σ_i ProjB(z_i(k))² and Σ_i ProjB(z_i(k)) dProjB/dscale (= Σ over the unclamped entries of z_i (-xk_i))
 // for K scalings in one pass.  The clamp is two compares and selects (a NaN z stays NaN; a NaN bound is
 // caught by the `mid - mid` poison term, so a NaN anywhere still makes every norm NaN like Base.min/max).
-template <class R, int K, int VEC>
+// MODE 0: mid = sj + q from the two vectors.  MODE 1: same, and mid is stored to `midbuf` (the first pass, when
+// the output vector aliases no input and can serve as scratch).  MODE 2: `sj` IS the stored mid, q is not read:
+// every later pass of the search moves 2R instead of 3R.
+template <class R, int K, int VEC, int MODE>
 __global__ void __launch_bounds__(kEwThreads)
-    l1b2_norm_kernel(const R* xk, const R* sj, const R* q, long long n, R ls, bool use_scale, ScaleSet<K> sc,
-                     int nblocks_stride, Partial* __restrict__ partials) {
+    l1b2_norm_kernel(const R* xk, const R* sj, const R* q, R* midbuf, long long n, R ls, bool use_scale,
+                     ScaleSet<K> sc, int nblocks_stride, Partial* __restrict__ partials) {
   double acc[K], dot[K];
 #pragma unroll
   for (int k = 0; k < K; ++k) { acc[k] = 0.0; dot[k] = 0.0; }
@@ -42,12 +46,13 @@ __global__ void __launch_bounds__(kEwThreads)
   const long long nvec = n / VEC;
   // one packet of VEC elements: products summed in R over the packet (4 terms for Float32: conversions to
   // Float64 are quarter-rate, one per packet and trial instead of two per element), then added in Float64
-  auto packet = [&](const R* x, const R* s, const R* qq, int m) {
+  auto packet = [&](const R* x, const R* s, const R* qq, int m, R* mid_out) {
     R lo[VEC], hi[VEC], nx[VEC];
 #pragma unroll
     for (int e = 0; e < VEC; ++e) {
       const bool on = e < m;
-      const R mid = on ? s[e] + qq[e] : R(0);
+      const R mid = on ? (MODE == 2 ? s[e] : s[e] + qq[e]) : R(0);
+      if (MODE == 1) mid_out[e] = mid;
       lo[e] = mid - ls;
       hi[e] = mid + ls;
       nx[e] = on ? -x[e] : R(0);
@@ -83,17 +88,19 @@ __global__ void __launch_bounds__(kEwThreads)
     }
   };
   for (long long v = (long long)blockIdx.x * kEwThreads + threadIdx.x; v < nvec; v += (long long)gridDim.x * kEwThreads) {
-    Pack<R, VEC> a, b, c;
+    Pack<R, VEC> a, b, c, mo;
     ld_stream(xk + v * VEC, a);
     ld_stream(sj + v * VEC, b);
-    ld_stream(q + v * VEC, c);
-    packet(a.v, b.v, c.v, VEC);
+    if (MODE != 2) ld_stream(q + v * VEC, c);
+    packet(a.v, b.v, c.v, VEC, mo.v);
+    if (MODE == 1) st_stream(midbuf + v * VEC, mo);
   }
   if (VEC > 1 && blockIdx.x == gridDim.x - 1) {
     const long long i = nvec * VEC + threadIdx.x;
     if (i < n) {
-      R x1[VEC] = {xk[i]}, s1[VEC] = {sj[i]}, q1[VEC] = {q[i]};
-      packet(x1, s1, q1, 1);
+      R x1[VEC] = {xk[i]}, s1[VEC] = {sj[i]}, q1[VEC] = {MODE != 2 ? q[i] : R(0)}, m1[VEC];
+      packet(x1, s1, q1, 1, m1);
+      if (MODE == 1) midbuf[i] = m1[0];
     }
   }
 #pragma unroll
@@ -109,10 +116,10 @@ __global__ void __launch_bounds__(kEwThreads)
 
 template <class R, int K>
 static int32_t norm_pass_k(spx_ctx* ctx, int64_t n, const R* xk, const R* sj, const R* q, R ls, const double* scale,
-                           int nscale, double* out, double* dot_out) {
+                           int nscale, double* out, double* dot_out, int mode, R* midbuf) {
   ScaleSet<K> sc;
   for (int k = 0; k < K; ++k) sc.s[k] = scale ? scale[k < nscale ? k : nscale - 1] : 1.0;
-  const uintptr_t bits = (uintptr_t)xk | (uintptr_t)sj | (uintptr_t)q;
+  const uintptr_t bits = (uintptr_t)xk | (uintptr_t)sj | (uintptr_t)q | (uintptr_t)midbuf;
   const bool vec = (bits & 15u) == 0;
   constexpr int VECW = 16 / (int)sizeof(R);
   const long long nv = vec ? n / VECW : n;
@@ -120,12 +127,19 @@ static int32_t norm_pass_k(spx_ctx* ctx, int64_t n, const R* xk, const R* sj, co
   if (want < 1) want = 1;
   long long cap = (long long)ctx->sm_count * 8;
   const int grid = (int)(want < cap ? want : cap);
-  if (vec)
-    l1b2_norm_kernel<R, K, VECW><<<grid, kEwThreads, 0, ctx->stream>>>(xk, sj, q, n, ls, scale != nullptr, sc, grid,
-                                                                      ctx->d_partials);
-  else
-    l1b2_norm_kernel<R, K, 1><<<grid, kEwThreads, 0, ctx->stream>>>(xk, sj, q, n, ls, scale != nullptr, sc, grid,
-                                                                   ctx->d_partials);
+#define SPX_L1B2_LAUNCH(V, M)                                                                                  \
+  l1b2_norm_kernel<R, K, V, M><<<grid, kEwThreads, 0, ctx->stream>>>(xk, sj, q, midbuf, n, ls, scale != nullptr, sc, \
+                                                                     grid, ctx->d_partials)
+  if (vec) {
+    if (mode == 0) SPX_L1B2_LAUNCH(VECW, 0);
+    else if (mode == 1) SPX_L1B2_LAUNCH(VECW, 1);
+    else SPX_L1B2_LAUNCH(VECW, 2);
+  } else {
+    if (mode == 0) SPX_L1B2_LAUNCH(1, 0);
+    else if (mode == 1) SPX_L1B2_LAUNCH(1, 1);
+    else SPX_L1B2_LAUNCH(1, 2);
+  }
+#undef SPX_L1B2_LAUNCH
   ctx->launches++;
   SPX_CUDA(cudaGetLastError());
   int32_t st = finalize_partials(ctx, grid, K, false);
@@ -138,17 +152,17 @@ static int32_t norm_pass_k(spx_ctx* ctx, int64_t n, const R* xk, const R* sj, co
 
 template <class R>
 static int32_t norm_pass(spx_ctx* ctx, int64_t n, const R* xk, const R* sj, const R* q, R ls, const double* scale,
-                         int nscale, double* out, double* dot_out = nullptr) {
+                         int nscale, double* out, double* dot_out = nullptr, int mode = 0, R* midbuf = nullptr) {
   if (n == 0) {
     for (int k = 0; k < nscale; ++k) out[k] = 0.0;
     if (dot_out)
       for (int k = 0; k < nscale; ++k) dot_out[k] = 0.0;
     return SPX_OK;
   }
-  if (nscale <= 1) return norm_pass_k<R, 1>(ctx, n, xk, sj, q, ls, scale, nscale, out, dot_out);
-  if (nscale <= 4) return norm_pass_k<R, 4>(ctx, n, xk, sj, q, ls, scale, nscale, out, dot_out);
-  if (nscale <= 8) return norm_pass_k<R, 8>(ctx, n, xk, sj, q, ls, scale, nscale, out, dot_out);
-  return norm_pass_k<R, 16>(ctx, n, xk, sj, q, ls, scale, nscale, out, dot_out);
+  if (nscale <= 1) return norm_pass_k<R, 1>(ctx, n, xk, sj, q, ls, scale, nscale, out, dot_out, mode, midbuf);
+  if (nscale <= 4) return norm_pass_k<R, 4>(ctx, n, xk, sj, q, ls, scale, nscale, out, dot_out, mode, midbuf);
+  if (nscale <= 8) return norm_pass_k<R, 8>(ctx, n, xk, sj, q, ls, scale, nscale, out, dot_out, mode, midbuf);
+  return norm_pass_k<R, 16>(ctx, n, xk, sj, q, ls, scale, nscale, out, dot_out, mode, midbuf);
 }
 
 // y = ProjB(-xk scale) post - sj, with Σ|xk+sj+y| and Σ(sj+y)² for ψ(y)
@@ -161,8 +175,9 @@ template <class R, bool PSI> struct L1B2Finish {
   R* y;
   R ls, scale, post;
   bool use_scale;
+  bool have_mid;  // in[2] is the stashed sj + q (the output vector itself) instead of q
   __device__ __forceinline__ R apply(const R (&x)[NIN], long long, Partial& acc) const {
-    const R mid = x[1] + x[2];
+    const R mid = have_mid ? x[2] : x[1] + x[2];
     const R lo = mid - ls, hi = mid + ls;
     const R nx = -x[0];
     const R z = use_scale ? nx * scale : nx;
@@ -180,7 +195,7 @@ template <class R, bool PSI> struct L1B2Finish {
 
 template <class R>
 static int32_t finish_pass(spx_ctx* ctx, int64_t n, R* y, const R* xk, const R* sj, const R* q, R ls, bool use_scale,
-                           R scale, R post, double* psi_sum, double* w_sumsq) {
+                           R scale, R post, double* psi_sum, double* w_sumsq, bool have_mid = false) {
   const bool psi = psi_sum != nullptr || w_sumsq != nullptr;
   int nb = 0;
   int32_t st;
@@ -189,6 +204,8 @@ static int32_t finish_pass(spx_ctx* ctx, int64_t n, R* y, const R* xk, const R* 
     op.in[0] = xk; op.in[1] = sj; op.in[2] = q;
     op.fill[0] = op.fill[1] = op.fill[2] = R(0);
     op.y = y; op.ls = ls; op.scale = scale; op.post = post; op.use_scale = use_scale;
+    op.have_mid = have_mid;
+    if (have_mid) op.in[2] = y;
     st = ew_launch(ctx, ctx->stream, op, n, 0, ctx->d_partials, &nb);
     if (st != SPX_OK) return st;
     st = finalize_partials(ctx, nb, 1, false);
@@ -201,6 +218,8 @@ static int32_t finish_pass(spx_ctx* ctx, int64_t n, R* y, const R* xk, const R* 
   op.in[0] = xk; op.in[1] = sj; op.in[2] = q;
   op.fill[0] = op.fill[1] = op.fill[2] = R(0);
   op.y = y; op.ls = ls; op.scale = scale; op.post = post; op.use_scale = use_scale;
+  op.have_mid = have_mid;
+  if (have_mid) op.in[2] = y;
   return ew_launch(ctx, ctx->stream, op, n, 0, ctx->d_partials, &nb);
 }
 
@@ -223,13 +242,24 @@ static int32_t prox_l1b2(spx_ctx* ctx, int64_t n, R* y, const R* xk, const R* sj
   const R lam = (R)lambda_, sig = (R)sigma_, delta = (R)delta_, chil = (R)chi_lambda_;
   const R ls = lam * sig;
   int passes = 0;
+  // y as scratch for mid = sj + q while the search runs (2R per pass instead of 3R): only when it overlaps no input
+  auto disjoint = [&](const R* p) {
+    return (const char*)p + (size_t)n * sizeof(R) <= (const char*)y || (const char*)y + (size_t)n * sizeof(R) <= (const char*)p;
+  };
+  const bool can_stash = n > 0 && disjoint(xk) && disjoint(sj) && disjoint(q);
+  bool stashed = false;
   // K residuals per pass: f_k = η_k - χ(ProjB(-xk η_k/Δ)) and their derivatives
   // f'_k = 1 - χ (Σ w dw/dscale) / (‖w‖ Δ)
   auto eval = [&](const std::vector<R>& etas, bool use_scale, std::vector<R>& f, std::vector<R>& df) -> int32_t {
     const int m = (int)etas.size();
     double scale[kMaxScale], ss[2 * kMaxScale];
     for (int k = 0; k < m; ++k) scale[k] = (double)(etas[k] / delta);
-    int32_t st = norm_pass<R>(ctx, n, xk, sj, q, ls, use_scale ? scale : nullptr, m, ss, ss + m);
+    // the first pass decides whether the ball is active at all and leaves y alone; the second (the first of
+    // the search proper) also stores mid into y; later passes read it back instead of sj and q
+    const int mode = (!can_stash || passes == 0) ? 0 : (stashed ? 2 : 1);
+    int32_t st = norm_pass<R>(ctx, n, xk, mode == 2 ? (const R*)y : sj, q, ls, use_scale ? scale : nullptr, m, ss,
+                              ss + m, mode, y);
+    if (mode == 1) stashed = true;
     if (st != SPX_OK) return st;
     ++passes;
     if (reduce) {
@@ -251,7 +281,7 @@ static int32_t prox_l1b2(spx_ctx* ctx, int64_t n, R* y, const R* xk, const R* sj
   auto finish = [&](bool use_scale, R scale, R post) -> int32_t {
     double s = 0.0, s2 = 0.0;
     int32_t st = finish_pass<R>(ctx, n, y, xk, sj, q, ls, use_scale, scale, post, psi_out ? &s : nullptr,
-                                psi_out ? &s2 : nullptr);
+                                psi_out ? &s2 : nullptr, stashed);
     ++passes;
     if (passes_out) *passes_out = passes;
     if (st != SPX_OK || psi_out == nullptr) return st;
@@ -355,7 +385,8 @@ static int32_t prox_l1b2(spx_ctx* ctx, int64_t n, R* y, const R* xk, const R* sj
         const R best = (std::fabs(fa) <= std::fabs(fb)) ? xa : xb;
         R err = std::max(std::fabs(best - xs), std::fabs(xa - xb));
         err = std::max(err, R(4) * (std::nextafter(best, b) - best));
-        const R c[8] = {xs, xa, xb, best - err, best + err, best - err / R(16), best + err / R(16), best};
+        // four trial points keep the pass HBM-bound (eight are FP64-issue bound)
+        const R c[4] = {xs, best, best - err, best + err};
         for (R x : c) pts.push_back(x);
       }
       std::sort(pts.begin(), pts.end());

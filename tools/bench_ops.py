@@ -118,8 +118,11 @@ def main():
         psi = two(sp.NormL1(lam), 0.5 * full, sp.NormL2(1.0))
         sp.prox_(y, psi, q, sigma)
         passes = psi.last_passes
-        timeit("prox_l1b2", lambda: sp.prox_(y, psi, q, sigma), 4 * R + 3 * R * (passes - 1),
-               note=f"{passes} passes (3R each) + 1 finish (4R)")
+        # bytes actually moved: decision pass 3R, first search pass 3R + 1W (stashes sj + q in y), later search
+        # passes 2R, finish 3R + 1W
+        nsearch = max(passes - 2, 0)
+        timeit("prox_l1b2", lambda: sp.prox_(y, psi, q, sigma), 3 * R + (4 * R if nsearch else 0) + 2 * R * max(nsearch - 1, 0) + 4 * R,
+               note=f"{passes - 1} norm passes (3R, 3R+1W, then 2R each) + 1 finish (4R)")
         timeit("prox_l1b2_inactive", lambda: sp.prox_(y, psi0, q, sigma), 7 * R, note="1 norm pass + finish")
     # groups of 64 (and ragged)
     for gname in ("g64", "ragged"):
