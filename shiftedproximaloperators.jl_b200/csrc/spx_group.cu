@@ -429,7 +429,7 @@ __device__ __forceinline__ float ulp_step(float x, int k) { return __int_as_floa
 // froot.  Same end state, an order of magnitude fewer evaluations: froot is smooth between the kinks of
 // the soft threshold and nearly linear above the root, so safeguarded Newton steps from lmax (the
 // derivative comes out of the same pass over the group) converge in three or four evaluations; as soon
-// as a step lands within a few ulps of an end of the bracket the next evaluation is placed k ulps inside
+// as a step lands within k ulps (k = 1, then 4, 16, ...) of an end of the bracket the next evaluation is placed k ulps inside
 // that end -- stepping over the root, which leaves a bracket of k ulps that two or three midpoint steps
 // close.  A step that leaves the bracket is replaced by the midpoint, and after 40 steps (never
 // observed) the search degrades to plain bisection, which terminates by itself.
@@ -465,7 +465,7 @@ __device__ __forceinline__ bool binf_solve(const View& gv, bool valid, R lam, R 
   R a = lmin, fa = R(0), bb = lmax, fb = R(0);
   R x = lmax, fx = R(0), dx = R(1);  // Newton state
   bool zero_out = false, done = !valid || !(lmin > R(0));
-  int kulp = 4;
+  int kulp = 1;
   for (int it = -2; it < 400; ++it) {
     R xn;
     bool probed = false;
