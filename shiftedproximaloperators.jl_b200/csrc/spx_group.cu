@@ -340,11 +340,12 @@ template <class R> struct TileView {
     }
     return sub_sum(ss, t.L);
   }
-  // Σ softthres(sol/σ - step xk, Δ step)², Σ sol², Σ xk²
-  __device__ __forceinline__ void norms(R step, R dstep, double& z2, double& s2, double& x2) const {
+  // Σ (σ softthres(sol/σ - step xk, Δ step))² = Σ S(sol - σ step xk, σ Δ step)² (division-free: lmax is only a
+  // bracket end), Σ sol², Σ xk²; sstep = σ step, sdstep = σ Δ step
+  __device__ __forceinline__ void norms(R sstep, R sdstep, double& z2, double& s2, double& x2) const {
 #pragma unroll
     for (int j = 0; j < kEPL; ++j) {
-      const double z = (double)softthres_fast(by_sigma(t.sol[j]) - step * t.xkr[j], dstep);
+      const double z = (double)softthres_fast(t.sol[j] - sstep * t.xkr[j], sdstep);
       z2 = __fma_rn(z, z, z2);
       s2 = __fma_rn((double)t.sol[j], (double)t.sol[j], s2);
       x2 = __fma_rn((double)t.xkr[j], (double)t.xkr[j], x2);
@@ -389,8 +390,8 @@ template <class R> struct LongView {
     }
     return warp_sum(ss);
   }
-  __device__ __forceinline__ void norms(R step, R dstep, double& z2, double& s2, double& x2) const {
-    z2 = sumsq([&](R, R u, R xg) -> R { return softthres_fast(u - step * xg, dstep); });
+  __device__ __forceinline__ void norms(R sstep, R sdstep, double& z2, double& s2, double& x2) const {
+    z2 = sumsq([&](R so, R, R xg) -> R { return softthres_fast(so - sstep * xg, sdstep); });
     s2 = sumsq([&](R so, R, R) -> R { return so; });
     x2 = sumsq([&](R, R, R xg) -> R { return xg; });
   }
@@ -457,8 +458,8 @@ __device__ __forceinline__ bool binf_solve(const View& gv, bool valid, R lam, R 
   const R dstep = delta * step;
   // the three norms of :97-100 in one pass
   double z2 = 0.0, s2 = 0.0, x2 = 0.0;
-  gv.norms(step, dstep, z2, s2, x2);
-  const R zlmax = (R)sqrt_fast(z2), nsol = (R)sqrt_fast(s2), nxk = (R)sqrt_fast(x2);
+  gv.norms(sigma * step, sigma * dstep, z2, s2, x2);
+  const R zlmax = (R)sqrt_fast(z2) / sigma, nsol = (R)sqrt_fast(s2), nxk = (R)sqrt_fast(x2);
   const R lmax = nsol + sigma * (zlmax + R(1) * lam * nxk);  // |(ϵ-1)/ϵ + 1| = 1 for ϵ = 1  (:100)
   // One froot call site (the kernel is instruction-cache bound otherwise): trips 0 and 1 evaluate the two
   // ends of the bracket, the following ones are the search.
