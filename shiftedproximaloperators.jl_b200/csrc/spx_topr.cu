@@ -40,7 +40,7 @@ constexpr int kTrCandMax = 1024;               // candidates of the threshold bi
 constexpr int kPickThreads = 1024;             // single-block digit pick of the global path
 
 #ifdef SPX_TR_TIMING
-__device__ unsigned long long g_tr_t[8];
+__device__ unsigned long long g_tr_t[16];
 #define TR_T(i)                                          \
   do {                                                   \
     if (threadIdx.x == 0 && blockIdx.x == 0) {           \
@@ -361,6 +361,9 @@ __global__ void __launch_bounds__(kTrThreads, 1)
     long long cnt = n - cbase;
     cnt = cnt < 0 ? 0 : (cnt > kTrChunk ? kTrChunk : cnt);
 
+#ifdef SPX_TR_TIMING
+    long long tr_last = clock64();
+#endif
     // ---- load: z in registers, xs in shared memory --------------------------
     R z[kTrE];
     unsigned valid = 0;
@@ -392,6 +395,8 @@ __global__ void __launch_bounds__(kTrThreads, 1)
     if (!select) {
       keepmask = (r >= n) ? valid : 0u;
     } else {
+      __syncthreads();
+      TR_T(8);  // load
       // ---- largest magnitude of the problem ---------------------------------
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
@@ -408,6 +413,7 @@ __global__ void __launch_bounds__(kTrThreads, 1)
       __syncthreads();
       if (t < (int)csize) cluster.map_shared_rank(sh, t)->kmax_slot[crank] = sh->kmax_slot[crank];
       cluster.sync();
+      TR_T(9);  // kmax exchange
       K gmax = 0;
       for (unsigned rr = 0; rr < csize; ++rr) {
         const K v = (K)sh->kmax_slot[rr];
@@ -432,6 +438,8 @@ __global__ void __launch_bounds__(kTrThreads, 1)
         for (int s = 0; s < kTrE; ++s)
           if ((valid >> s) & 1u) atomicAdd(&sh->hist[bin_of(z[s])], 1u);
       }
+      __syncthreads();
+      TR_T(10);  // histogram
       cluster.sync();  // every CTA's histogram is complete (a hard problem still keeps the barriers aligned)
       if (!hard) {
         for (int b = t; b < kTrBins; b += kTrThreads) {
@@ -441,6 +449,7 @@ __global__ void __launch_bounds__(kTrThreads, 1)
         }
       }
       cluster.sync();  // remote reads done
+      TR_T(11);  // sync + remote sum + sync
       long long bin_count = 0;
       if (!hard) {
         int c[kTrBpt], mine = 0;
@@ -466,6 +475,7 @@ __global__ void __launch_bounds__(kTrThreads, 1)
         bin_count = sh->sel_count;
         hard = bin_count > kTrCandMax;
       }
+      TR_T(12);  // scan + pick
       // ---- gather the threshold bin into CTA 0 --------------------------------
       if (!hard) {
 #pragma unroll
@@ -482,6 +492,7 @@ __global__ void __launch_bounds__(kTrThreads, 1)
         }
       }
       cluster.sync();
+      TR_T(13);  // gather + sync
       if (!hard && crank == 0) {
         // direct ranking: key descending, position ascending; the element of rank `need` is the threshold
         const int C = sh->cand_count;
@@ -503,6 +514,7 @@ __global__ void __launch_bounds__(kTrThreads, 1)
         }
       }
       cluster.sync();
+      TR_T(14);  // ranking + sync
       if (!hard) {
         const K tk = (K)sh->thr_key;
         const int ti = sh->thr_idx;
@@ -542,6 +554,7 @@ __global__ void __launch_bounds__(kTrThreads, 1)
       }
     }
     cluster.sync();  // shared state is reused by the next problem
+    TR_T(15);  // keep masks + write + sync
   }
 }
 
@@ -903,10 +916,10 @@ using namespace spx;
 
 #ifdef SPX_TR_TIMING
 extern "C" int32_t spx_debug_topr_timing(unsigned long long* out8, int reset) {
-  cudaMemcpyFromSymbol(out8, g_tr_t, 64);
+  cudaMemcpyFromSymbol(out8, g_tr_t, 128);
   if (reset) {
-    unsigned long long z[8] = {0};
-    cudaMemcpyToSymbol(g_tr_t, z, 64);
+    unsigned long long z[16] = {0};
+    cudaMemcpyToSymbol(g_tr_t, z, 128);
   }
   return 0;
 }

@@ -26,14 +26,17 @@ args = (ctx, C.c_int64(nprob), C.c_int64(pn), C.c_void_p(y.data_ptr()), C.c_void
         C.c_void_p(sj.data_ptr()), C.c_void_p(q.data_ptr()), C.c_int64(r), C.c_int32(0), C.c_double(0.0))
 L.call("spx_prox_indballl0_f64", *args)
 torch.cuda.synchronize()
-out = (C.c_ulonglong * 8)()
+out = (C.c_ulonglong * 16)()
 L.lib().spx_debug_topr_timing(out, 1)
 L.call("spx_prox_indballl0_f64", *args)
 torch.cuda.synchronize()
 L.lib().spx_debug_topr_timing(out, 1)
-names = ["load", "local histogram", "cluster sync (hist ready)", "remote sum + sync", "scan + pick",
-         "keep masks / ties", "write + final sync"]
-tot = sum(out[i] for i in range(7))
-for i, nm in enumerate(names):
-    print(f"{nm:28s} {out[i]:12d} cycles  {100.0 * out[i] / tot:5.1f} %")
+names = {0: "radix: load", 1: "radix: local histogram", 2: "radix: cluster sync (hist ready)", 3: "radix: remote sum + sync",
+         4: "radix: scan + pick", 5: "radix: keep masks / ties", 6: "radix: write + final sync",
+         8: "lin: load", 9: "lin: kmax exchange", 10: "lin: histogram", 11: "lin: sync + remote sum + sync",
+         12: "lin: scan + pick", 13: "lin: gather + sync", 14: "lin: ranking + sync", 15: "lin: keep + write + sync"}
+tot = sum(out[i] for i in range(16))
+for i, nm in names.items():
+    if out[i]:
+        print(f"{nm:34s} {out[i]:12d} cycles  {100.0 * out[i] / tot:5.1f} %")
 print("total cycles of CTA 0:", tot)
