@@ -91,6 +91,19 @@ __device__ __forceinline__ double sub_sum(double v, int L) {
   return v;
 }
 
+// Next task of a warp: round-robin (deterministic: required when ψ(y) partial sums ride along), or, when the
+// tasks are very unequal and heavy (the Binf root search on long groups) and nothing order-dependent is
+// accumulated, from a global counter in chunks of kTaskChunk consecutive tasks (one atomic per chunk).
+constexpr int kTaskChunk = 1;
+__device__ __forceinline__ long long next_task(long long cur, long long nwarps, unsigned long long* counter,
+                                               int lane) {
+  if (counter == nullptr) return cur + nwarps;
+  if (cur >= 0 && ((cur + 1) % kTaskChunk) != 0) return cur + 1;  // still inside the claimed chunk
+  unsigned long long t = 0;
+  if (lane == 0) t = atomicAdd(counter, (unsigned long long)kTaskChunk);
+  return (long long)__shfl_sync(0xffffffffu, t, 0);
+}
+
 // ---- round planning ----------------------------------------------------------------------------
 // le[k] bit j: group j of the task has at most 8 << k elements (k = 0..5).  Returns k such that the
 // round holds 32 >> k groups of 1 << k lanes, or -1 when the group at `pos` is a long one.
@@ -227,13 +240,14 @@ template <class R, bool PSI, int PART>  // PART 0: groups of <= 256 elements, 1:
 __global__ void __launch_bounds__(kGroupThreads)
     group_l2_kernel(R* y, const R* xk, const R* sj, const R* q, long long ngroups,
                     const long long* __restrict__ offs, const R* __restrict__ lambda_g, R sigma,
-                    Partial* __restrict__ partials) {
+                    Partial* __restrict__ partials, unsigned long long* task_counter) {
   const int lane = threadIdx.x & 31;
   const long long warp = ((long long)blockIdx.x * kGroupThreads + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * kGroupThreads) >> 5;
   const long long ntasks = (ngroups + kTask - 1) / kTask;
   double psi = 0.0;
-  for (long long task = warp; task < ntasks; task += nwarps) {
+  for (long long task = task_counter ? next_task(-1, 0, task_counter, lane) : warp; task < ntasks;
+       task = next_task(task, nwarps, task_counter, lane)) {
     const long long g0 = task * kTask;
     const TaskHead th = load_task(offs, g0, ngroups, lane);
     // le[5]: groups of <= 256 elements (lanes beyond the task count as such)
@@ -535,12 +549,13 @@ template <class R, int PART>
 __global__ void __launch_bounds__(kGroupThreads, PART == 0 ? SPX_GB_MINB : 2)
     group_l2binf_kernel(R* y, const R* xk, const R* sj, const R* q, long long ngroups,
                         const long long* __restrict__ offs, const R* __restrict__ lambda_g, R sigma, R delta,
-                        UDiv<R> by_sigma) {
+                        UDiv<R> by_sigma, unsigned long long* task_counter) {
   const int lane = threadIdx.x & 31;
   const long long warp = ((long long)blockIdx.x * kGroupThreads + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * kGroupThreads) >> 5;
   const long long ntasks = (ngroups + kTask - 1) / kTask;
-  for (long long task = warp; task < ntasks; task += nwarps) {
+  for (long long task = task_counter ? next_task(-1, 0, task_counter, lane) : warp; task < ntasks;
+       task = next_task(task, nwarps, task_counter, lane)) {
     const long long g0 = task * kTask;
     const TaskHead th = load_task(offs, g0, ngroups, lane);
     // le[5]: groups of <= 256 elements (lanes beyond the task count as such)
@@ -873,9 +888,9 @@ static int32_t prox_group(spx_ctx* ctx, bool binf, int64_t n, R* y, const R* xk,
         const int grid0 = group_grid(ctx, ngroups, (const void*)group_l2_kernel<R, true, 0>);
         const int grid1 = group_grid(ctx, ngroups, (const void*)group_l2_kernel<R, true, 1>);
         group_l2_kernel<R, true, 0><<<grid0, kGroupThreads, 0, ctx->stream>>>(
-            y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, (R)sigma, ctx->d_partials);
+            y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, (R)sigma, ctx->d_partials, nullptr);
         group_l2_kernel<R, true, 1><<<grid1, kGroupThreads, 0, ctx->stream>>>(
-            y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, (R)sigma, ctx->d_partials + grid0);
+            y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, (R)sigma, ctx->d_partials + grid0, nullptr);
         ctx->launches += 2;
         SPX_CUDA(cudaGetLastError());
         int32_t st = finalize_partials(ctx, grid0 + grid1, 1, false);
@@ -885,10 +900,12 @@ static int32_t prox_group(spx_ctx* ctx, bool binf, int64_t n, R* y, const R* xk,
       }
       const int grid0 = group_grid(ctx, ngroups, (const void*)group_l2_kernel<R, false, 0>);
       const int grid1 = group_grid(ctx, ngroups, (const void*)group_l2_kernel<R, false, 1>);
+      // (a task counter does not pay here: the skipped tasks of a short-group problem would all hit one atomic)
+      unsigned long long* counter = nullptr;
       group_l2_kernel<R, false, 0><<<grid0, kGroupThreads, 0, ctx->stream>>>(
-          y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, (R)sigma, ctx->d_partials);
+          y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, (R)sigma, ctx->d_partials, nullptr);
       group_l2_kernel<R, false, 1><<<grid1, kGroupThreads, 0, ctx->stream>>>(
-          y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, (R)sigma, ctx->d_partials);
+          y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, (R)sigma, ctx->d_partials, counter);
       ctx->launches += 2;
       SPX_CUDA(cudaGetLastError());
       return SPX_OK;
@@ -897,10 +914,14 @@ static int32_t prox_group(spx_ctx* ctx, bool binf, int64_t n, R* y, const R* xk,
     by_sigma.set((R)sigma);
     const int grid0 = group_grid(ctx, ngroups, (const void*)group_l2binf_kernel<R, 0>);
     const int grid1 = group_grid(ctx, ngroups, (const void*)group_l2binf_kernel<R, 1>);
+    int32_t st0 = ensure_scratch(ctx, 4096);
+    if (st0 != SPX_OK) return st0;
+    unsigned long long* counter = (unsigned long long*)ctx->d_scratch;  // long groups: dynamic task hand-out
+    SPX_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), ctx->stream));
     group_l2binf_kernel<R, 0><<<grid0, kGroupThreads, 0, ctx->stream>>>(
-        y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, (R)sigma, (R)delta, by_sigma);
+        y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, (R)sigma, (R)delta, by_sigma, nullptr);
     group_l2binf_kernel<R, 1><<<grid1, kGroupThreads, 0, ctx->stream>>>(
-        y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, (R)sigma, (R)delta, by_sigma);
+        y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, (R)sigma, (R)delta, by_sigma, counter);
     ctx->launches += 2;
     SPX_CUDA(cudaGetLastError());
   }
