@@ -172,7 +172,9 @@ typedef struct spx_box_job_f32 {
   int32_t spx_iprox_l0_##SUF(spx_ctx* ctx, int64_t n, R* y, const R* xk, const R* sj,            \
                              const R* g, const R* d, double lambda, int64_t* first_bad_d,        \
                              double* psi_out);                                                   \
-  /* ShiftedRootNormLhalf.prox! shiftedRootNormLhalf.jl:41-63 (ψ.sol is not materialised) */     \
+  /* ShiftedRootNormLhalf.prox! shiftedRootNormLhalf.jl:41-63 (ψ.sol is not materialised). */    \
+  /* xk == sj == NULL: the unshifted RootNormLhalf.prox!(y, h, x = q, γ = sigma) of */           \
+  /* rootNormLhalf.jl:31-51; psi_out then receives its return value h(y). */                     \
   int32_t spx_prox_lhalf_##SUF(spx_ctx* ctx, int64_t n, R* y, const R* xk, const R* sj,          \
                                const R* q, double lambda, double sigma, double* psi_out);        \
   /* ---------------------------------------------------- Box / BInf (a8-a12) */                 \
@@ -227,6 +229,8 @@ typedef struct spx_box_job_f32 {
   /* ------------------------------------------------------ group norms (a14-a15) */             \
   /* ShiftedGroupNormL2.prox! shiftedGroupNormL2.jl:52-79; groups are contiguous index */       \
   /* ranges offs[g]..offs[g+1]-1 (device int64, ngroups+1 entries), lambda_g device R[ngroups] */\
+  /* xk == sj == NULL (prox_groupl2 only): the unshifted GroupNormL2.prox!(y, h, x = q, γ = sigma) of */ \
+  /* groupNormL2.jl:41-58; psi_out then receives its return value Σ_g λ_g ‖x_g‖ (input norms). */ \
   int32_t spx_prox_groupl2_##SUF(spx_ctx* ctx, int64_t n, R* y, const R* xk, const R* sj,        \
                                  const R* q, int64_t ngroups, const int64_t* offs,               \
                                  const R* lambda_g, double sigma, double* psi_out);              \

@@ -74,7 +74,12 @@ template <class R> static double lhalf_threshold(R nulam) {
 template <class R>
 static int32_t prox_lhalf(spx_ctx* ctx, int64_t n, R* y, const R* xk, const R* sj, const R* q, double lambda,
                           double sigma, double* psi_out) {
-  SPX_CHECK_VEC3(ctx, n, y, xk, sj, q);
+  // xk == sj == NULL: the unshifted RootNormLhalf prox! (rootNormLhalf.jl:31-51), shifts read as zeros
+  SPX_REQUIRE(ctx != nullptr, "null context");
+  SPX_REQUIRE(n >= 0, "n < 0");
+  SPX_REQUIRE(n == 0 || (y && q), "null device vector");
+  SPX_REQUIRE((xk == nullptr) == (sj == nullptr), "xk and sj must both be given or both be NULL");
+  DeviceGuard guard__(ctx->device);
   const R lam = (R)lambda, sig = (R)sigma;
   const R nulam = sig * lam;
   return run_sep<ProxLhalf, R>(ctx, n, SPX_H_LHALF, lam, psi_out, [&](auto& op) {

@@ -164,7 +164,8 @@ template <class R, bool KEEP_XS> struct Tile {
       xkr[j] = R(0);
       if (KEEP_XS) xs[j] = R(0);
       if (i < e) {
-        const R xi = ldv(xk + i), si = ldv(sj + i), qi = ldv(q + i);
+        // xk == NULL: the unshifted GroupNormL2 prox! (groupNormL2.jl:41-58), shifts read as zeros
+        const R xi = xk ? ldv(xk + i) : R(0), si = xk ? ldv(sj + i) : R(0), qi = ldv(q + i);
         sol[j] = (qi + xi) + si;  // shiftedGroupNormL2.jl:65, shiftedGroupNormL2Binf.jl:80
         xkr[j] = xi;
         if (KEEP_XS) xs[j] = xi + si;
@@ -188,8 +189,8 @@ __device__ __forceinline__ double l2_long_group(R* y, const R* xk, const R* sj, 
     for (int u = 0; u < 4; ++u) {
       const long long i = i0 + 32 * u;
       if (i < e) {
-        xv[u] = ldv(xk + i);
-        sv[u] = ldv(sj + i);
+        xv[u] = xk ? ldv(xk + i) : R(0);
+        sv[u] = xk ? ldv(sj + i) : R(0);
         qv[u] = ldv(q + i);
       }
     }
@@ -213,8 +214,8 @@ __device__ __forceinline__ double l2_long_group(R* y, const R* xk, const R* sj, 
     for (int u = 0; u < 4; ++u) {
       const long long i = i0 + 32 * u;
       if (i < e) {
-        xv[u] = xk[i];
-        sv[u] = sj[i];
+        xv[u] = xk ? xk[i] : R(0);
+        sv[u] = xk ? sj[i] : R(0);
         yv[u] = y[i];
       }
     }
@@ -233,7 +234,8 @@ __device__ __forceinline__ double l2_long_group(R* y, const R* xk, const R* sj, 
     }
   }
   if (PSI) vv = warp_sum(vv);
-  return vv;
+  // unshifted GroupNormL2.prox! returns Σ λ_g ‖x_g‖ -- the norms of its INPUT (groupNormL2.jl:49-54)
+  return (PSI && xk == nullptr) ? ss : vv;
 }
 
 template <class R, bool PSI, int PART>  // PART 0: groups of <= 256 elements, 1: the longer ones
@@ -294,7 +296,8 @@ __global__ void __launch_bounds__(kGroupThreads)
       }
       if (PSI) {
         vv = sub_sum(vv, t.L);
-        if (t.valid && t.sub == 0) psi += (double)(lam * (R)sqrt_fast(vv));
+        // shifted: λ_g ‖(xk + sj + y)_g‖; unshifted (xk == NULL): λ_g ‖x_g‖ of the input, as groupNormL2.jl:49-54
+        if (t.valid && t.sub == 0) psi += (double)(lam * (xk ? (R)sqrt_fast(vv) : snorm));
       }
       pos += 32 >> k;
     }
@@ -879,9 +882,11 @@ static int32_t prox_group(spx_ctx* ctx, bool binf, int64_t n, R* y, const R* xk,
                           double* psi_out) {
   SPX_REQUIRE(ctx != nullptr, "null context");
   SPX_REQUIRE(n >= 0 && ngroups >= 0, "negative size");
-  SPX_REQUIRE(ngroups == 0 || (y && xk && sj && q && offs && lambda_g), "null device vector");
+  SPX_REQUIRE(ngroups == 0 || (y && q && offs && lambda_g), "null device vector");
+  SPX_REQUIRE((xk == nullptr) == (sj == nullptr), "xk and sj must both be given or both be NULL");
+  SPX_REQUIRE(!(binf && xk == nullptr), "the Binf form needs its shifts");
   DeviceGuard g(ctx->device);
-  if (ngroups == 1 && !binf && n >= kSingleGroupMin) return prox_single_group<R>(ctx, n, y, xk, sj, q, lambda_g, (R)sigma, psi_out);
+  if (ngroups == 1 && !binf && xk != nullptr && n >= kSingleGroupMin) return prox_single_group<R>(ctx, n, y, xk, sj, q, lambda_g, (R)sigma, psi_out);
   if (ngroups > 0) {
     if (!binf) {
       if (psi_out) {

@@ -633,8 +633,33 @@ def set_radius_(psi, delta):
     return psi
 
 
+def _prox_base_(y, h, x, gamma):
+    """prox!(y, h, x, γ) of the in-tree base functions -- RootNormLhalf (src/rootNormLhalf.jl:31-51) and
+    GroupNormL2 (src/groupNormL2.jl:41-58): same kernels as the shifted forms with the shifts read as zeros
+    (NULL pointers: nothing extra crosses HBM).  Returns (y, value) with the reference's return value, out of
+    the same pass: λ Σ√|y_i| for RootNormLhalf, Σ_g λ_g ‖x_g‖ -- the norms of the INPUT -- for GroupNormL2
+    (groupNormL2.jl:49-54)."""
+    _vec(x, name="x")
+    _vec(y, x, "y")
+    suf = _SUF[x.dtype]
+    out = C.c_double()
+    ctx = context(x.device)
+    if isinstance(h, RootNormLhalf):
+        L.call(f"spx_prox_lhalf_{suf}", ctx, C.c_int64(x.numel()), _p(y), None, None, _p(x), C.c_double(h.lam),
+               C.c_double(gamma), C.byref(out))
+    else:
+        g = _GroupBase.__new__(_GroupBase)
+        g._init_groups(h, x)
+        L.call(f"spx_prox_groupl2_{suf}", ctx, C.c_int64(x.numel()), _p(y), None, None, _p(x), C.c_int64(g.ngroups),
+               _p(g._offs), _p(g._lam_g), C.c_double(gamma), C.byref(out))
+    return y, out.value
+
+
 def prox_(y, psi, q, sigma, want_value=False):
-    """prox!(y, ψ, q, σ).  `want_value=True` (extension) also returns ψ(y), fused into the same pass."""
+    """prox!(y, ψ, q, σ).  `want_value=True` (extension) also returns ψ(y), fused into the same pass.
+    With a base function (RootNormLhalf, GroupNormL2) instead of a shifted ψ: prox!(y, h, x, γ) -> (y, value)."""
+    if isinstance(psi, (RootNormLhalf, GroupNormL2)):
+        return _prox_base_(y, psi, q, sigma)
     return psi.prox_(y, q, sigma, want_value)
 
 

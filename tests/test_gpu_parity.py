@@ -519,3 +519,29 @@ def test_indballl0_batch_mixing_ordinary_and_flagged_problems(dt):
     for p in range(nprob):
         ref = orc.prox_indballl0(xk[sl(p)], sj[sl(p)], q[sl(p)], r)
         assert np.array_equal(got[sl(p)], ref, equal_nan=True), p
+
+
+# ------------------------------------------- unshifted in-tree base functions ---
+@pytest.mark.parametrize("dt", DT)
+def test_unshifted_rootnormlhalf_and_groupnorml2_prox(dt):
+    """prox!(y, h, x, γ) of RootNormLhalf (rootNormLhalf.jl:31-51) and GroupNormL2 (groupNormL2.jl:41-58):
+    the shifted kernels with NULL shifts; the returned value is the reference's (h(y), resp. Σ λ_g ‖x_g‖)."""
+    n = 40_003
+    x = orc.uniform(n, 2, dt, 4.0, -2.0)
+    y = torch.empty(n, dtype=T(x).dtype, device=DEV)
+    _, v = sp.prox_(y, sp.RootNormLhalf(0.9), T(x), 0.2)
+    ref, vref = orc.prox_rootlhalf_unshifted(x, 0.9, 0.2)
+    got = N(y)
+    assert np.array_equal(got == 0, ref == 0)
+    assert np.all(np.abs(got.astype(np.float64) - ref.astype(np.float64)) <= 4 * eps(dt) * (np.abs(x) + 1))
+    # the reference sums in R, sequentially (ysum += ...); the kernel sums in Float64
+    assert v == pytest.approx(vref, rel=1e-12 if dt == np.float64 else 1e-4)
+    offs = ragged_offsets(200, 700)
+    n = int(offs[-1])
+    x = orc.uniform(n, 2, dt, 4.0, -2.0)
+    lam_g = (dt(0.5) + orc.uniform(len(offs) - 1, 12, dt)).astype(dt)
+    y = torch.empty(n, dtype=T(x).dtype, device=DEV)
+    _, v = sp.prox_(y, sp.GroupNormL2(T(lam_g), None, offsets=T(offs)), T(x), 0.3)
+    ref, vref = orc.prox_groupl2_unshifted(x, offs, lam_g, 0.3)
+    assert np.all(np.abs(N(y).astype(np.float64) - ref.astype(np.float64)) <= 8 * eps(dt) * (np.abs(x) + 1))
+    assert v == pytest.approx(vref, rel=1e-12 if dt == np.float64 else 1e-4)
