@@ -6,19 +6,13 @@
 
 namespace spx {
 
-// ---------------------------------------------------- RootNormLhalf closed form
-// `2*sign(z)/3*|z|*(1+cos(2π/3 - 2ϕ(z)/3))`, ϕ(z) = acos(νλ/4 (|z|/3)^(-3/2))
-// shiftedRootNormLhalf.jl:48,57.  The power, acos and cos run in Float64 for
-// every R (Float64 literals -3/2, 2π/3 promote); the leading factors stay in R.
-constexpr double kTwoPiOver3 = 6.283185307179586 / 3.0;  // (2*π)/3 in Float64
-
 // ---- FP64 building blocks sized for the B200 FP64 pipe (64 lanes/clk/SM: at
 // the HBM roofline a Float64 element has ~150 FP64 issue slots in total) -------
 
 // Correctly rounded a / s for a warp-uniform divisor s, given y = RN(1/s)
 // (Markstein: q faithful + exact FMA residual => the corrected quotient is the
-// IEEE quotient; two correction steps, checked exhaustively-by-sampling in
-// tests/test_div_markstein.py).  Falls back to the true division outside the
+// IEEE quotient; two correction steps, checked on the device against the IEEE
+// division by spx_selftest_math / tests/test_gpu_math.py).  Falls back to the true division outside the
 // range where every intermediate is a normal number.
 __device__ __forceinline__ double div_uniform(double a, double s, double y) {
   const double q0 = a * y;
@@ -31,9 +25,6 @@ __device__ __forceinline__ double div_uniform(double a, double s, double y) {
   return q2;
 }
 
-// t = c4 * w^(-3/2) to ~1.5 ulp (the reference's `^` is < 1 ulp, its product adds
-// half an ulp): s = sqrt(w) from rsqrt + one FMA correction, u = w*s, then the
-// quotient c4/u by one Markstein step on the reciprocal estimate r^3.
 // sqrt(x) and 1/(2 sqrt(x)) for a normal positive x, branch-free: MUFU.RSQ64H seed
 // (rsqrt.approx.ftz.f64, ~2^-22), two Goldschmidt rounds (g -> sqrt x, h -> 1/(2 sqrt x), each
 // round squares the error), one final residual correction, which makes g the correctly
@@ -64,6 +55,12 @@ __device__ __forceinline__ double sqrt_fast(double x) {
 }
 __device__ __forceinline__ float sqrt_fast(float x) { return sqrtf(x); }
 
+// RootNormLhalf closed form, operation by operation (the rare path of the kernels; the common one is the
+// stationarity cubic below): `2*sign(z)/3*|z|*(1+cos(2π/3 - 2ϕ(z)/3))`, ϕ(z) = acos(νλ/4 (|z|/3)^(-3/2))
+// (shiftedRootNormLhalf.jl:48,57).  The power, acos and cos run in Float64 for every R (the Float64 literals
+// -3/2 and 2π/3 promote); the leading factors stay in R.
+// t = c4 * w^(-3/2) to ~2 ulp (the reference's `^` is < 1 ulp, its product adds half an ulp): s = sqrt(w)
+// correctly rounded, u = w*s, then the quotient c4/u by one Markstein step on the reciprocal estimate r^3.
 static __device__ __noinline__ double lhalf_t_slow(double c4, double w) { return c4 * pow(w, -1.5); }
 __device__ __forceinline__ double lhalf_t(double c4, double w) {
   if (!(w > 1e-200 && w < 1e200)) return lhalf_t_slow(c4, w);  // 0, Inf, NaN, denormal: library path
@@ -123,22 +120,6 @@ __device__ __forceinline__ double lhalf_G_real(double t) {  // 0 <= t <= 1
   }
   return 2.0 * (d * d);
 }
-// The complex branch (t > 1), kept for reference and for tools/check_lhalf_branch.py:
-// G = 1 + cos(2π/3) (2c² - 1), c = cosh(acosh(t)/3) the root >= 1 of 4c³ - 3c = t.
-__device__ __forceinline__ double lhalf_G(double t, double cos_2pi3) {
-  if (t <= 1.0) return lhalf_G_real(t);
-  if (t < 1e30) {
-    const float tf = (float)t;
-    const float w = tf > 1e15f ? 2.0f * tf : tf + sqrtf(fmaf(tf, tf, -1.0f));
-    const float k = exp2f(__log2f(w) * 0.33333334f);
-    double c = (double)(0.5f * (k + __fdividef(1.0f, k)));
-    c = cubic_newton(c, t);
-    c = cubic_newton(c, t);
-    return 1.0 + cos_2pi3 * __fma_rn(2.0 * c, c, -1.0);
-  }
-  return 1.0 + cos_2pi3 * cosh((2.0 * acosh(t)) / 3.0);
-}
-
 // a / s for a warp-uniform divisor s: Float64 goes through div_uniform, Float32
 // through the native (FP32-pipe) division
 template <class R> struct UDiv;
@@ -675,18 +656,6 @@ template <class R, bool PSI> struct IproxL0Box {
     return yi;
   }
 };
-
-// Base.isless / isgreater on Float64 (findmin's ordering: NaN counts as minimal,
-// first minimal index wins) -- shiftedRootNormLhalfBox.jl:108
-__device__ __forceinline__ bool jl_isless(double a, double b) {
-  if (a != a) return false;
-  if (b != b) return true;
-  if (a == b) return sgnbit(a) && !sgnbit(b);
-  return a < b;
-}
-__device__ __forceinline__ bool jl_isgreater(double x, double y) {
-  return (x != x || y != y) ? jl_isless(x, y) : jl_isless(y, x);
-}
 
 // shiftedRootNormLhalfBox.jl:86-120 -- the operation-by-operation form of one selected element: four
 // candidate objectives RNorm(tt) = (tt - q)²/2/σ + λ sqrt|tt + xs| with IEEE divisions and square roots,
