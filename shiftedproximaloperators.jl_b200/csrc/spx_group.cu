@@ -884,7 +884,7 @@ static int32_t prox_group(spx_ctx* ctx, bool binf, int64_t n, R* y, const R* xk,
   SPX_REQUIRE(n >= 0 && ngroups >= 0, "negative size");
   SPX_REQUIRE(ngroups == 0 || (y && q && offs && lambda_g), "null device vector");
   SPX_REQUIRE((xk == nullptr) == (sj == nullptr), "xk and sj must both be given or both be NULL");
-  SPX_REQUIRE(!(binf && xk == nullptr), "the Binf form needs its shifts");
+  SPX_REQUIRE(!(binf && ngroups > 0 && xk == nullptr), "the Binf form needs its shifts");
   DeviceGuard g(ctx->device);
   if (ngroups == 1 && !binf && xk != nullptr && n >= kSingleGroupMin) return prox_single_group<R>(ctx, n, y, xk, sj, q, lambda_g, (R)sigma, psi_out);
   if (ngroups > 0) {

@@ -545,3 +545,55 @@ def test_unshifted_rootnormlhalf_and_groupnorml2_prox(dt):
     ref, vref = orc.prox_groupl2_unshifted(x, offs, lam_g, 0.3)
     assert np.all(np.abs(N(y).astype(np.float64) - ref.astype(np.float64)) <= 8 * eps(dt) * (np.abs(x) + 1))
     assert v == pytest.approx(vref, rel=1e-12 if dt == np.float64 else 1e-4)
+
+
+# ----------------------------------------------------------------- edge cases: aliasing, empty input ---
+@pytest.mark.parametrize("dt", DT)
+def test_prox_in_place_for_every_operator_family(dt):
+    """prox!(y, ψ, y, σ) (test_allocs.jl:108 style): Box, L1B2 (the search must not use y as scratch then), groups
+    (short and long), top-r -- the in-place result equals the out-of-place one."""
+    n = 20_011
+    xk, sj, q = inputs(n, dt)
+    l, u = bounds(n, dt)
+    offs = ragged_offsets(60, 2000)
+    m = int(offs[-1])
+    lam_g = (dt(0.5) + orc.uniform(len(offs) - 1, 12, dt)).astype(dt)
+    y0 = orc.prox_l1b2(xk, sj, q, 1.0, 0.1, 1e30)
+    full = float(np.linalg.norm((y0 + sj).astype(np.float64)))
+    hg = sp.GroupNormL2(T(lam_g), None, offsets=T(offs))
+    cases = [
+        (sp.shifted(sp.shifted(sp.RootNormLhalf(1.0), T(xk), T(l), T(u)), T(sj)), n, 0.1),
+        (sp.shifted(sp.shifted(sp.NormL1(1.0), T(xk), 0.5 * full, sp.NormL2(1.0)), T(sj)), n, 0.1),
+        (sp.shifted(sp.shifted(hg, T(xk[:m])), T(sj[:m])), m, 0.3),
+        (sp.shifted(sp.shifted(hg, T(xk[:m]), 0.5, sp.NormLinf(1.0)), T(sj[:m])), m, 0.3),
+        (sp.shifted(sp.shifted(sp.IndBallL0(777), T(xk), 1.0, sp.NormLinf(1.0)), T(sj)), n, 1.0),
+    ]
+    for psi, k, sigma in cases:
+        out = torch.empty(k, dtype=T(q).dtype, device=DEV)
+        sp.prox_(out, psi, T(q[:k]), sigma)
+        y = T(q[:k]).clone()
+        sp.prox_(y, psi, y, sigma)
+        assert torch.equal(y, out), type(psi).__name__
+
+
+def test_empty_vectors_are_accepted_by_every_entry_point():
+    """n = 0 (and no groups / no problems): every prox!/iprox!/ψ(y) entry returns SPX_OK without touching memory."""
+    import ctypes as C
+    from shiftedprox import _lib as L
+
+    ctx = sp.context(DEV)
+    z64, zd, nul = C.c_int64(0), C.c_double(1.0), None
+    out = C.c_double(-1.0)
+    for suf in ("f64", "f32"):
+        for name in ("prox_l1", "prox_l0", "prox_lhalf"):
+            L.call(f"spx_{name}_{suf}", ctx, z64, nul, nul, nul, nul, zd, zd, C.byref(out))
+            assert out.value == 0.0
+        for name in ("iprox_l1", "iprox_l0"):
+            L.call(f"spx_{name}_{suf}", ctx, z64, nul, nul, nul, nul, nul, zd, nul, nul)
+        b = L.Bound(None, 1.0)
+        for name in ("prox_l1box", "prox_l0box", "prox_lhalfbox"):
+            L.call(f"spx_{name}_{suf}", ctx, z64, nul, nul, nul, nul, C.byref(b), C.byref(b), nul, zd, zd, nul)
+        L.call(f"spx_prox_l1b2_{suf}", ctx, z64, nul, nul, nul, nul, zd, zd, zd, zd, nul, nul)
+        L.call(f"spx_prox_groupl2_{suf}", ctx, z64, nul, nul, nul, nul, z64, nul, nul, zd, nul)
+        L.call(f"spx_prox_groupl2binf_{suf}", ctx, z64, nul, nul, nul, nul, z64, nul, nul, zd, zd, nul)
+        L.call(f"spx_prox_indballl0_{suf}", ctx, z64, z64, nul, nul, nul, nul, C.c_int64(3), C.c_int32(0), zd)
