@@ -49,8 +49,8 @@ __global__ void __launch_bounds__(kEwThreads, MinBlocks<Op>::value)
 #pragma unroll
       for (int k = 0; k < NIN; ++k) {
         const bool is_vec = NPTR < 0 ? (op.in[k] != nullptr) : (k < NPTR);
-        if (is_vec && v < nvec) {
-          ld_stream(op.in[k] + v * VEC, reg[k][u]);
+        if (is_vec) {
+          if (v < nvec) ld_stream(op.in[k] + v * VEC, reg[k][u]);  // past the end: never used below
         } else {
 #pragma unroll
           for (int e = 0; e < VEC; ++e) reg[k][u].v[e] = op.fill[k];

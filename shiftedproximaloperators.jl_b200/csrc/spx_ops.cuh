@@ -183,7 +183,8 @@ __device__ __forceinline__ LhalfStart lhalf_start(float zf, float c4f) {
   return st;
 }
 // s² for the largest root s; a = σλ/2.  NEAR1: t may approach 1 (Box form), where the slope
-// az(4d² - 1) shrinks: one more step and a compensated last residual (s² = p + e, p - az by Fast2Sum).
+// az(4d² - 1) shrinks: one more step and a compensated last residual (s² = p + e, p - az by Fast2Sum) for
+// 0.9 < t < 1.002 (beyond 1.002 the stationary point is not a candidate and the value is never used).
 // SINGLE: the result is rounded to Float32 (R = Float32): one Float64 step already leaves an error of
 // ~1e-11, far below a Float32 ulp (two where the slope shrinks).
 template <bool NEAR1, bool SINGLE = false>
@@ -194,7 +195,7 @@ __device__ __forceinline__ double lhalf_newton(double az, double a, const LhalfS
   double f = __fma_rn(s, u, a);
   s = __fma_rn(-f, inv, s);
   if (SINGLE) {
-    if (NEAR1 && st.t32 > 0.9f) {
+    if (NEAR1 && st.t32 > 0.9f && st.t32 < 1.002f) {
       u = __fma_rn(s, s, -az);
       f = __fma_rn(s, u, a);
       s = __fma_rn(-f, inv, s);
@@ -204,7 +205,7 @@ __device__ __forceinline__ double lhalf_newton(double az, double a, const LhalfS
     }
     return s * s;
   }
-  if (NEAR1 && st.t32 > 0.9f) {
+  if (NEAR1 && st.t32 > 0.9f && st.t32 < 1.002f) {
     u = __fma_rn(s, s, -az);
     f = __fma_rn(s, u, a);
     s = __fma_rn(-f, inv, s);
