@@ -172,6 +172,7 @@ static int32_t launch_box_t(spx_ctx* ctx, cudaStream_t stream, int opc, bool inv
       op.kf = (float)(0.5 / (double)sigma);
       op.lamf = (float)lambda;
       op.c4f = (float)op.k.c4;
+      op.a2 = op.k.c4 + op.k.c4;
       op.fast = lhalf_f32_range_host(op.k.c4) && lhalf_f32_range_host((double)sigma) &&
                 lhalf_f32_range_host((double)lambda);
       return ew_launch(ctx, stream, op, n, base, partials, nb);

@@ -736,6 +736,7 @@ template <class R, bool PSI> struct ProxLhalfBox {
   float kf;    // 1/(2σ)
   float lamf;  // λ
   float c4f;   // σλ/4
+  double a2;   // σλ/2 (= 2 c4), the constant term of the cubic
   bool fast;   // σ, λ, σλ/4 inside the Float32-friendly range (host-checked)
   __device__ __forceinline__ R apply(const R (&x)[NIN], long long i, Partial& acc) const {
     const R xi = x[0], si = x[1], qi = x[2], li = x[3], ui = x[4];
@@ -747,7 +748,7 @@ template <class R, bool PSI> struct ProxLhalfBox {
     // stationary point (candidate 4)
     const float zf = (float)axsq;
     const LhalfStart st = lhalf_start(zf, c4f);
-    const double mag = lhalf_newton<true, sizeof(R) == 4>((double)axsq, k.c4 + k.c4, st);
+    const double mag = lhalf_newton<true, sizeof(R) == 4>((double)axsq, a2, st);
     const double val = copysign(mag, (double)xsq);
     const bool real_branch = st.t32 <= 0.998f;
     bool hard = !(fast && lhalf_f32_range(zf)) || !(st.t32 <= 0.998f || st.t32 >= 1.002f);
