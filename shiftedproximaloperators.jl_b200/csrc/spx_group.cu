@@ -147,6 +147,8 @@ template <class R, bool KEEP_XS> struct Tile {
   long long b, e;  // the lane's group (b == e: none)
   int L, sub;
   bool valid;
+  // SHIFTED = false: xk == sj == NULL, the shifts read as zeros (unshifted GroupNormL2 prox!, groupNormL2.jl:41-58)
+  template <bool SHIFTED = true>
   __device__ __forceinline__ void load(const TaskHead& t, int k, int pos, int lane, const R* xk, const R* sj,
                                        const R* q) {
     L = 1 << k;
@@ -164,8 +166,7 @@ template <class R, bool KEEP_XS> struct Tile {
       xkr[j] = R(0);
       if (KEEP_XS) xs[j] = R(0);
       if (i < e) {
-        // xk == NULL: the unshifted GroupNormL2 prox! (groupNormL2.jl:41-58), shifts read as zeros
-        const R xi = xk ? ldv(xk + i) : R(0), si = xk ? ldv(sj + i) : R(0), qi = ldv(q + i);
+        const R xi = SHIFTED ? ldv(xk + i) : R(0), si = SHIFTED ? ldv(sj + i) : R(0), qi = ldv(q + i);
         sol[j] = (qi + xi) + si;  // shiftedGroupNormL2.jl:65, shiftedGroupNormL2Binf.jl:80
         xkr[j] = xi;
         if (KEEP_XS) xs[j] = xi + si;
@@ -179,7 +180,7 @@ template <class R, bool KEEP_XS> struct Tile {
 // shiftedGroupNormL2.jl:52-79
 // Loads are batched four iterations deep before anything is stored: y may alias q, so the compiler
 // cannot hoist them itself, and a warp that owns a long group is alone in hiding its latency.
-template <class R, bool PSI>
+template <class R, bool PSI, bool SHIFTED>
 __device__ __forceinline__ double l2_long_group(R* y, const R* xk, const R* sj, const R* q, long long b, long long e,
                                                 R lam, R sigma, int lane) {
   double ss = 0.0;
@@ -189,8 +190,8 @@ __device__ __forceinline__ double l2_long_group(R* y, const R* xk, const R* sj, 
     for (int u = 0; u < 4; ++u) {
       const long long i = i0 + 32 * u;
       if (i < e) {
-        xv[u] = xk ? ldv(xk + i) : R(0);
-        sv[u] = xk ? ldv(sj + i) : R(0);
+        xv[u] = SHIFTED ? ldv(xk + i) : R(0);
+        sv[u] = SHIFTED ? ldv(sj + i) : R(0);
         qv[u] = ldv(q + i);
       }
     }
@@ -214,8 +215,8 @@ __device__ __forceinline__ double l2_long_group(R* y, const R* xk, const R* sj, 
     for (int u = 0; u < 4; ++u) {
       const long long i = i0 + 32 * u;
       if (i < e) {
-        xv[u] = xk ? xk[i] : R(0);
-        sv[u] = xk ? sj[i] : R(0);
+        xv[u] = SHIFTED ? xk[i] : R(0);
+        sv[u] = SHIFTED ? sj[i] : R(0);
         yv[u] = y[i];
       }
     }
@@ -235,21 +236,21 @@ __device__ __forceinline__ double l2_long_group(R* y, const R* xk, const R* sj, 
   }
   if (PSI) vv = warp_sum(vv);
   // unshifted GroupNormL2.prox! returns Σ λ_g ‖x_g‖ -- the norms of its INPUT (groupNormL2.jl:49-54)
-  return (PSI && xk == nullptr) ? ss : vv;
+  return (PSI && !SHIFTED) ? ss : vv;
 }
 
-template <class R, bool PSI, int PART>  // PART 0: groups of <= 256 elements, 1: the longer ones
+// PART 0: groups of <= 256 elements, 1: the longer ones; SHIFTED = false: xk == sj == NULL
+template <class R, bool PSI, int PART, bool SHIFTED>
 __global__ void __launch_bounds__(kGroupThreads)
     group_l2_kernel(R* y, const R* xk, const R* sj, const R* q, long long ngroups,
                     const long long* __restrict__ offs, const R* __restrict__ lambda_g, R sigma,
-                    Partial* __restrict__ partials, unsigned long long* task_counter) {
+                    Partial* __restrict__ partials) {
   const int lane = threadIdx.x & 31;
   const long long warp = ((long long)blockIdx.x * kGroupThreads + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * kGroupThreads) >> 5;
   const long long ntasks = (ngroups + kTask - 1) / kTask;
   double psi = 0.0;
-  for (long long task = task_counter ? next_task(-1, 0, task_counter, lane) : warp; task < ntasks;
-       task = next_task(task, nwarps, task_counter, lane)) {
+  for (long long task = warp; task < ntasks; task += nwarps) {
     const long long g0 = task * kTask;
     const TaskHead th = load_task(offs, g0, ngroups, lane);
     // le[5]: groups of <= 256 elements (lanes beyond the task count as such)
@@ -262,7 +263,7 @@ __global__ void __launch_bounds__(kGroupThreads)
         if (PART == 1) {
           const long long b = __shfl_sync(0xffffffffu, th.lo, pos), e = __shfl_sync(0xffffffffu, th.hi, pos);
           const R lam = __shfl_sync(0xffffffffu, lam_lane, pos);
-          const double vv = l2_long_group<R, PSI>(y, xk, sj, q, b, e, lam, sigma, lane);
+          const double vv = l2_long_group<R, PSI, SHIFTED>(y, xk, sj, q, b, e, lam, sigma, lane);
           if (PSI && lane == 0) psi += (double)(lam * (R)sqrt(vv));  // λ_g ‖v_g‖  groupNormL2.jl:36
         }
         pos += 1;
@@ -273,7 +274,7 @@ __global__ void __launch_bounds__(kGroupThreads)
         continue;
       }
       Tile<R, true> t;
-      t.load(th, k, pos, lane, xk, sj, q);
+      t.template load<SHIFTED>(th, k, pos, lane, xk, sj, q);
       const R lam = __shfl_sync(0xffffffffu, lam_lane, t.group_in_task(pos, k, lane) & 31);
       double ss = 0.0;
 #pragma unroll
@@ -297,7 +298,7 @@ __global__ void __launch_bounds__(kGroupThreads)
       if (PSI) {
         vv = sub_sum(vv, t.L);
         // shifted: λ_g ‖(xk + sj + y)_g‖; unshifted (xk == NULL): λ_g ‖x_g‖ of the input, as groupNormL2.jl:49-54
-        if (t.valid && t.sub == 0) psi += (double)(lam * (xk ? (R)sqrt_fast(vv) : snorm));
+        if (t.valid && t.sub == 0) psi += (double)(lam * (SHIFTED ? (R)sqrt_fast(vv) : snorm));
       }
       pos += 32 >> k;
     }
@@ -552,7 +553,8 @@ template <class R, int PART>
 __global__ void __launch_bounds__(kGroupThreads, PART == 0 ? SPX_GB_MINB : 2)
     group_l2binf_kernel(R* y, const R* xk, const R* sj, const R* q, long long ngroups,
                         const long long* __restrict__ offs, const R* __restrict__ lambda_g, R sigma, R delta,
-                        UDiv<R> by_sigma, unsigned long long* task_counter) {
+                        UDiv<R> by_sigma, unsigned long long* task_counter, unsigned* long_flag) {
+  if (PART == 1 && long_flag != nullptr && *long_flag == 0u) return;
   const int lane = threadIdx.x & 31;
   const long long warp = ((long long)blockIdx.x * kGroupThreads + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * kGroupThreads) >> 5;
@@ -562,12 +564,14 @@ __global__ void __launch_bounds__(kGroupThreads, PART == 0 ? SPX_GB_MINB : 2)
     const long long g0 = task * kTask;
     const TaskHead th = load_task(offs, g0, ngroups, lane);
     // le[5]: groups of <= 256 elements (lanes beyond the task count as such)
+    if (PART == 0 && th.le[5] != 0xffffffffu && long_flag != nullptr && lane == 0) *long_flag = 1u;
     if (PART == 1 ? (th.le[5] == 0xffffffffu) : (th.le[5] == 0u)) continue;
     const R lam_lane = lane < th.cnt ? lambda_g[g0 + lane] : R(0);
     int pos = 0;
     while (pos < th.cnt) {
       const int k = plan_round(th.le, pos);
       if (k < 0 && PART == 0) {
+        if (long_flag != nullptr && lane == 0) *long_flag = 1u;
         pos += 1;
         continue;
       }
@@ -876,6 +880,35 @@ template int32_t value_group_binf<double>(spx_ctx*, int64_t, const double*, cons
 template int32_t value_group_binf<float>(spx_ctx*, int64_t, const float*, const float*, const float*, bool, double,
                                          int64_t, const int64_t*, const float*, double*);
 
+template <class R, bool SHIFTED>
+static int32_t launch_group_l2(spx_ctx* ctx, int64_t n, R* y, const R* xk, const R* sj, const R* q, int64_t ngroups,
+                               const int64_t* offs, const R* lambda_g, R sigma, double* psi_out) {
+  (void)n;
+  if (psi_out) {
+    const int grid0 = group_grid(ctx, ngroups, (const void*)group_l2_kernel<R, true, 0, SHIFTED>);
+    const int grid1 = group_grid(ctx, ngroups, (const void*)group_l2_kernel<R, true, 1, SHIFTED>);
+    group_l2_kernel<R, true, 0, SHIFTED><<<grid0, kGroupThreads, 0, ctx->stream>>>(
+        y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, sigma, ctx->d_partials);
+    group_l2_kernel<R, true, 1, SHIFTED><<<grid1, kGroupThreads, 0, ctx->stream>>>(
+        y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, sigma, ctx->d_partials + grid0);
+    ctx->launches += 2;
+    SPX_CUDA(cudaGetLastError());
+    int32_t st = finalize_partials(ctx, grid0 + grid1, 1, false);
+    if (st != SPX_OK) return st;
+    *psi_out = (double)(R)ctx->h_result[0].s;
+    return SPX_OK;
+  }
+  const int grid0 = group_grid(ctx, ngroups, (const void*)group_l2_kernel<R, false, 0, SHIFTED>);
+  const int grid1 = group_grid(ctx, ngroups, (const void*)group_l2_kernel<R, false, 1, SHIFTED>);
+  group_l2_kernel<R, false, 0, SHIFTED><<<grid0, kGroupThreads, 0, ctx->stream>>>(
+      y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, sigma, ctx->d_partials);
+  group_l2_kernel<R, false, 1, SHIFTED><<<grid1, kGroupThreads, 0, ctx->stream>>>(
+      y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, sigma, ctx->d_partials);
+  ctx->launches += 2;
+  SPX_CUDA(cudaGetLastError());
+  return SPX_OK;
+}
+
 template <class R>
 static int32_t prox_group(spx_ctx* ctx, bool binf, int64_t n, R* y, const R* xk, const R* sj, const R* q,
                           int64_t ngroups, const int64_t* offs, const R* lambda_g, double sigma, double delta,
@@ -889,31 +922,8 @@ static int32_t prox_group(spx_ctx* ctx, bool binf, int64_t n, R* y, const R* xk,
   if (ngroups == 1 && !binf && xk != nullptr && n >= kSingleGroupMin) return prox_single_group<R>(ctx, n, y, xk, sj, q, lambda_g, (R)sigma, psi_out);
   if (ngroups > 0) {
     if (!binf) {
-      if (psi_out) {
-        const int grid0 = group_grid(ctx, ngroups, (const void*)group_l2_kernel<R, true, 0>);
-        const int grid1 = group_grid(ctx, ngroups, (const void*)group_l2_kernel<R, true, 1>);
-        group_l2_kernel<R, true, 0><<<grid0, kGroupThreads, 0, ctx->stream>>>(
-            y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, (R)sigma, ctx->d_partials, nullptr);
-        group_l2_kernel<R, true, 1><<<grid1, kGroupThreads, 0, ctx->stream>>>(
-            y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, (R)sigma, ctx->d_partials + grid0, nullptr);
-        ctx->launches += 2;
-        SPX_CUDA(cudaGetLastError());
-        int32_t st = finalize_partials(ctx, grid0 + grid1, 1, false);
-        if (st != SPX_OK) return st;
-        *psi_out = (double)(R)ctx->h_result[0].s;
-        return SPX_OK;
-      }
-      const int grid0 = group_grid(ctx, ngroups, (const void*)group_l2_kernel<R, false, 0>);
-      const int grid1 = group_grid(ctx, ngroups, (const void*)group_l2_kernel<R, false, 1>);
-      // (a task counter does not pay here: the skipped tasks of a short-group problem would all hit one atomic)
-      unsigned long long* counter = nullptr;
-      group_l2_kernel<R, false, 0><<<grid0, kGroupThreads, 0, ctx->stream>>>(
-          y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, (R)sigma, ctx->d_partials, nullptr);
-      group_l2_kernel<R, false, 1><<<grid1, kGroupThreads, 0, ctx->stream>>>(
-          y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, (R)sigma, ctx->d_partials, counter);
-      ctx->launches += 2;
-      SPX_CUDA(cudaGetLastError());
-      return SPX_OK;
+      return xk ? launch_group_l2<R, true>(ctx, n, y, xk, sj, q, ngroups, offs, lambda_g, (R)sigma, psi_out)
+                : launch_group_l2<R, false>(ctx, n, y, xk, sj, q, ngroups, offs, lambda_g, (R)sigma, psi_out);
     }
     UDiv<R> by_sigma;
     by_sigma.set((R)sigma);
@@ -922,11 +932,12 @@ static int32_t prox_group(spx_ctx* ctx, bool binf, int64_t n, R* y, const R* xk,
     int32_t st0 = ensure_scratch(ctx, 4096);
     if (st0 != SPX_OK) return st0;
     unsigned long long* counter = (unsigned long long*)ctx->d_scratch;  // long groups: dynamic task hand-out
-    SPX_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), ctx->stream));
+    unsigned* long_flag = (unsigned*)((char*)ctx->d_scratch + 8);
+    SPX_CUDA(cudaMemsetAsync(ctx->d_scratch, 0, 16, ctx->stream));
     group_l2binf_kernel<R, 0><<<grid0, kGroupThreads, 0, ctx->stream>>>(
-        y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, (R)sigma, (R)delta, by_sigma, nullptr);
+        y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, (R)sigma, (R)delta, by_sigma, nullptr, long_flag);
     group_l2binf_kernel<R, 1><<<grid1, kGroupThreads, 0, ctx->stream>>>(
-        y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, (R)sigma, (R)delta, by_sigma, counter);
+        y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, (R)sigma, (R)delta, by_sigma, counter, long_flag);
     ctx->launches += 2;
     SPX_CUDA(cudaGetLastError());
   }
