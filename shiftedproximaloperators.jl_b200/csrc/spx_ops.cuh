@@ -491,9 +491,12 @@ __device__ __forceinline__ Quot4<double> quot4(double g, double d, double lambda
 // shiftedNormL1Box.jl:131-225.  Straight-line like IproxL0Box below: the three regimes are evaluated
 // for every element and selected.  `x < min(a, b)` is written `x < a && x < b` (same truth table,
 // NaNs included, since Base.min propagates NaN and every comparison with NaN is false).
+#ifndef SPX_IPB_MINB
+#define SPX_IPB_MINB 3
+#endif
 template <class R, bool PSI> struct IproxL1Box {
   using Real = R;
-  static constexpr int NIN = 6, UNROLL = 1, MINB = 3;
+  static constexpr int NIN = 6, UNROLL = 1, MINB = SPX_IPB_MINB;
   static constexpr bool OUT = true, ACC = PSI;
   static constexpr bool SPLIT_NULL = true;  // l, u: both vectors or both scalars at compile time
   const R* in[NIN];  // xk, sj, g, d, l, u
@@ -595,7 +598,7 @@ template <class R, bool PSI> struct ProxL0Box {
 // so predication beats divergence, and the two lanes of a 128-bit pair interleave.
 template <class R, bool PSI> struct IproxL0Box {
   using Real = R;
-  static constexpr int NIN = 6, UNROLL = 1, MINB = 3;
+  static constexpr int NIN = 6, UNROLL = 1, MINB = SPX_IPB_MINB;
   static constexpr bool OUT = true, ACC = PSI;
   static constexpr bool SPLIT_NULL = true;  // l, u: both vectors or both scalars at compile time
   const R* in[NIN];  // xk, sj, g, d, l, u
