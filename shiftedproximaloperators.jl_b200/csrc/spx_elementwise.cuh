@@ -48,9 +48,15 @@ __global__ void __launch_bounds__(kEwThreads, MinBlocks<Op>::value)
       const long long v = base + (long long)u * kEwThreads + threadIdx.x;
 #pragma unroll
       for (int k = 0; k < NIN; ++k) {
-        const bool is_vec = NPTR < 0 ? (op.in[k] != nullptr) : (k < NPTR);
-        if (is_vec) {
-          if (v < nvec) ld_stream(op.in[k] + v * VEC, reg[k][u]);  // past the end: never used below
+        if (NPTR >= 0) {  // vector-ness known at compile time: no fill moves, no null tests
+          if (k < NPTR) {
+            if (v < nvec) ld_stream(op.in[k] + v * VEC, reg[k][u]);  // past the end: never used below
+          } else {
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) reg[k][u].v[e] = op.fill[k];
+          }
+        } else if (op.in[k] != nullptr && v < nvec) {  // one predicate: keeps every load of the tile in one batch
+          ld_stream(op.in[k] + v * VEC, reg[k][u]);
         } else {
 #pragma unroll
           for (int e = 0; e < VEC; ++e) reg[k][u].v[e] = op.fill[k];
