@@ -99,6 +99,39 @@ def value_sharded(psi, y_local: torch.Tensor, group=None) -> float:
                            getattr(psi.h, "r", 0), device=psi.xk.device, group=group)
 
 
+# ------------------------------------------------------- the all-reduce callback ---
+_REDUCE_BUFS: dict = {}
+
+
+def _make_reduce(dev, group):
+    """SUM all-reduce of `count` doubles handed over by libshiftedprox (spx_allreduce_sum_fn): a pinned host
+    mirror and a device buffer are kept per device, the values travel H2D -> NCCL -> D2H on the current stream."""
+
+    def _reduce(_user, vals, count):
+        try:
+            key = (dev.index, max(count, 64))
+            bufs = _REDUCE_BUFS.get(key)
+            if bufs is None:
+                host = torch.empty(max(count, 64), dtype=torch.float64, pin_memory=dev.type == "cuda")
+                bufs = _REDUCE_BUFS[key] = (host, torch.empty(max(count, 64), dtype=torch.float64, device=dev))
+            host, buf = bufs
+            hv = host.numpy()
+            for i in range(count):
+                hv[i] = vals[i]
+            buf[:count].copy_(host[:count], non_blocking=True)
+            dist.all_reduce(buf[:count], op=dist.ReduceOp.SUM, group=group)
+            host[:count].copy_(buf[:count], non_blocking=True)
+            if dev.type == "cuda":
+                torch.cuda.current_stream(dev).synchronize()
+            for i in range(count):
+                vals[i] = float(hv[i])
+            return 0
+        except Exception:  # never let an exception cross the C boundary
+            return -1
+
+    return _reduce
+
+
 # ---------------------------------------------------------------- L1B2 sharded ---
 def prox_l1b2_sharded_(y_local, psi, q_local, sigma, group=None, want_value=False):
     """ShiftedNormL1B2 prox! on a sharded vector: every pass's K partial sums of squares go through one
@@ -107,18 +140,7 @@ def prox_l1b2_sharded_(y_local, psi, q_local, sigma, group=None, want_value=Fals
 
     dev = psi.xk.device
 
-    def _reduce(_user, vals, count):
-        try:
-            buf = torch.tensor([vals[i] for i in range(count)], dtype=torch.float64, device=dev)
-            dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
-            host = buf.cpu()
-            for i in range(count):
-                vals[i] = float(host[i])
-            return 0
-        except Exception:  # pragma: no cover
-            return 1
-
-    cb = L.ALLREDUCE_FN(_reduce)
+    cb = L.ALLREDUCE_FN(_make_reduce(dev, group))
     passes = C.c_int32()
     out = C.c_double() if want_value else None
     psi._call("prox_l1b2_sharded", C.c_int64(psi.n), _p(y_local), _p(psi.xk), _p(psi.sj), _p(q_local),
@@ -139,18 +161,7 @@ def prox_indballl0_sharded_(y_local, psi, q_local, n_global: int, group=None):
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     world = dist.get_world_size(group) if dist.is_initialized() else 1
 
-    def _reduce(_user, vals, count):
-        try:
-            buf = torch.tensor([vals[i] for i in range(count)], dtype=torch.float64, device=dev)
-            dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
-            host = buf.cpu()
-            for i in range(count):
-                vals[i] = float(host[i])
-            return 0
-        except Exception:  # never let an exception cross the C boundary
-            return -1
-
-    cb = L.ALLREDUCE_FN(_reduce)
+    cb = L.ALLREDUCE_FN(_make_reduce(dev, group))
     binf = isinstance(psi, ShiftedIndBallL0BInf)
     psi._call("prox_indballl0_sharded", C.c_int64(psi.n), C.c_int64(n_global), _p(y_local), _p(psi.xk), _p(psi.sj),
               _p(q_local), C.c_int64(psi.h.r), C.c_int32(1 if binf else 0),
