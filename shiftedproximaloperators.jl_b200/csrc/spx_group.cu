@@ -18,6 +18,11 @@ namespace spx {
 constexpr int kGroupThreads = 256;
 constexpr int kEPL = 8;    // elements per lane kept in registers
 constexpr int kTask = 32;  // consecutive groups per warp task
+// groups of kBigMin < m <= kBigMax elements take a whole CTA: 16 elements per thread in registers, one HBM
+// read per operand like the short groups (the warp path would stash and re-read them)
+constexpr long long kBigMin = 1024, kBigMax = 4096;
+constexpr int kBigE = (int)(kBigMax / kGroupThreads);
+__device__ __forceinline__ bool is_big(long long m) { return m > kBigMin && m <= kBigMax; }
 
 #ifdef SPX_GROUP_STATS
 __device__ unsigned long long g_stat_evals = 0, g_stat_groups = 0;
@@ -259,12 +264,14 @@ __global__ void __launch_bounds__(kGroupThreads)
     int pos = 0;
     while (pos < th.cnt) {
       const int k = plan_round(th.le, pos);
-      if (k < 0) {  // long group: the whole warp
+      if (k < 0) {  // long group: the whole warp (a whole CTA of group_l2_big_kernel for 1024 < m <= 4096)
         if (PART == 1) {
           const long long b = __shfl_sync(0xffffffffu, th.lo, pos), e = __shfl_sync(0xffffffffu, th.hi, pos);
-          const R lam = __shfl_sync(0xffffffffu, lam_lane, pos);
-          const double vv = l2_long_group<R, PSI, SHIFTED>(y, xk, sj, q, b, e, lam, sigma, lane);
-          if (PSI && lane == 0) psi += (double)(lam * (R)sqrt(vv));  // λ_g ‖v_g‖  groupNormL2.jl:36
+          if (!is_big(e - b)) {
+            const R lam = __shfl_sync(0xffffffffu, lam_lane, pos);
+            const double vv = l2_long_group<R, PSI, SHIFTED>(y, xk, sj, q, b, e, lam, sigma, lane);
+            if (PSI && lane == 0) psi += (double)(lam * (R)sqrt(vv));  // λ_g ‖v_g‖  groupNormL2.jl:36
+          }
         }
         pos += 1;
         continue;
@@ -310,6 +317,103 @@ __global__ void __launch_bounds__(kGroupThreads)
     p.bad = -1;
     p = block_fold<kGroupThreads>(p);
     if (threadIdx.x == 0) partials[blockIdx.x] = p;
+  }
+}
+
+// ---- one CTA per group of 1025..4096 elements ------------------------------------------------------
+// Every CTA scans chunks of 256 groups (grid-stride), lists the big ones in index order and takes them one
+// after the other: 16 elements per thread in registers (all 48 loads of a thread in flight at once), one block
+// reduction for the norm, y written once.
+__device__ __forceinline__ double block_sum(double v, double* red) {
+  v = warp_sum(v);
+  __syncthreads();  // red reuse
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = 0.0;
+#pragma unroll
+  for (int w = 0; w < kGroupThreads / 32; ++w) t += red[w];
+  return t;
+}
+// index-ordered list of the big groups of one chunk; returns how many
+__device__ __forceinline__ int list_big_groups(const long long* __restrict__ offs, long long g0, long long ngroups,
+                                               int* list, int* wcount) {
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  const long long g = g0 + t;
+  const bool big = g < ngroups && is_big(offs[g + 1] - offs[g]);
+  const unsigned bal = __ballot_sync(0xffffffffu, big);
+  __syncthreads();  // list / wcount reuse
+  if (lane == 0) wcount[w] = __popc(bal);
+  __syncthreads();
+  int base = 0, total = 0;
+#pragma unroll
+  for (int ww = 0; ww < kGroupThreads / 32; ++ww) {
+    if (ww < w) base += wcount[ww];
+    total += wcount[ww];
+  }
+  if (big) list[base + __popc(bal & ((1u << lane) - 1u))] = t;
+  __syncthreads();
+  return total;
+}
+
+template <class R, bool PSI, bool SHIFTED>
+__global__ void __launch_bounds__(kGroupThreads)
+    group_l2_big_kernel(R* y, const R* xk, const R* sj, const R* q, long long ngroups,
+                        const long long* __restrict__ offs, const R* __restrict__ lambda_g, R sigma,
+                        Partial* __restrict__ partials) {
+  __shared__ int list[kGroupThreads];
+  __shared__ int wcount[kGroupThreads / 32];
+  __shared__ double red[kGroupThreads / 32];
+  const int t = threadIdx.x;
+  double psi = 0.0;
+  for (long long g0 = (long long)blockIdx.x * kGroupThreads; g0 < ngroups; g0 += (long long)gridDim.x * kGroupThreads) {
+    const int nbig = list_big_groups(offs, g0, ngroups, list, wcount);
+    for (int j = 0; j < nbig; ++j) {
+      const long long g = g0 + list[j];
+      const long long b = offs[g], e = offs[g + 1];
+      const R lam = lambda_g[g];
+      R sol[kBigE], xs[kBigE];
+      double ss = 0.0;
+#pragma unroll
+      for (int k = 0; k < kBigE; ++k) {
+        const long long i = b + (long long)k * kGroupThreads + t;
+        sol[k] = R(0);
+        xs[k] = R(0);
+        if (i < e) {
+          const R xi = SHIFTED ? ldv(xk + i) : R(0), si = SHIFTED ? ldv(sj + i) : R(0), qi = ldv(q + i);
+          sol[k] = (qi + xi) + si;  // shiftedGroupNormL2.jl:65
+          xs[k] = xi + si;
+          ss += (double)sol[k] * (double)sol[k];
+        }
+      }
+      ss = block_sum(ss, red);
+      const R snorm = (R)sqrt(ss);
+      const R alpha = jl_max(R(1) - sigma * lam / snorm, R(0));
+      double vv = 0.0;
+#pragma unroll
+      for (int k = 0; k < kBigE; ++k) {
+        const long long i = b + (long long)k * kGroupThreads + t;
+        if (i < e) {
+          const R o = (snorm == R(0) ? R(0) : alpha * sol[k]) - xs[k];  // :70-77
+          stv(y + i, o);
+          if (PSI) {
+            const double v = (double)(xs[k] + o);
+            vv += v * v;
+          }
+        }
+      }
+      if (PSI) {
+        vv = block_sum(vv, red);
+        // shifted: λ_g ‖(xk + sj + y)_g‖; unshifted: λ_g ‖x_g‖ of the input (groupNormL2.jl:49-54)
+        if (t == 0) psi += (double)(lam * (SHIFTED ? (R)sqrt(vv) : snorm));
+      }
+    }
+  }
+  if (PSI && t == 0) {
+    Partial p;
+    p.s = psi;
+    p.s2 = 0.0;
+    p.bad = -1;
+    partials[blockIdx.x] = p;
   }
 }
 
@@ -833,6 +937,18 @@ static int group_grid(spx_ctx* ctx, int64_t ngroups, const void* kernel) {
   return (int)(want < cap ? want : cap);
 }
 
+// grid of the CTA-per-group kernels: one CTA per chunk of 256 groups, at most the resident CTAs
+static int big_grid(spx_ctx* ctx, int64_t ngroups, const void* kernel) {
+  int per_sm = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kGroupThreads, 0) != cudaSuccess || per_sm < 1)
+    per_sm = 1;
+  long long want = (ngroups + kGroupThreads - 1) / kGroupThreads;
+  long long cap = (long long)ctx->sm_count * per_sm;
+  if (cap > kMaxPartials / 4) cap = kMaxPartials / 4;
+  if (want < 1) want = 1;
+  return (int)(want < cap ? want : cap);
+}
+
 template <class R>
 int32_t value_group_binf(spx_ctx* ctx, int64_t n, const R* xk, const R* sj, const R* y, bool binf, double delta,
                          int64_t ngroups, const int64_t* offs, const R* lambda_g, double* out) {
@@ -884,6 +1000,7 @@ template <class R, bool SHIFTED>
 static int32_t launch_group_l2(spx_ctx* ctx, int64_t n, R* y, const R* xk, const R* sj, const R* q, int64_t ngroups,
                                const int64_t* offs, const R* lambda_g, R sigma, double* psi_out) {
   (void)n;
+  const int grid2 = big_grid(ctx, ngroups, (const void*)group_l2_big_kernel<R, false, SHIFTED>);
   if (psi_out) {
     const int grid0 = group_grid(ctx, ngroups, (const void*)group_l2_kernel<R, true, 0, SHIFTED>);
     const int grid1 = group_grid(ctx, ngroups, (const void*)group_l2_kernel<R, true, 1, SHIFTED>);
@@ -891,9 +1008,11 @@ static int32_t launch_group_l2(spx_ctx* ctx, int64_t n, R* y, const R* xk, const
         y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, sigma, ctx->d_partials);
     group_l2_kernel<R, true, 1, SHIFTED><<<grid1, kGroupThreads, 0, ctx->stream>>>(
         y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, sigma, ctx->d_partials + grid0);
-    ctx->launches += 2;
+    group_l2_big_kernel<R, true, SHIFTED><<<grid2, kGroupThreads, 0, ctx->stream>>>(
+        y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, sigma, ctx->d_partials + grid0 + grid1);
+    ctx->launches += 3;
     SPX_CUDA(cudaGetLastError());
-    int32_t st = finalize_partials(ctx, grid0 + grid1, 1, false);
+    int32_t st = finalize_partials(ctx, grid0 + grid1 + grid2, 1, false);
     if (st != SPX_OK) return st;
     *psi_out = (double)(R)ctx->h_result[0].s;
     return SPX_OK;
@@ -904,7 +1023,9 @@ static int32_t launch_group_l2(spx_ctx* ctx, int64_t n, R* y, const R* xk, const
       y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, sigma, ctx->d_partials);
   group_l2_kernel<R, false, 1, SHIFTED><<<grid1, kGroupThreads, 0, ctx->stream>>>(
       y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, sigma, ctx->d_partials);
-  ctx->launches += 2;
+  group_l2_big_kernel<R, false, SHIFTED><<<grid2, kGroupThreads, 0, ctx->stream>>>(
+      y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, sigma, ctx->d_partials);
+  ctx->launches += 3;
   SPX_CUDA(cudaGetLastError());
   return SPX_OK;
 }
