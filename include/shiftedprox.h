@@ -282,6 +282,24 @@ typedef struct spx_box_job_f32 {
                                   const R* sj, const R* y, const spx_bound* l,                   \
                                   const spx_bound* u, const spx_sel* sel, int32_t boxed,         \
                                   double* out_host);                                             \
+  /* ------------------------------ fused solver step */                 \
+  /* The sweeps a solver iteration wraps around every prox! (R2 / TR of RegularizedOptimization.jl, */ \
+  /* reference README.md:17), in the one pass of the prox! itself:                                */ \
+  /*   q = (-nu) .* grad;  prox!(s, ψ, q, nu)   [the method bodies cited at spx_prox_* above]      */ \
+  /*   xsy = (xk + sj) + s                      [ψ's argument, ShiftedProximalOperators.jl:52;     */ \
+  /*                                             xsy == NULL: not written]                         */ \
+  /*   out3_host[0] = ψ(s)                      [ShiftedProximalOperators.jl:51-54; Box forms      */ \
+  /*                                             shiftedNormL1Box.jl:70-82: Inf outside the box]   */ \
+  /*   out3_host[1] = Σ s_i²,  out3_host[2] = Σ grad_i s_i   (Float64 sums)                        */ \
+  /* s is bit-identical to spx_prox_*(q = (-nu) .* grad rounded to R, sigma = nu).  sj == NULL: ψ   */ \
+  /* shifted once (sj = 0).  kind = SPX_H_L1, _L0, _LHALF.  The call synchronises.                 */ \
+  int32_t spx_step_sep_##SUF(spx_ctx* ctx, int32_t kind, int64_t n, R* s, R* xsy, const R* xk,   \
+                             const R* sj, const R* grad, double lambda, double nu,               \
+                             double* out3_host);                                                 \
+  /* the same step for the Box / BInf forms; op: 0 L1Box, 1 L0Box, 2 LhalfBox */                 \
+  int32_t spx_step_box_##SUF(spx_ctx* ctx, int32_t op, int64_t n, R* s, R* xsy, const R* xk,     \
+                             const R* sj, const R* grad, const spx_bound* l, const spx_bound* u, \
+                             const spx_sel* sel, double lambda, double nu, double* out3_host);   \
   /* ------------------------------ host-buffer entry points (end-to-end path) */              \
   /* Box prox!/iprox! with every vector in HOST memory (pinned for full speed): chunked, */     \
   /* H2D / kernel / D2H overlapped on three streams.  op: 0 L1Box, 1 L0Box, 2 LhalfBox; */      \

@@ -235,6 +235,28 @@ def value_groupl2(xk, sj, y, offs, lam_g):
                  _p(lam_g))
 
 
+def solver_step(op, xk, sj, grad, lam, nu, l=None, u=None, selected=None):
+    """The sweeps a solver iteration of the reference's callers wraps around one prox! (R2 / TR of
+    RegularizedOptimization.jl, reference README.md:17 -- that package is NOT under /root/reference, so the step
+    is DEFINED here as the composition of the reference's own prox! and ψ(y); "parity unpinned" beyond that):
+
+        q = -ν .* ∇f;  s = prox!(ψ, q, ν);  xsy = xk .+ sj .+ s;  ψ(s);  ‖s‖₂;  ∇f's
+
+    op: "l1" | "l0" | "lhalf"; with bounds (l, u) the Box form of the same h.
+    Returns (s, xsy, ψ(s), ‖s‖₂, ∇f's) -- the two sums in Float64."""
+    dt = grad.dtype
+    q = (dt.type(-dt.type(nu)) * grad).astype(dt)
+    if l is None:
+        s = {"l1": prox_l1, "l0": prox_l0, "lhalf": prox_lhalf}[op](xk, sj, q, lam, nu)
+        psi = value_plain(op, xk, sj, s, lam)
+    else:
+        s = prox_box(op, xk, sj, q, l, u, lam, nu, selected)
+        psi = value_box(op, xk, sj, s, l, u, lam, selected)
+    xsy = ((xk + sj) + s).astype(dt)
+    s64 = s.astype(np.float64)
+    return s, xsy, psi, float(np.sqrt(np.sum(s64 * s64))), float(np.sum(grad.astype(np.float64) * s64))
+
+
 def prox_zero(q, l, u, dtype=np.float64):
     return _call(f"orc_prox_zero_{_suf(dtype)}", f64, f64(q), f64(l), f64(u))
 

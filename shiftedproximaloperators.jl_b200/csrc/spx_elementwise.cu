@@ -1,21 +1,9 @@
 // spx_elementwise.cu -- C entry points of the separable / Box prox!, iprox! and ψ(y).
 #include "spx_elementwise.cuh"
 #include "spx_ops.cuh"
+#include "spx_setup.cuh"
 
 namespace spx {
-
-template <class Op, class R> static void set3(Op& op, const R* a, const R* b, const R* c) {
-  op.in[0] = a; op.in[1] = b; op.in[2] = c;
-  for (int k = 0; k < Op::NIN; ++k) op.fill[k] = R(0);
-}
-
-static const double kInf = std::numeric_limits<double>::infinity();
-
-// λ·Σ in R, returned as double (NormL1/NormL0/RootNormLhalf value functors)
-template <class R> static double scale_value(int kind, R lambda, double sum, int64_t r) {
-  if (kind == SPX_H_INDBALLL0) return sum <= (double)r ? 0.0 : kInf;
-  return (double)(lambda * (R)sum);
-}
 
 #define SPX_CHECK_VEC3(ctx, n, y, a, b, c)                                   \
   SPX_REQUIRE((ctx) != nullptr, "null context");                             \
@@ -50,7 +38,7 @@ static int32_t prox_l1(spx_ctx* ctx, int64_t n, R* y, const R* xk, const R* sj, 
   return run_sep<ProxL1, R>(ctx, n, SPX_H_L1, lam, psi_out, [&](auto& op) {
     set3(op, xk, sj, q);
     op.y = y;
-    op.a = lam * sig;
+    configure(op, lam, sig);
   });
 }
 
@@ -62,13 +50,8 @@ static int32_t prox_l0(spx_ctx* ctx, int64_t n, R* y, const R* xk, const R* sj, 
   return run_sep<ProxL0, R>(ctx, n, SPX_H_L0, lam, psi_out, [&](auto& op) {
     set3(op, xk, sj, q);
     op.y = y;
-    op.c = std::sqrt(R(2) * lam * sig);  // sqrt(2λσ)  shiftedNormL0.jl:44
+    configure(op, lam, sig);
   });
-}
-
-// 54^(1/3) (2νλ)^(2/3) / 4 in Float64  (shiftedRootNormLhalf.jl:49)
-template <class R> static double lhalf_threshold(R nulam) {
-  return std::pow(54.0, 1.0 / 3.0) * std::pow((double)(R(2) * nulam), 2.0 / 3.0) / 4.0;
 }
 
 template <class R>
@@ -81,14 +64,10 @@ static int32_t prox_lhalf(spx_ctx* ctx, int64_t n, R* y, const R* xk, const R* s
   SPX_REQUIRE((xk == nullptr) == (sj == nullptr), "xk and sj must both be given or both be NULL");
   DeviceGuard guard__(ctx->device);
   const R lam = (R)lambda, sig = (R)sigma;
-  const R nulam = sig * lam;
   return run_sep<ProxLhalf, R>(ctx, n, SPX_H_LHALF, lam, psi_out, [&](auto& op) {
     set3(op, xk, sj, q);
     op.y = y;
-    op.p = lhalf_threshold(nulam);
-    op.c4 = (double)(nulam / R(4));
-    op.c4f = (float)op.c4;
-    op.fast = lhalf_f32_range_host(op.c4);
+    configure(op, lam, sig);
   });
 }
 
@@ -133,18 +112,6 @@ static int32_t iprox_sep(spx_ctx* ctx, int kind, int64_t n, R* y, const R* xk, c
 }
 
 // --------------------------------------------------------------------- Box --
-template <class Op, class R>
-static void set_box(Op& op, const R* xk, const R* sj, const R* qg, const R* d, const R* lvec, R lval, const R* uvec,
-                    R uval) {
-  int k = 0;
-  op.in[k] = xk; op.fill[k++] = R(0);
-  op.in[k] = sj; op.fill[k++] = R(0);
-  op.in[k] = qg; op.fill[k++] = R(0);
-  if (Op::NIN == 6) { op.in[k] = d; op.fill[k++] = R(0); }
-  op.in[k] = lvec; op.fill[k++] = lval;
-  op.in[k] = uvec; op.fill[k++] = uval;
-}
-
 template <class R, bool PSI>
 static int32_t launch_box_t(spx_ctx* ctx, cudaStream_t stream, int opc, bool inverse, int64_t n, R* y, const R* xk,
                             const R* sj, const R* qg, const R* d, const R* lvec, R lval, const R* uvec, R uval,
@@ -153,28 +120,20 @@ static int32_t launch_box_t(spx_ctx* ctx, cudaStream_t stream, int opc, bool inv
     if (opc == BOX_L1) {
       ProxL1Box<R, PSI> op;
       set_box(op, xk, sj, qg, d, lvec, lval, uvec, uval);
-      op.y = y; op.sel = sel; op.sl = sigma * lambda;
+      op.y = y; op.sel = sel;
+      configure(op, lambda, sigma);
       return ew_launch(ctx, stream, op, n, base, partials, nb);
     } else if (opc == BOX_L0) {
       ProxL0Box<R, PSI> op;
       set_box(op, xk, sj, qg, d, lvec, lval, uvec, uval);
-      op.y = y; op.sel = sel; op.c = R(2) * lambda * sigma;
+      op.y = y; op.sel = sel;
+      configure(op, lambda, sigma);
       return ew_launch(ctx, stream, op, n, base, partials, nb);
     } else if (opc == BOX_LHALF) {
       ProxLhalfBox<R, PSI> op;
       set_box(op, xk, sj, qg, d, lvec, lval, uvec, uval);
       op.y = y; op.sel = sel;
-      op.k.lambda = lambda;
-      op.k.c4 = (double)(sigma * lambda / R(4));
-      op.k.by3.set(R(3));
-      op.k.by_sigma.set(sigma);
-      op.k.by_sigma64.set((double)sigma);
-      op.kf = (float)(0.5 / (double)sigma);
-      op.lamf = (float)lambda;
-      op.c4f = (float)op.k.c4;
-      op.a2 = op.k.c4 + op.k.c4;
-      op.fast = lhalf_f32_range_host(op.k.c4) && lhalf_f32_range_host((double)sigma) &&
-                lhalf_f32_range_host((double)lambda);
+      configure(op, lambda, sigma);
       return ew_launch(ctx, stream, op, n, base, partials, nb);
     }
   } else {
@@ -212,8 +171,6 @@ template int32_t launch_box<double>(spx_ctx*, cudaStream_t, int, bool, int64_t, 
 template int32_t launch_box<float>(spx_ctx*, cudaStream_t, int, bool, int64_t, float*, const float*, const float*,
                                    const float*, const float*, const float*, float, const float*, float, DevSel, float,
                                    float, bool, Partial*, int*, int64_t);
-
-static int box_kind(int opc) { return opc == BOX_L1 ? SPX_H_L1 : (opc == BOX_L0 ? SPX_H_L0 : SPX_H_LHALF); }
 
 template <class R>
 static int32_t box_entry(spx_ctx* ctx, int opc, bool inverse, int64_t n, R* y, const R* xk, const R* sj, const R* qg,

@@ -38,11 +38,12 @@ __all__ = [
     "ShiftedNormL0Box", "ShiftedRootNormLhalfBox", "ShiftedNormL1B2", "ShiftedIndBallL0", "ShiftedIndBallL0BInf",
     "ShiftedGroupNormL2", "ShiftedGroupNormL2Binf",
     "shifted", "shift_", "set_radius_", "set_bounds_", "prox_", "prox", "iprox_", "iprox", "prox_zero",
-    "iprox_zero", "context", "launch_count",
+    "iprox_zero", "step_", "StepResult", "context", "launch_count",
 ]
 
 _SUF = {torch.float64: "f64", torch.float32: "f32"}
 _CT = {torch.float64: C.c_double, torch.float32: C.c_float}
+_BOX_OP = {"l1box": L.BOX_L1, "l0box": L.BOX_L0, "lhalfbox": L.BOX_LHALF}
 
 
 # ------------------------------------------------------------------ context ---
@@ -237,8 +238,36 @@ class ShiftedProximableFunction:
     def iprox_(self, y, g, d, want_value=False):
         raise NotImplementedError(f"iprox! is not defined for {type(self).__name__}")
 
+    def step_(self, s, grad, nu, xsy=None):
+        raise NotImplementedError(f"the fused solver step is not defined for {type(self).__name__}")
+
+    def _step_sep(self, s, grad, nu, xsy):
+        # spx_step_sep_*: q = -ν∇f, prox!, ψ(s), xk+sj+s, Σs², Σ∇f·s in the one pass of the prox!
+        self._check(s, grad, ("s", "grad"))
+        if xsy is not None:
+            _vec(xsy, self.xk, "xsy")
+        out = (C.c_double * 3)()
+        # ψ shifted once: sj is the zero vector the constructor made (shift! then writes xk,
+        # ShiftedProximalOperators.jl:72-79) -- NULL reads it as zeros without the traffic
+        sj = self.sj if self.shifted_twice else None
+        self._call("step_sep", C.c_int32(self._H_KIND), C.c_int64(self.n), _p(s), _p(xsy), _p(self.xk), _p(sj),
+                   _p(grad), C.c_double(self.h.lam), C.c_double(nu), out)
+        return s, StepResult(out[0], math.sqrt(out[1]), out[2])
+
     def __repr__(self):  # Base.show  (ShiftedProximalOperators.jl:123-133)
         return f"{type(self).__name__}(n={self.n}, dtype={self.xk.dtype}, shifted_twice={self.shifted_twice})"
+
+
+class StepResult(tuple):
+    """(ψ(s), ‖s‖₂, ∇f·s) of a fused solver step."""
+    __slots__ = ()
+
+    def __new__(cls, psi, snorm, gdots):
+        return super().__new__(cls, (psi, snorm, gdots))
+
+    psi = property(lambda self: self[0])
+    snorm = property(lambda self: self[1])
+    gdots = property(lambda self: self[2])
 
 
 def _psi_arg(want_value):
@@ -252,6 +281,9 @@ class ShiftedNormL1(ShiftedProximableFunction):
 
     def __init__(self, h, xk, sj=None, shifted_twice=False):
         self._init_common(h, xk, sj, shifted_twice)
+
+    def step_(self, s, grad, nu, xsy=None):
+        return self._step_sep(s, grad, nu, xsy)
 
     def prox_(self, y, q, sigma, want_value=False):  # shiftedNormL1.jl:40-54
         self._check(y, q)
@@ -277,6 +309,9 @@ class ShiftedNormL0(ShiftedProximableFunction):
     def __init__(self, h, xk, sj=None, shifted_twice=False):
         self._init_common(h, xk, sj, shifted_twice)
 
+    def step_(self, s, grad, nu, xsy=None):
+        return self._step_sep(s, grad, nu, xsy)
+
     def prox_(self, y, q, sigma, want_value=False):  # shiftedNormL0.jl:38-55
         self._check(y, q)
         out, ref = _psi_arg(want_value)
@@ -300,6 +335,9 @@ class ShiftedRootNormLhalf(ShiftedProximableFunction):
 
     def __init__(self, h, xk, sj=None, shifted_twice=False):
         self._init_common(h, xk, sj, shifted_twice)
+
+    def step_(self, s, grad, nu, xsy=None):
+        return self._step_sep(s, grad, nu, xsy)
 
     def prox_(self, y, q, sigma, want_value=False):  # shiftedRootNormLhalf.jl:41-63
         self._check(y, q)
@@ -377,6 +415,17 @@ class _BoxBase(ShiftedProximableFunction):
         self._call(f"iprox_{self._BOX_NAME}", C.c_int64(self.n), _p(y), _p(self.xk), _p(self.sj), _p(g), _p(d),
                    C.byref(lb), C.byref(ub), self._sel.ref(), C.c_double(self.h.lam), ref)
         return (y, out.value) if want_value else y
+
+    def step_(self, s, grad, nu, xsy=None):
+        self._check(s, grad, ("s", "grad"))
+        if xsy is not None:
+            _vec(xsy, self.xk, "xsy")
+        lb, ub = self._bounds()
+        out = (C.c_double * 3)()
+        self._call("step_box", C.c_int32(_BOX_OP[self._BOX_NAME]), C.c_int64(self.n), _p(s), _p(xsy), _p(self.xk),
+                   _p(self.sj), _p(grad), C.byref(lb), C.byref(ub), self._sel.ref(), C.c_double(self.h.lam),
+                   C.c_double(nu), out)
+        return s, StepResult(out[0], math.sqrt(out[1]), out[2])
 
     def __call__(self, y):  # shiftedNormL1Box.jl:70-82
         _vec(y, self.xk, "y")
@@ -676,6 +725,17 @@ def iprox_(y, psi, g, d, want_value=False):
 def iprox(psi, g, d):
     """iprox(ψ, g, d) = iprox!(ψ.sol, ψ, g, d)  (ShiftedProximalOperators.jl:180)."""
     return psi.iprox_(psi.sol, g, d)
+
+
+def step_(s, psi, grad, nu, xsy=None):
+    """Fused solver step (extension): what an R2 / TR iteration of the reference's callers
+    (README.md:17) wraps around its prox!, in the one pass of the prox! itself --
+
+        q = -ν .* ∇f;  prox!(s, ψ, q, ν);  xsy .= xk .+ sj .+ s (if given);  ψ(s);  ‖s‖₂;  ∇f's
+
+    Returns (s, StepResult(psi, snorm, gdots)).  `s` is bit-identical to prox_(s, ψ, -ν*grad, ν).  Defined for
+    ShiftedNormL1 / L0 / RootNormLhalf and their Box / BInf forms."""
+    return psi.step_(s, grad, nu, xsy)
 
 
 def prox_zero(q, l, u):

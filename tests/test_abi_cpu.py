@@ -42,7 +42,8 @@ def test_library_exports_every_declared_symbol(lib):
         for op in ("prox_l1", "iprox_l1", "prox_l0", "iprox_l0", "prox_lhalf", "prox_l1box", "iprox_l1box",
                    "prox_l0box", "iprox_l0box", "prox_lhalfbox", "prox_l1b2", "prox_l1b2_sharded", "prox_groupl2",
                    "prox_groupl2binf", "prox_indballl0", "value_sep", "value_box", "value_l1b2", "value_binf",
-                   "value_groupl2", "value_partial", "box_host", "box_multi_host", "prox_indballl0_sharded"):
+                   "value_groupl2", "value_partial", "box_host", "box_multi_host", "prox_indballl0_sharded", "step_sep",
+                   "step_box"):
             assert f"spx_{op}_{suf}" in names
 
 

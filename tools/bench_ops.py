@@ -110,6 +110,24 @@ def main():
         if nm != "lhalfbox":
             timeit(f"iprox_{nm}_vec", lambda psi=psi: sp.iprox_(y, psi, q, d), 7 * R)
             timeit(f"iprox_{nm}_scalar", lambda psi=psis: sp.iprox_(y, psi, q, d), 5 * R)
+    # fused solver step: q = -ν∇f, prox!, ψ(s), xk+sj+s, ‖s‖, ∇f's in one pass
+    if re.search(args.only, "step_"):
+        xsy = torch.empty(n, dtype=tdt, device=dev)
+        for nm, h in (("l1", sp.NormL1(lam)), ("l0", sp.NormL0(lam)), ("lhalf", sp.RootNormLhalf(lam))):
+            once = sp.shifted(h, xk)
+            timeit(f"step_{nm}_once", lambda psi=once: sp.step_(y, psi, q, sigma, xsy=xsy), 4 * R,
+                   note="ψ shifted once (R2): 2 reads + 2 writes")
+            timeit(f"step_{nm}", lambda psi=two(h): sp.step_(y, psi, q, sigma, xsy=xsy), 5 * R)
+            timeit(f"step_{nm}box_vec", lambda psi=two(h, l, u): sp.step_(y, psi, q, sigma, xsy=xsy), 7 * R)
+            timeit(f"step_{nm}box_scalar", lambda psi=two(h, -1.0, 1.0): sp.step_(y, psi, q, sigma, xsy=xsy), 5 * R)
+
+        def unfused(psi=sp.shifted(sp.NormL1(lam), xk)):  # the same step as separate sweeps (torch for the BLAS-1 parts)
+            mq = q * (-sigma)
+            sp.prox_(y, psi, mq, sigma)
+            v = psi(y)
+            torch.add(xk, y, out=xsy)
+            return v, float(torch.linalg.vector_norm(y)), float(torch.dot(q, y))
+        timeit("step_l1_once_unfused", unfused, 4 * R, note="prox! + ψ(s) + 4 BLAS-1 sweeps, same result")
     # L1B2 (ball active: Δ = half the unconstrained norm)
     if re.search(args.only, "prox_l1b2"):
         psi0 = two(sp.NormL1(lam), 1e30, sp.NormL2(1.0))
