@@ -14,7 +14,7 @@ using ProximalOperators
 import ProximalOperators: prox, prox!
 
 export DeviceVector, ShiftedProximableFunction
-export prox, prox!, iprox, iprox!, set_radius!, shift!, shifted, set_bounds!
+export prox, prox!, iprox, iprox!, set_radius!, shift!, shifted, set_bounds!, step!
 
 const libshiftedprox = get(ENV, "LIBSHIFTEDPROX", joinpath(@__DIR__, "..", "libshiftedprox.so"))
 
@@ -214,6 +214,29 @@ for R in (Float64, Float32)
                    (Ptr{Cvoid}, Int32, Int64, Ptr{$R}, Ptr{$R}, Ptr{$R}, Ref{SpxBound}, Ref{SpxBound}, Ref{SpxSel}, Cdouble, Ref{Cdouble}),
                    ctx(), 1, length(y), ψ.xk, ψ.sj, y, bound(ψ.l), bound(ψ.u), sel(ψ.selected, length(y)), ψ.λ, out))
       $R(out[])
+    end
+    # Fused solver step (extension; SURVEY.md §8f rank 1): the sweeps an R2 / TR iteration of
+    # RegularizedOptimization.jl wraps around its prox! (reference README.md:17), in the pass of the prox!:
+    #   s .= prox(ψ, -ν .* ∇f, ν);  xsy .= ψ.xk .+ ψ.sj .+ s;  returns (ψ(s), ‖s‖₂, ∇f's)
+    function step!(s::DeviceVector{$R}, xsy::Union{DeviceVector{$R}, Nothing}, ψ::ShiftedNormL1{$R},
+                   ∇f::DeviceVector{$R}, ν::$R)
+      out = zeros(Cdouble, 3)
+      chkspx(ccall(($(QuoteNode(Symbol("spx_step_sep_", s))), libshiftedprox), Int32,
+                   (Ptr{Cvoid}, Int32, Int64, Ptr{$R}, Ptr{$R}, Ptr{$R}, Ptr{$R}, Ptr{$R}, Cdouble, Cdouble, Ptr{Cdouble}),
+                   ctx(), 0, length(s), s, xsy === nothing ? C_NULL : xsy, ψ.xk,
+                   ψ.shifted_twice ? ψ.sj : C_NULL,   # shifted once: sj is the constructor's zero vector
+                   ∇f, ψ.λ, ν, out))
+      ($R(out[1]), sqrt(out[2]), out[3])
+    end
+    function step!(s::DeviceVector{$R}, xsy::Union{DeviceVector{$R}, Nothing}, ψ::ShiftedNormL0Box{$R},
+                   ∇f::DeviceVector{$R}, ν::$R)
+      out = zeros(Cdouble, 3)
+      chkspx(ccall(($(QuoteNode(Symbol("spx_step_box_", s))), libshiftedprox), Int32,
+                   (Ptr{Cvoid}, Int32, Int64, Ptr{$R}, Ptr{$R}, Ptr{$R}, Ptr{$R}, Ptr{$R}, Ref{SpxBound}, Ref{SpxBound},
+                    Ref{SpxSel}, Cdouble, Cdouble, Ptr{Cdouble}),
+                   ctx(), 1, length(s), s, xsy === nothing ? C_NULL : xsy, ψ.xk, ψ.sj, ∇f, bound(ψ.l), bound(ψ.u),
+                   sel(ψ.selected, length(s)), ψ.λ, ν, out))
+      ($R(out[1]), sqrt(out[2]), out[3])
     end
   end
 end

@@ -424,9 +424,13 @@ def test_group_l2binf_golden_vectors():
 
 
 @pytest.mark.parametrize("dt", DT)
-@pytest.mark.parametrize("layout", ["g64", "ragged"])
+@pytest.mark.parametrize("layout", ["g64", "ragged", "ragged4096", "edges"])
 def test_group_l2binf_against_oracle(dt, layout):
-    offs = {"g64": np.arange(0, 64 * 201, 64), "ragged": ragged_offsets(120, 1500)}[layout]
+    # "ragged4096" / "edges": groups of 1025..4096 elements take a whole CTA (group_l2binf_big_kernel); the sizes
+    # either side of both limits stay on the warp paths
+    offs = {"g64": np.arange(0, 64 * 201, 64), "ragged": ragged_offsets(120, 1500),
+            "ragged4096": ragged_offsets(90, 4096, seed=11),
+            "edges": np.concatenate([[0], np.cumsum([1024, 1025, 7, 4096, 4097, 256, 257, 2049, 1, 3000])])}[layout]
     n = int(offs[-1]); ng = len(offs) - 1
     xk, sj, q = inputs(n, dt)
     lam_g = (dt(0.5) + orc.uniform(ng, 12, dt)).astype(dt)
