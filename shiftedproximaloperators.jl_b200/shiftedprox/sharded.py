@@ -99,6 +99,27 @@ def value_sharded(psi, y_local: torch.Tensor, group=None) -> float:
                            getattr(psi.h, "r", 0), device=psi.xk.device, group=group)
 
 
+# ------------------------------------------------------- fused solver step, sharded ---
+def allreduce_step(psi_value: float, s_sumsq: float, gdots: float, device=None, group=None):
+    """Scalars of a fused solver step over all shards: (ψ(s), ‖s‖₂, ∇f's) from the per-shard
+    (ψ(s_shard), Σs², Σ∇f·s) -- one SUM all-reduce of three doubles.  ψ is a sum over entries for every separable
+    h and an infeasible shard contributes Inf, which survives the sum (ψ >= 0: never Inf - Inf)."""
+    t = torch.tensor([psi_value, s_sumsq, gdots], dtype=torch.float64, device=device or "cpu")
+    if dist.is_available() and dist.is_initialized():
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    v = t.tolist()
+    return v[0], math.sqrt(v[1]), v[2]
+
+
+def step_sharded_(s_local, psi, grad_local, nu, xsy_local=None, group=None):
+    """Fused solver step (shiftedprox.step_) on this rank's contiguous shard: no data-path collective, one scalar
+    all-reduce.  Returns (s_local, StepResult) with the whole-vector scalars, identical on every rank."""
+    from . import StepResult  # local import: needs the CUDA library
+
+    _, r = psi.step_(s_local, grad_local, nu, xsy_local)
+    return s_local, StepResult(*allreduce_step(r.psi, r.snorm * r.snorm, r.gdots, device=s_local.device, group=group))
+
+
 # ------------------------------------------------------- the all-reduce callback ---
 _REDUCE_BUFS: dict = {}
 

@@ -131,3 +131,34 @@ def test_topr_single_vector_over_two_shards(dt, n, r, quant, binf):
     [t.join() for t in th]
     assert not errs, errs
     assert np.array_equal(np.concatenate(outs), ref)
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_step_shards_add_up(dt):
+    # fused solver step on two contiguous shards: s is the concatenation, the three scalars add up
+    n = 100_003
+    xk, sj, grad = inputs(n, dt)
+    l, u = bounds(n, dt)
+    nu = 0.15
+    for h, boxed in ((sp.NormL1(1.2), False), (sp.NormL0(1.2), True), (sp.RootNormLhalf(1.2), True)):
+        mk = (lambda a, b: sp.shifted(sp.shifted(h, T(xk[a:b]), T(l[a:b]), T(u[a:b])), T(sj[a:b]))) if boxed else \
+             (lambda a, b: sp.shifted(sp.shifted(h, T(xk[a:b])), T(sj[a:b])))
+        whole = mk(0, n)
+        s = torch.empty(n, dtype=T(grad).dtype, device=DEV)
+        _, ref = sp.step_(s, whole, T(grad), nu)
+        psi_sum, ss, gd, parts = 0.0, 0.0, 0.0, []
+        for r in range(2):
+            lo, hi = sharded.shard_bounds(n, 2, r)
+            sl = torch.empty(hi - lo, dtype=s.dtype, device=DEV)
+            _, res = sp.step_(sl, mk(lo, hi), T(grad[lo:hi]), nu)
+            parts.append(sl)
+            psi_sum += res.psi; ss += res.snorm ** 2; gd += res.gdots
+        assert torch.equal(torch.cat(parts), s)
+        got = sharded.allreduce_step(psi_sum, ss, gd)  # un-initialised process group: the identity
+        rel = 1e-12 if dt == np.float64 else 1e-5
+        assert got[0] == pytest.approx(ref.psi, rel=rel) and got[1] == pytest.approx(ref.snorm, rel=1e-12)
+        assert abs(got[2] - ref.gdots) <= 1e-12 * float(np.sum(np.abs(grad.astype(np.float64) * N(s).astype(np.float64))))
+        # step_sharded_ without a process group degenerates to the local step
+        s2 = torch.empty_like(s)
+        _, r2 = sharded.step_sharded_(s2, whole, T(grad), nu)
+        assert torch.equal(s2, s) and r2.psi == ref.psi and r2.snorm == pytest.approx(ref.snorm, rel=1e-15)

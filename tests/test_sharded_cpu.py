@@ -112,3 +112,55 @@ def test_value_allreduce_gloo_world2():
         assert res[kind + "_bad"] == np.inf
     assert res["indball"] == 0.0
     assert res["indball_small_r"] == np.inf
+
+
+def _step_worker(rank, world, port, n, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        xk = orc.uniform(n, 0, np.float64, 4.0, -2.0)
+        sj = orc.uniform(n, 1, np.float64, 1.0, -0.5)
+        grad = orc.uniform(n, 2, np.float64, 4.0, -2.0)
+        l = -(0.25 + orc.uniform(n, 3))
+        u = 0.25 + orc.uniform(n, 4)
+        lo, hi = sharded.shard_bounds(n, world, rank)
+        sl = slice(lo, hi)
+        res = {}
+        for op in ("l1", "l0", "lhalf"):
+            # the per-shard scalars come from the oracle here; on the GPU box from spx_step_* (step_sharded_)
+            _, _, psi, sn, gd = orc.solver_step(op, xk[sl], sj[sl], grad[sl], 1.3, 0.2)
+            res[op] = sharded.allreduce_step(psi, sn * sn, gd)
+            _, _, psi, sn, gd = orc.solver_step(op, xk[sl], sj[sl], grad[sl], 1.3, 0.2, l[sl], u[sl])
+            res[op + "_box"] = sharded.allreduce_step(psi, sn * sn, gd)
+        # an infeasible shard (inverted box on the last rank only) makes the whole value Inf
+        lbad = l.copy()
+        lbad[n - 1] = u[n - 1] + 1.0
+        _, _, psi, sn, gd = orc.solver_step("lhalf", xk[sl], sj[sl], grad[sl], 1.3, 0.2, lbad[sl], u[sl])
+        res["bad"] = sharded.allreduce_step(psi, sn * sn, gd)
+        if rank == 0:
+            full = {}
+            for op in ("l1", "l0", "lhalf"):
+                full[op] = orc.solver_step(op, xk, sj, grad, 1.3, 0.2)[2:]
+                full[op + "_box"] = orc.solver_step(op, xk, sj, grad, 1.3, 0.2, l, u)[2:]
+            out.put((res, full))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_step_allreduce_gloo_world2():
+    world, n = 2, 10_007
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_step_worker, args=(r, world, port, n, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res, full = out.get(timeout=100)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for k, ref in full.items():
+        assert res[k] == pytest.approx(ref, rel=1e-12)
+    assert res["bad"][0] == np.inf and np.isfinite(res["bad"][1])

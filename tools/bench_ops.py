@@ -111,7 +111,8 @@ def main():
             timeit(f"iprox_{nm}_vec", lambda psi=psi: sp.iprox_(y, psi, q, d), 7 * R)
             timeit(f"iprox_{nm}_scalar", lambda psi=psis: sp.iprox_(y, psi, q, d), 5 * R)
     # fused solver step: q = -ν∇f, prox!, ψ(s), xk+sj+s, ‖s‖, ∇f's in one pass
-    if re.search(args.only, "step_"):
+    step_names = [f"step_{nm}{sfx}" for nm in ("l1", "l0", "lhalf") for sfx in ("_once", "", "box_vec", "box_scalar")]
+    if any(re.search(args.only, nm) for nm in step_names + ["step_l1_once_unfused"]):
         xsy = torch.empty(n, dtype=tdt, device=dev)
         for nm, h in (("l1", sp.NormL1(lam)), ("l0", sp.NormL0(lam)), ("lhalf", sp.RootNormLhalf(lam))):
             once = sp.shifted(h, xk)
