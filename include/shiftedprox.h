@@ -110,6 +110,11 @@ int32_t spx_memcpy_d2h(spx_ctx* ctx, void* dst_host, const void* src, size_t byt
 /* `shift!`: ψ.xk .= v / ψ.sj .= v   (ShiftedProximalOperators.jl:72-79) and
  * vector `set_bounds!` (ShiftedProximalOperators.jl:107-111) */
 int32_t spx_memcpy_d2d(spx_ctx* ctx, void* dst, const void* src, size_t bytes);
+/* dst[i * dst_stride] = src[i * src_stride], i < n (strides in elements of elem_bytes = 4 or 8 bytes): gather of a
+ * strided `SubArray` shift (`x = view(y, 1:2:10); shifted(h, x)`, test/runtests.jl:199-200) into the contiguous
+ * shadow the kernels read, and the scatter back after `shift!` writes it */
+int32_t spx_copy_strided(spx_ctx* ctx, int64_t n, int32_t elem_bytes, void* dst, int64_t dst_stride,
+                         const void* src, int64_t src_stride);
 int32_t spx_fill_f64(spx_ctx* ctx, double* p, int64_t n, double v);
 int32_t spx_fill_f32(spx_ctx* ctx, float* p, int64_t n, float v);
 /* ctor validation `any(l .> u)` (shiftedNormL1Box.jl:33, shiftedNormL0Box.jl:33); *out = 1 if any */

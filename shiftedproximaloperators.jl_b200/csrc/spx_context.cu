@@ -111,6 +111,13 @@ int32_t finalize_partials(spx_ctx* ctx, int nblocks, int nslot, bool) {
 }
 
 // ------------------------------------------------------------ small kernels --
+// strided copy (strides in elements): the gather / scatter between a strided `SubArray` shift and its contiguous shadow
+template <class W>
+__global__ void __launch_bounds__(256) copy_strided_kernel(long long n, W* __restrict__ dst, long long ds,
+                                                           const W* __restrict__ src, long long ss) {
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256)
+    dst[i * ds] = src[i * ss];
+}
 template <class R> struct FillOp {
   using Real = R;
   static constexpr int NIN = 1, UNROLL = 4;
@@ -371,6 +378,28 @@ int32_t spx_memcpy_d2d(spx_ctx* c, void* dst, const void* src, size_t bytes) {
   SPX_REQUIRE(dst && src, "null buffer");
   DeviceGuard g(c->device);
   SPX_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, c->stream));
+  return SPX_OK;
+}
+int32_t spx_copy_strided(spx_ctx* c, int64_t n, int32_t elem_bytes, void* dst, int64_t dst_stride, const void* src,
+                         int64_t src_stride) {
+  SPX_REQUIRE(c != nullptr, "null context");
+  SPX_REQUIRE(n >= 0, "n < 0");
+  SPX_REQUIRE(elem_bytes == 4 || elem_bytes == 8, "element size must be 4 or 8 bytes");
+  SPX_REQUIRE(dst_stride != 0 && src_stride != 0, "zero stride");
+  if (n == 0) return SPX_OK;
+  SPX_REQUIRE(dst && src, "null buffer");
+  DeviceGuard g(c->device);
+  long long want = (n + 255) / 256;
+  const long long cap = (long long)c->sm_count * 8;
+  const int grid = (int)(want < cap ? want : cap);
+  if (elem_bytes == 8)
+    spx::copy_strided_kernel<unsigned long long><<<grid, 256, 0, c->stream>>>(n, (unsigned long long*)dst, dst_stride,
+                                                                         (const unsigned long long*)src, src_stride);
+  else
+    spx::copy_strided_kernel<unsigned><<<grid, 256, 0, c->stream>>>(n, (unsigned*)dst, dst_stride, (const unsigned*)src,
+                                                               src_stride);
+  c->launches++;
+  SPX_CUDA(cudaGetLastError());
   return SPX_OK;
 }
 int32_t spx_fill_f64(spx_ctx* c, double* p, int64_t n, double v) { return fill_impl<double>(c, p, n, v); }

@@ -102,6 +102,31 @@ def _vec(t: torch.Tensor, like: Optional[torch.Tensor] = None, name: str = "vect
     return t
 
 
+def _copy_strided(dst: torch.Tensor, src: torch.Tensor) -> None:
+    L.call("spx_copy_strided", context(dst.device), C.c_int64(dst.numel()), C.c_int32(dst.element_size()),
+           C.c_void_p(dst.data_ptr()), C.c_int64(dst.stride(0)), C.c_void_p(src.data_ptr()), C.c_int64(src.stride(0)))
+
+
+def _adopt(t: torch.Tensor, like: Optional[torch.Tensor] = None, name: str = "vector") -> torch.Tensor:
+    """A shift vector: contiguous (aliased as is, like the reference), or a strided 1-D view -- the reference's
+    `SubArray` shifts (`x = view(y, 1:2:10); shifted(h, x)`, test/runtests.jl:199-200).  The kernels stream
+    contiguous operands, so a strided view gets a contiguous shadow that is re-gathered from the view before every
+    call (the caller may have written the parent array) and scattered back when shift! writes it."""
+    if isinstance(t, torch.Tensor) and t.is_cuda and t.dim() == 1 and not t.is_contiguous() and t.dtype in _SUF \
+            and t.stride(0) != 0:
+        shadow = torch.empty(t.numel(), dtype=t.dtype, device=t.device)
+        _copy_strided(shadow, t)
+        shadow._spx_view = t
+        t = shadow
+    return _vec(t, like, name)
+
+
+def _sync_shadow(t: Optional[torch.Tensor]) -> None:
+    view = getattr(t, "_spx_view", None)
+    if view is not None:
+        _copy_strided(t, view)
+
+
 def _p(t: Optional[torch.Tensor]) -> C.c_void_p:
     return C.c_void_p(0 if t is None else t.data_ptr())
 
@@ -193,11 +218,11 @@ class ShiftedProximableFunction:
 
     def _init_common(self, h, xk, sj, shifted_twice):
         self.h = h
-        self.xk = _vec(xk, name="xk")  # aliased, not copied (shiftedNormL1.jl:16-25)
-        self.sj = torch.zeros_like(xk) if sj is None else _vec(sj, xk, "sj")
-        self.sol = torch.empty_like(xk)
+        self.xk = _adopt(xk, name="xk")  # aliased, not copied (shiftedNormL1.jl:16-25)
+        self.sj = torch.zeros_like(self.xk) if sj is None else _adopt(sj, self.xk, "sj")
+        self.sol = torch.empty_like(self.xk)
         self.shifted_twice = bool(shifted_twice)
-        self._suf = _SUF[xk.dtype]
+        self._suf = _SUF[self.xk.dtype]
 
     # getproperty sugar: ψ.λ, ψ.r  (ShiftedProximalOperators.jl:113-121)
     @property
@@ -216,6 +241,8 @@ class ShiftedProximableFunction:
         return context(self.xk.device)
 
     def _call(self, name, *args):
+        _sync_shadow(self.xk)  # strided SubArray shifts: refresh the contiguous shadows
+        _sync_shadow(self.sj)
         L.call(f"spx_{name}_{self._suf}", self._ctx(), *args)
 
     def _check(self, y, q, names=("y", "q")):
@@ -604,7 +631,7 @@ def shifted(h, x, *args, selected=None, nprob: int = 1):
     `nprob` (extension): the IndBallL0 types can hold a batch of independent problems back to back.
     """
     if isinstance(h, ShiftedProximableFunction):  # shifted(ψ, sj)
-        psi, sj = h, _vec(x, h.xk, "sj")
+        psi, sj = h, _adopt(x, h.xk, "sj")
         if isinstance(psi, _BoxBase):
             return type(psi)(psi.h, psi.xk, sj, psi.l, psi.u, True, psi._sel)
         if isinstance(psi, (ShiftedNormL1B2, ShiftedGroupNormL2Binf)):
@@ -614,7 +641,7 @@ def shifted(h, x, *args, selected=None, nprob: int = 1):
         if isinstance(psi, ShiftedIndBallL0):
             return ShiftedIndBallL0(psi.h, psi.xk, sj, True, psi.nprob)
         return type(psi)(psi.h, psi.xk, sj, True)
-    xk = _vec(x, name="xk")
+    xk = _adopt(x, name="xk")
     if len(args) == 0:
         if type(h) in _PLAIN:
             return _PLAIN[type(h)](h, xk)
@@ -652,6 +679,9 @@ def shift_(psi, v):
     dst = psi.sj if psi.shifted_twice else psi.xk
     _vec(v, dst, "shift")
     L.call("spx_memcpy_d2d", psi._ctx(), _p(dst), _p(v), C.c_size_t(dst.numel() * dst.element_size()))
+    view = getattr(dst, "_spx_view", None)
+    if view is not None:  # strided SubArray shift: write through into the caller's parent array
+        _copy_strided(view, dst)
     return psi
 
 

@@ -601,3 +601,37 @@ def test_empty_vectors_are_accepted_by_every_entry_point():
         L.call(f"spx_prox_groupl2_{suf}", ctx, z64, nul, nul, nul, nul, z64, nul, nul, zd, nul)
         L.call(f"spx_prox_groupl2binf_{suf}", ctx, z64, nul, nul, nul, nul, z64, nul, nul, zd, zd, nul)
         L.call(f"spx_prox_indballl0_{suf}", ctx, z64, z64, nul, nul, nul, nul, C.c_int64(3), C.c_int32(0), zd)
+
+
+# ---------------------------------------------------------------- strided SubArray shifts ---
+@pytest.mark.parametrize("dt", DT)
+def test_strided_view_shift_aliases_the_parent_array(dt):
+    # runtests.jl:199-215: `y = rand(Float32, 10); x = view(y, 1:2:10); ψ = shifted(h, x); ψ(zeros(5)) == h(x)`;
+    # and the aliasing of shift! (runtests.jl:183-191) through the view: ψ.xk .= v lands in the parent array
+    n = 4099
+    parent = orc.uniform(2 * n, 0, dt, 4.0, -2.0)
+    tp = T(parent)
+    x = tp[0::2]
+    assert not x.is_contiguous()
+    lam = 1.2
+    for h, kind in ((sp.NormL1(lam), "l1"), (sp.NormL0(lam), "l0"), (sp.RootNormLhalf(lam), "lhalf")):
+        psi = sp.shifted(h, x)
+        z = np.zeros(n, dt)
+        assert psi(T(z)) == pytest.approx(orc.value_plain(kind, parent[0::2], z, z, lam), rel=1e-6 if dt == np.float32 else 1e-13)
+    psi = sp.shifted(sp.NormL1(lam), x)
+    _, sj, q = inputs(n, dt)
+    psi2 = sp.shifted(psi, T(sj))
+    y = torch.empty(n, dtype=tp.dtype, device=DEV)
+    sp.prox_(y, psi2, T(q), 0.1)
+    assert np.array_equal(N(y), orc.prox_l1(parent[0::2].copy(), sj, q, lam, 0.1))
+    # the caller writes the parent array: ψ sees it (the shadow is re-gathered before every call)
+    tp[0::2] += 1.0
+    sp.prox_(y, psi2, T(q), 0.1)
+    assert np.array_equal(N(y), orc.prox_l1((parent[0::2] + dt(1.0)).astype(dt), sj, q, lam, 0.1))
+    # shift!(ψ, v) writes through the view into the parent array, odd entries untouched
+    v = orc.uniform(n, 9, dt, 2.0, -1.0)
+    before_odd = N(tp[1::2]).copy()
+    sp.shift_(psi, T(v))
+    assert np.array_equal(N(tp[0::2]), v) and np.array_equal(N(tp[1::2]), before_odd)
+    sp.prox_(y, psi2, T(q), 0.1)
+    assert np.array_equal(N(y), orc.prox_l1(v, sj, q, lam, 0.1))
