@@ -29,7 +29,7 @@ template <class Op> struct StepBlocks {
 
 template <int VEC, int UNROLL, class Op>
 __global__ void __launch_bounds__(kEwThreads, StepBlocks<Op>::value)
-    step_kernel(const Op op, const typename Op::Real mnu, typename Op::Real* __restrict__ xsy, const long long n,
+    step_kernel(const Op op, const typename Op::Real mnu, typename Op::Real* xsy, const long long n,
                 Partial* __restrict__ partials) {
   using R = typename Op::Real;
   constexpr int NIN = Op::NIN;

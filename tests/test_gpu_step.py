@@ -125,3 +125,18 @@ def test_step_unaligned_and_empty(dt):
     psi0 = sp.shifted(sp.NormL0(1.0), e)
     _, r0 = sp.step_(e.clone(), psi0, e.clone(), 0.2)
     assert tuple(r0) == (0.0, 0.0, 0.0)
+
+
+@pytest.mark.parametrize("dt", DT)
+def test_step_in_place(dt):
+    # s may overwrite the gradient and xsy may overwrite xk (x <- x + s): every element's operands are read
+    # before its results are written, as for prox!(y, ψ, y, σ) (test/test_allocs.jl:108)
+    n = 100_001
+    xk, sj, grad = inputs(n, dt)
+    z = np.zeros(n, dt)
+    rs, rxsy, rpsi, rsn, rgd = orc.solver_step("l0", xk, z, grad, 0.9, 0.25)
+    txk, tg = T(xk), T(grad)
+    psi = sp.shifted(sp.NormL0(0.9), txk)
+    _, res = sp.step_(tg, psi, tg, 0.25, xsy=txk)
+    assert np.array_equal(N(tg), rs) and np.array_equal(N(txk), rxsy)
+    assert res.psi == pytest.approx(rpsi, rel=1e-5) and res.snorm == pytest.approx(rsn) and res.gdots == pytest.approx(rgd)
