@@ -25,6 +25,18 @@
 namespace spx {
 
 template <int K> struct ScaleSet { double s[K]; };
+#ifndef SPX_L1B2_UNROLL
+#define SPX_L1B2_UNROLL 2
+#endif
+// Packets loaded per thread and trip before the first use.  Float64: two (a 2R pass keeps only 32 B per thread in
+// flight otherwise).  Float32: two only in the single-trial pass (the decision pass -- all there is when the ball
+// is inactive); with four trials a Float32 packet already carries 16 element-trials of arithmetic per 16 bytes and
+// the second packet's registers spill.  Measured: Float64 n = 2^28 7.34 -> 6.64 ms; Float32 n = 2^29 active
+// 7.47 -> 7.99 ms with two packets everywhere, inactive 2.49 -> 2.38 ms.
+template <class R, int K> struct L1b2Unroll {
+  static constexpr int value = sizeof(R) == 8 ? SPX_L1B2_UNROLL : (K == 1 ? SPX_L1B2_UNROLL : 1);
+  static constexpr int minb = (value > 1 && sizeof(R) == 8 && K <= 4) ? 4 : 1;  // resident CTAs asked of ptxas
+};
 
 // Σ_i ProjB(z_i(k))² and Σ_i ProjB(z_i(k)) dProjB/dscale (= Σ over the unclamped entries of z_i (-xk_i))
 // for K scalings in one pass.  The clamp is two compares and selects (a NaN z stays NaN; a NaN bound is
@@ -33,7 +45,7 @@ template <int K> struct ScaleSet { double s[K]; };
 // the output vector aliases no input and can serve as scratch).  MODE 2: `sj` IS the stored mid, q is not read:
 // every later pass of the search moves 2R instead of 3R.
 template <class R, int K, int VEC, int MODE>
-__global__ void __launch_bounds__(kEwThreads)
+__global__ void __launch_bounds__(kEwThreads, L1b2Unroll<R, K>::minb)
     l1b2_norm_kernel(const R* xk, const R* sj, const R* q, R* midbuf, long long n, R ls, bool use_scale,
                      ScaleSet<K> sc, int nblocks_stride, Partial* __restrict__ partials) {
   double acc[K], dot[K];
@@ -87,13 +99,30 @@ __global__ void __launch_bounds__(kEwThreads)
       }
     }
   };
-  for (long long v = (long long)blockIdx.x * kEwThreads + threadIdx.x; v < nvec; v += (long long)gridDim.x * kEwThreads) {
-    Pack<R, VEC> a, b, c, mo;
-    ld_stream(xk + v * VEC, a);
-    ld_stream(sj + v * VEC, b);
-    if (MODE != 2) ld_stream(q + v * VEC, c);
-    packet(a.v, b.v, c.v, VEC, mo.v);
-    if (MODE == 1) st_stream(midbuf + v * VEC, mo);
+  // U packets per thread and trip, all loads issued before the first use: a 2R pass keeps only 32 B per
+  // thread in flight otherwise, too little to cover the HBM latency at the occupancy the K accumulators allow
+  constexpr int U = L1b2Unroll<R, K>::value;
+  for (long long v0 = (long long)blockIdx.x * (kEwThreads * U) + threadIdx.x; v0 < nvec;
+       v0 += (long long)gridDim.x * (kEwThreads * U)) {
+    Pack<R, VEC> a[U], b[U], c[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long v = v0 + (long long)u * kEwThreads;
+      if (v < nvec) {
+        ld_stream(xk + v * VEC, a[u]);
+        ld_stream(sj + v * VEC, b[u]);
+        if (MODE != 2) ld_stream(q + v * VEC, c[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long v = v0 + (long long)u * kEwThreads;
+      if (v < nvec) {
+        Pack<R, VEC> mo;
+        packet(a[u].v, b[u].v, c[u].v, VEC, mo.v);
+        if (MODE == 1) st_stream(midbuf + v * VEC, mo);
+      }
+    }
   }
   if (VEC > 1 && blockIdx.x == gridDim.x - 1) {
     const long long i = nvec * VEC + threadIdx.x;
@@ -123,7 +152,7 @@ static int32_t norm_pass_k(spx_ctx* ctx, int64_t n, const R* xk, const R* sj, co
   const bool vec = (bits & 15u) == 0;
   constexpr int VECW = 16 / (int)sizeof(R);
   const long long nv = vec ? n / VECW : n;
-  long long want = (nv + kEwThreads - 1) / kEwThreads;
+  long long want = (nv + kEwThreads * L1b2Unroll<R, K>::value - 1) / (kEwThreads * L1b2Unroll<R, K>::value);
   if (want < 1) want = 1;
   long long cap = (long long)ctx->sm_count * 8;
   const int grid = (int)(want < cap ? want : cap);
