@@ -168,18 +168,22 @@ class ClockSampler(threading.Thread):
              0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
              0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
 
-    def run(self):
+    def poll(self):
+        """One sample (SM clock + throttle reasons)."""
         if self.nv is None:
             return
-        while not self._halt.is_set():
-            try:
-                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
-                r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
-                for bit, name in self.NAMES.items():
-                    if r & bit and name != "gpu_idle":
-                        self.reasons.add(name)
-            except Exception:
-                pass
+        try:
+            self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+            r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            for bit, name in self.NAMES.items():
+                if r & bit and name != "gpu_idle":
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
+    def run(self):
+        while self.nv is not None and not self._halt.is_set():
+            self.poll()
             time.sleep(self.period)
 
     def stop(self):
@@ -261,6 +265,10 @@ def run_ours(args, rank, local_rank, world):
     for k in range(K):
         step(evs[k])
     t_end.record()
+    # the K steps are queued and the GPU is still working through them: a few samples from this thread as well (on
+    # some boxes the sampler thread gets a single NVML answer during a 140 ms region)
+    for _ in range(4):
+        sampler.poll()
     barrier()
     launches = sp.launch_count(dev) - launches0
     clocks = sampler.stop()
