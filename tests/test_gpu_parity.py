@@ -635,3 +635,37 @@ def test_strided_view_shift_aliases_the_parent_array(dt):
     assert np.array_equal(N(tp[0::2]), v) and np.array_equal(N(tp[1::2]), before_odd)
     sp.prox_(y, psi2, T(q), 0.1)
     assert np.array_equal(N(y), orc.prox_l1(v, sj, q, lam, 0.1))
+
+
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("regime", ["big_lambda", "tiny_lambda", "tiny_delta", "huge_delta", "tiny_shift"])
+def test_group_l2binf_search_regimes(dt, regime):
+    # the root search evaluates neither end of the reference's bracket unless it walks into it (froot is increasing):
+    # regimes where it does -- no sign change at all (y = 0), roots next to lmin or lmax, an interval with lmax < lmin
+    offs = np.concatenate([[0], np.cumsum([64] * 40 + [5, 1, 300, 17, 1100, 2])])
+    n = int(offs[-1]); ng = len(offs) - 1
+    xk, sj, q = inputs(n, dt)
+    lam_g = (dt(0.5) + orc.uniform(ng, 12, dt)).astype(dt)
+    sigma, delta = 0.3, 0.5
+    if regime == "big_lambda":
+        lam_g = (lam_g * dt(200)).astype(dt)
+    elif regime == "tiny_lambda":
+        lam_g = (lam_g * dt(1e-6)).astype(dt)
+    elif regime == "tiny_delta":
+        delta = 1e-4
+    elif regime == "huge_delta":
+        delta = 50.0
+    elif regime == "tiny_shift":
+        xk = (xk * dt(1e-3)).astype(dt); sj = (sj * dt(1e-3)).astype(dt); q = (q * dt(1e-3)).astype(dt)
+        lam_g = (lam_g * dt(5)).astype(dt)
+    h = sp.GroupNormL2(T(lam_g), None, offsets=T(offs))
+    psi = sp.shifted(sp.shifted(h, T(xk), delta, sp.NormLinf(1.0)), T(sj))
+    y = torch.empty(n, dtype=T(q).dtype, device=DEV)
+    sp.prox_(y, psi, T(q), sigma)
+    ref = orc.prox_groupl2binf(xk, sj, q, offs, lam_g, sigma, delta)
+    got = N(y)
+    scale = np.abs(xk) + np.abs(sj) + np.abs(q) + (1 if regime != "tiny_shift" else 1e-3)
+    tol = (1e-9 if dt == np.float64 else 2e-4) * scale
+    assert np.all(np.abs(got.astype(np.float64) - ref.astype(np.float64)) <= tol)
+    zr = ref == (np.zeros(n, dt) - (xk + sj)); zg = got == (np.zeros(n, dt) - (xk + sj))
+    assert np.array_equal(zr, zg)
