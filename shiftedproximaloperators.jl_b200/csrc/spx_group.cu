@@ -549,22 +549,14 @@ __device__ __forceinline__ float ulp_step(float x, int k) { return __int_as_floa
 // copies of its state).  Returns the step c(n*) and whether the group's prox is zero.
 //
 // fzero(froot, lmin, lmax) (Roots' bisection) ends on two adjacent floats around the sign change of
-// froot.  Same end state, an order of magnitude fewer evaluations:
-//  * froot(n) = n - ||w(c(n))|| is INCREASING: every |w_i| = |clamp(sol_i, σc (xk_i - Δ), σc (xk_i + Δ))| grows with
-//    c, and c(n) = n / (σ (n - σλ)) falls with n.  So the reference's "no root" test f(lmin) f(lmax) > 0 (:102)
-//    means f(lmin) > 0 or f(lmax) < 0, and neither end has to be evaluated unless the search walks into it.
-//  * the search starts at ||sol|| (the root itself when nothing is thresholded, and close to it otherwise; it
-//    comes out of the pass that computes lmax) and gets its bracket from Newton steps -- the derivative comes out
-//    of the same pass over the group: from the right a Newton step on this concave function lands left of the
-//    root, from the left it is stretched by 1.5 to land right of it; after three tries on a side the end of the
-//    interval itself is evaluated, which also settles the "no root" cases.
-//  * inside the bracket: safeguarded Newton steps from the last point; as soon as a step lands within k ulps
-//    (k = 1, then 4, 16, ...) of an end of the bracket the next evaluation is placed k ulps inside that end --
-//    stepping over the root, which leaves a bracket of k ulps that two or three midpoint steps close.  A step
-//    that leaves the bracket is replaced by the midpoint, and after 40 steps (never observed) the search
-//    degrades to plain bisection, which terminates by itself.
-// 5.1 evaluations per round of four groups of 64 instead of 6.8 with both ends evaluated first and Newton
-// started from lmax (and ~60 bisections per group in the reference).
+// froot.  Same end state, an order of magnitude fewer evaluations: froot is smooth between the kinks of
+// the soft threshold and nearly linear above the root, so safeguarded Newton steps from lmax (the
+// derivative comes out of the same pass over the group) converge in three or four evaluations; as soon
+// as a step lands within k ulps (k = 1, then 4, 16, ...) of an end of the bracket the next evaluation is placed k ulps inside
+// that end -- stepping over the root, which leaves a bracket of k ulps that two or three midpoint steps
+// close.  A step that leaves the bracket is replaced by the midpoint -- unless one end of the bracket already sits
+// on the root, which is then stepped over -- and after 40 steps (never observed) the search degrades to plain
+// bisection, which terminates by itself.
 template <class R, class View>
 __device__ __forceinline__ bool binf_solve(const View& gv, bool valid, R lam, R sigma, R delta, R& step_out) {
   const R eps = Eps<R>::value;
@@ -592,88 +584,70 @@ __device__ __forceinline__ bool binf_solve(const View& gv, bool valid, R lam, R 
   gv.norms(sigma * step, sigma * dstep, z2, s2, x2);
   const R zlmax = (R)sqrt_fast(z2) / sigma, nsol = (R)sqrt_fast(s2), nxk = (R)sqrt_fast(x2);
   const R lmax = nsol + sigma * (zlmax + R(1) * lam * nxk);  // |(ϵ-1)/ϵ + 1| = 1 for ϵ = 1  (:100)
-  // One froot call site (the kernel is instruction-cache bound otherwise).
-  R a = lmin, fa = R(-1), bb = lmax, fb = R(1);  // ends of the bracket; the signs stand in until an end is evaluated
-  bool have_a = false, have_b = false;
-  R x = nsol < lmin ? lmin : (nsol > lmax ? lmax : nsol), fx = R(0), dx = R(1);  // last point evaluated
-  // lmax < lmin (a shift far inside the threshold): no interval to search; both ends are evaluated in the
-  // reference's order and the better one is taken, as its bisection loop does when it cannot split the bracket
-  const bool reversed = !(lmin <= lmax);
+  // One froot call site (the kernel is instruction-cache bound otherwise): trips 0 and 1 evaluate the two
+  // ends of the bracket, the following ones are the search.
+  R a = lmin, fa = R(0), bb = lmax, fb = R(0);
+  R x = lmax, fx = R(0), dx = R(1);  // Newton state
   bool zero_out = false, done = !valid || !(lmin > R(0));
-  int kulp = 1, tries = 0;
-  for (int it = 0; it < 400; ++it) {
-    R xn = x;
+  int kulp = 1;
+  for (int it = -2; it < 400; ++it) {
+    R xn;
     bool probed = false;
-    if (reversed) {
-      done = done || it >= 2;
-      if (it > 0 && !__any_sync(0xffffffffu, !done)) break;
-      xn = it == 0 ? lmin : lmax;
-    } else if (it > 0) {
-      const bool bracketed = have_a && have_b;
+    if (it < 0) {
+      xn = (it == -2) ? lmin : lmax;
+    } else {
       const R mid = a + (bb - a) / R(2);
-      if (bracketed) done = done || adjacent_or_crossed(a, mid, bb);
+      done = done || adjacent_or_crossed(a, mid, bb);
       if (!__any_sync(0xffffffffu, !done)) break;
-      const R xs_ = x - div_fast(fx, dx);
-      if (bracketed) {
-        xn = mid;
-        if (it < 40) {
-          if ((a < xs_) && (xs_ < bb)) xn = xs_;
-          const R a_k = ulp_step(a, kulp), b_k = ulp_step(bb, -kulp);
-          if (xn <= a_k) {
-            xn = (a_k < mid) ? a_k : mid;
-            probed = true;
-          } else if (xn >= b_k) {
-            xn = (b_k > mid) ? b_k : mid;
-            probed = true;
-          }
+      xn = mid;
+      if (it < 40) {
+        const R xs_ = x - div_fast(fx, dx);
+        const bool inside = (a < xs_) && (xs_ < bb);
+        if (inside) xn = xs_;
+        // A Newton step that leaves the bracket while one end already sits on the root (|f| within 4096 ulps of n;
+        // froot' >= 1: the norm it subtracts falls with n) -- Newton converged onto it from one side while the other
+        // end is still far, the usual course when σλ >> ||sol|| (a sparse solution) and the root sits next to the
+        // pole of c(n): step over that end instead of halving the distance to the far one ~50 times.  The vote keeps
+        // this out of the common trip.
+        if (__any_sync(0xffffffffu, !done && !inside)) {
+          const R tiny = R(4096) * eps;
+          if (!inside) xn = (jl_abs(fa) <= tiny * a) ? a : ((jl_abs(fb) <= tiny * bb) ? bb : mid);
         }
-      } else if (!have_a) {  // f(x) > 0: a Newton step to the left, or lmin itself
-        ++tries;
-        xn = (tries <= 3 && (lmin < xs_) && (xs_ < x)) ? xs_ : lmin;
-      } else {  // f(x) < 0: a stretched Newton step to the right, or lmax itself
-        ++tries;
-        const R xo = x + R(1.5) * (xs_ - x);
-        xn = (tries <= 3 && (x < xo) && (xo < lmax)) ? xo : lmax;
+        const R a_k = ulp_step(a, kulp), b_k = ulp_step(bb, -kulp);
+        if (xn <= a_k) {
+          xn = (a_k < mid) ? a_k : mid;
+          probed = true;
+        } else if (xn >= b_k) {
+          xn = (b_k > mid) ? b_k : mid;
+          probed = true;
+        }
       }
     }
     const R fn = froot(xn);
-    if (!done && reversed) {
-      if (it == 0) fa = fn;
-      else {
-        fb = fn;
-        zero_out = fa * fb > R(0);
-        done = true;
-      }
+    if (it == -2) {
+      fa = fn;
+    } else if (it == -1) {
+      fb = fn;
+      fx = fn;
+      dx = dfx;
+      zero_out = fa * fb > R(0);
+      done = done || zero_out || (fa != fa) || (fb != fb);
+      if (!done && fa == R(0)) { bb = a; fb = R(0); done = true; }
+      if (!done && fb == R(0)) { a = bb; fa = R(0); done = true; }
     } else if (!done) {
       x = xn;
       fx = fn;
       dx = dfx;
-      if (fn != fn) {  // NaN: no search; the far end is taken like the reference's order of tests would
-        a = lmin;
-        bb = lmax;
-        fa = fn;
-        fb = fn;
-        done = true;
-      } else if (fn == R(0)) {
+      if (fn == R(0)) {
         a = bb = xn;
         fa = fb = R(0);
         done = true;
-      } else if (fn < R(0)) {
+      } else if ((fn < R(0)) == (fa < R(0))) {
         a = xn;
         fa = fn;
-        have_a = true;
-        if (xn == lmax) {  // f(lmax) < 0: f(lmin) f(lmax) > 0
-          zero_out = true;
-          done = true;
-        }
       } else {
         bb = xn;
         fb = fn;
-        have_b = true;
-        if (xn == lmin) {  // f(lmin) > 0: f(lmin) f(lmax) > 0
-          zero_out = true;
-          done = true;
-        }
       }
       if (probed) kulp = kulp < (1 << 20) ? kulp * 4 : kulp;
     }
@@ -691,7 +665,7 @@ __device__ __forceinline__ bool binf_solve(const View& gv, bool valid, R lam, R 
 #define SPX_GB_MINB 3
 #endif
 template <class R, int PART>
-__global__ void __launch_bounds__(kGroupThreads, (PART == 0 || sizeof(R) == 4) ? SPX_GB_MINB : 2)
+__global__ void __launch_bounds__(kGroupThreads, PART == 0 ? SPX_GB_MINB : 2)
     group_l2binf_kernel(R* y, const R* xk, const R* sj, const R* q, long long ngroups,
                         const long long* __restrict__ offs, const R* __restrict__ lambda_g, R sigma, R delta,
                         UDiv<R> by_sigma, unsigned long long* task_counter, unsigned* long_flag) {

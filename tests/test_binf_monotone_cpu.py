@@ -1,7 +1,8 @@
-"""The GroupNormL2Binf kernels never evaluate the ends of the reference's bracket unless the search walks into them:
-they rely on froot (shiftedGroupNormL2Binf.jl:87-93) being increasing in n, so that the reference's "no root" test
-f(lmin) f(lmax) > 0 (:102) is f(lmin) > 0 or f(lmax) < 0.  This pins that property on the reference's own formula
-(numpy restatement, CPU only) together with the end state the search must reach."""
+"""Properties of froot (shiftedGroupNormL2Binf.jl:87-93) the GroupNormL2Binf root search leans on, pinned on the
+reference's own formula (numpy restatement, CPU only): froot is increasing in n with slope >= 1 (the norm it
+subtracts falls with n), so a bracket end whose residual is within k ulps of n lies within k ulps of the root --
+the rule by which the kernel steps over such an end instead of bisecting towards the far one (csrc/spx_group.cu,
+binf_solve) -- and the reference's "no root" test f(lmin) f(lmax) > 0 (:102) means f(lmin) > 0 or f(lmax) < 0."""
 import numpy as np
 import pytest
 
@@ -31,7 +32,7 @@ def test_froot_is_increasing_between_lmin_and_lmax(m, delta):
         grid = sl + (lmin - sl) * np.geomspace(1.0, (lmax - sl) / (lmin - sl), 400)
         f = np.array([froot(n, sol, xk, lam, sigma, delta) for n in grid])
         scale = np.abs(grid) + np.abs(grid - f)
-        assert np.all(np.diff(f) >= -1e-12 * scale[1:])  # increasing up to the rounding of the norm
+        assert np.all(np.diff(f) >= np.diff(grid) - 1e-12 * scale[1:])  # slope >= 1 up to the rounding of the norm
 
 
 def test_oracle_prox_is_zero_exactly_when_there_is_no_sign_change():

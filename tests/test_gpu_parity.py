@@ -640,8 +640,8 @@ def test_strided_view_shift_aliases_the_parent_array(dt):
 @pytest.mark.parametrize("dt", DT)
 @pytest.mark.parametrize("regime", ["big_lambda", "tiny_lambda", "tiny_delta", "huge_delta", "tiny_shift"])
 def test_group_l2binf_search_regimes(dt, regime):
-    # the root search evaluates neither end of the reference's bracket unless it walks into it (froot is increasing):
-    # regimes where it does -- no sign change at all (y = 0), roots next to lmin or lmax, an interval with lmax < lmin
+    # regimes that stress the root search: no sign change at all (y = 0), roots next to lmin (the pole of c(n): the
+    # end-on-root rule of binf_solve) or next to lmax, an interval with lmax < lmin
     offs = np.concatenate([[0], np.cumsum([64] * 40 + [5, 1, 300, 17, 1100, 2])])
     n = int(offs[-1]); ng = len(offs) - 1
     xk, sj, q = inputs(n, dt)

@@ -166,6 +166,11 @@ def main():
         timeit(f"value_groupl2_{gname}", lambda psi=psi: psi(y), 3 * R)
         psib = sp.shifted(sp.shifted(h, xk, 0.5, sp.NormLinf(1.0)), sj)
         timeit(f"prox_groupl2binf_{gname}", lambda psi=psib: sp.prox_(y, psi, q, 0.3), 4 * R, note=f"{ng} groups")
+        if gname == "g64":  # σλ_g >> ||sol_g||: the regime of a sparse solution (root next to the pole of c(n) at σλ)
+            hb = sp.GroupNormL2(lam_g * 200.0, None, offsets=offs)
+            psil = sp.shifted(sp.shifted(hb, xk, 0.5, sp.NormLinf(1.0)), sj)
+            timeit("prox_groupl2binf_g64_biglambda", lambda psi=psil: sp.prox_(y, psi, q, 0.3), 4 * R,
+                   note="lambda_g x 200")
     # top-r batch: problems of 65536, r = 1024
     if re.search(args.only, "prox_indballl0"):
         pn = 65536
