@@ -54,6 +54,20 @@ def test_cuda_path_against_the_committed_fixtures(suf):
     assert close(sp.prox(sh(sp.shifted(hg, T(xk))), T(q), 0.3), "prox_groupl2", 8 * eps)
     assert close(sp.prox(sh(sp.shifted(hg, T(xk), delta, sp.NormLinf(1.0))), T(q), 0.3), "prox_groupl2binf",
                  1e-9 if suf == "f64" else 2e-4)
+    # fused solver step: s and xsy like the prox! of the same h, the three scalars to the sums' accuracy
+    for name, h in (("l1", sp.NormL1(lam)), ("l0", sp.NormL0(lam)), ("lhalf", sp.RootNormLhalf(lam))):
+        for tag, psi in (("step", sh(sp.shifted(h, T(xk)))), ("stepbox", sh(sp.shifted(h, T(xk), T(l), T(ub))))):
+            s_ = torch.empty(len(q), dtype=T(q).dtype, device=DEV)
+            xsy = torch.empty_like(s_)
+            _, res = sp.step_(s_, psi, T(q), mg.NU, xsy=xsy)
+            if name == "lhalf":
+                assert close(s_, f"{tag}_{name}_s", 4 * eps) and close(xsy, f"{tag}_{name}_xsy", 4 * eps)
+            else:
+                assert exact(s_, f"{tag}_{name}_s") and exact(xsy, f"{tag}_{name}_xsy")
+            gpsi, gsn, ggd = GOLD[f"{tag}_{name}_scalars_{suf}"]
+            rel = (1e-12 if suf == "f64" else 1e-5) if name != "lhalf" else (1e-9 if suf == "f64" else 1e-4)
+            assert res.psi == pytest.approx(gpsi, rel=rel) and res.snorm == pytest.approx(gsn, rel=rel)
+            assert abs(res.gdots - ggd) <= rel * (abs(ggd) + float(np.sum(np.abs(q.astype(np.float64)) ** 2)))
     assert exact(sp.prox(sh(sp.shifted(sp.IndBallL0(31), T(xk))), T(q), 1.0), "prox_indballl0")
     assert exact(sp.prox(sh(sp.shifted(sp.IndBallL0(31), T(xk), 1.0, sp.NormLinf(1.0))), T(q), 1.0), "prox_indballl0binf")
     torch.cuda.synchronize()

@@ -17,6 +17,7 @@ from oracle import oracle as orc  # noqa: E402
 
 N = 257
 LAM, SIGMA, DELTA = 0.8, 0.1, 0.5
+NU = 0.35  # step length of the fused solver step
 
 
 def inputs(dt):
@@ -53,6 +54,13 @@ def build():
         out[f"l1b2_delta_{suf}"] = np.array([0.5 * full])
         out[f"prox_groupl2_{suf}"] = orc.prox_groupl2(xk, sj, q, offs, lam_g, 0.3)
         out[f"prox_groupl2binf_{suf}"] = orc.prox_groupl2binf(xk, sj, q, offs, lam_g, 0.3, DELTA)
+        # fused solver step (oracle.solver_step: the composition -ν∇f, prox!, xk+sj+s, ψ(s), ‖s‖, ∇f's), ∇f = q
+        for h in ("l1", "l0", "lhalf"):
+            for tag, bounds in (("step", ()), ("stepbox", (l, ub))):
+                s_, xsy, psi, sn, gd = orc.solver_step(h, xk, sj, q, LAM, NU, *bounds)
+                out[f"{tag}_{h}_s_{suf}"] = s_
+                out[f"{tag}_{h}_xsy_{suf}"] = xsy
+                out[f"{tag}_{h}_scalars_{suf}"] = np.array([psi, sn, gd])
         out[f"prox_indballl0_{suf}"] = orc.prox_indballl0(xk, sj, q, 31)
         out[f"prox_indballl0binf_{suf}"] = orc.prox_indballl0(xk, sj, q, 31, delta=1.0)
     return out
