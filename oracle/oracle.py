@@ -141,6 +141,20 @@ def prox_box(op, xk, sj, q, l, u, lam, sigma, selected=None):
     return y
 
 
+def prox_lhalfbox_dbg(xk, sj, q, l, u, lam, sigma, selected=None):
+    """ShiftedRootNormLhalfBox prox! plus, per element, the candidate `findmin` chose (0 left edge, 1 right edge,
+    2 the kink -xs, 3 the stationary point; -1 not selected), the four objectives (obj[:, :4]) and the stationary
+    candidate `val - xs` itself (obj[:, 4]).  Returns (y, pick, obj[n, 5])."""
+    dt = q.dtype; s = _suf(dt); xk, sj, q = (_vec(a, dt) for a in (xk, sj, q))
+    lv, ls = _bound(l, dt); uv, us = _bound(u, dt)
+    kind, lst, nsel = _sel(selected)
+    y = np.empty_like(q); sol = np.empty_like(q)
+    pick = np.empty(q.size, np.int8); obj = np.full((q.size, 5), np.nan)
+    _call(f"orc_prox_lhalfbox_dbg_{s}", None, i64(q.size), _p(y), _p(sol), _p(xk), _p(sj), _p(q),
+          _p(lv), f64(ls), _p(uv), f64(us), i32(kind), _p(lst), i64(nsel), f64(lam), f64(sigma), _p(pick), _p(obj))
+    return y, pick, obj
+
+
 def iprox_box(op, xk, sj, g, d, l, u, lam, selected=None):
     dt = g.dtype; s = _suf(dt); xk, sj, g, d = (_vec(a, dt) for a in (xk, sj, g, d))
     lv, ls = _bound(l, dt); uv, us = _bound(u, dt)
@@ -185,6 +199,19 @@ def prox_groupl2binf(xk, sj, q, offs, lam_g, sigma, delta):
     _call(f"orc_prox_groupl2binf_{s}", None, i64(q.size), _p(y), _p(sol), _p(xk), _p(sj), _p(q),
           i64(offs.size - 1), _p(offs), _p(lam_g), f64(sigma), f64(delta))
     return y
+
+
+def prox_groupl2binf_dbg(xk, sj, q, offs, lam_g, sigma, delta, ulp_shift=0):
+    """ShiftedGroupNormL2Binf prox! plus per-group diagnostics: the root the bisection ended on (NaN when the
+    bracket held no sign change) and whether the group was zeroed.  `ulp_shift` moves every root by that many
+    ulps before the final formula (conditioning probe).  Returns (y, nroot[ng], zeroed[ng])."""
+    dt = q.dtype; s = _suf(dt); xk, sj, q, lam_g = (_vec(a, dt) for a in (xk, sj, q, lam_g))
+    offs = _offsets(offs); y = np.empty_like(q); sol = np.empty_like(q)
+    ng = offs.size - 1
+    nroot = np.empty(ng, np.float64); zg = np.empty(ng, np.int8)
+    _call(f"orc_prox_groupl2binf_dbg_{s}", None, i64(q.size), _p(y), _p(sol), _p(xk), _p(sj), _p(q),
+          i64(ng), _p(offs), _p(lam_g), f64(sigma), f64(delta), _p(nroot), _p(zg), i64(int(ulp_shift)))
+    return y, nroot, zg.astype(bool)
 
 
 def prox_indballl0(xk, sj, q, r, delta=None):

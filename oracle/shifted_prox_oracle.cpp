@@ -405,7 +405,10 @@ void iprox_l0box(int64_t n, R* y, const R* xk, const R* sj, const R* g, const R*
 // restated with std::complex<double> (glibc cacos/ccos), real part taken.
 template <class R>
 void prox_lhalfbox(int64_t n, R* y, R* sol, const R* xk, const R* sj, const R* q, Bound<R> l,
-                   Bound<R> u, const Sel& sel, R lambda, R sigma) {
+                   Bound<R> u, const Sel& sel, R lambda, R sigma, int8_t* pick = nullptr,
+                   double* obj = nullptr) {
+  // pick / obj (tests only): index of the candidate `findmin` chose (-1: not selected) and the
+  // four objectives (c[0..3]) plus candidate 4 itself (obj[5 i + 4]) for every element, so a parity test can tell a true tie from a wrong pick
   for (int64_t i = 0; i < n; ++i) sol[i] = xk[i] + sj[i];  // :94
   const double two_pi_3 = 6.283185307179586 / 3.0;
   const double inf = std::numeric_limits<double>::infinity();
@@ -413,6 +416,7 @@ void prox_lhalfbox(int64_t n, R* y, R* sol, const R* xk, const R* sj, const R* q
     R li = l.at(i), ui = u.at(i), xi = xk[i], si = sj[i], qi = q[i];
     if (!sel.has(i)) {
       y[i] = prox_zero(qi, li - si, ui - si);
+      if (pick) pick[i] = -1;
       continue;
     }
     R xs = sol[i];
@@ -445,6 +449,11 @@ void prox_lhalfbox(int64_t n, R* y, R* sol, const R* xk, const R* sj, const R* q
     for (int k = 1; k < 4; ++k)
       if (jl_isgreater(fm, c[k])) { fm = c[k]; a = k; }
     y[i] = a == 0 ? (li - si) : a == 1 ? (ui - si) : a == 2 ? -xs : (R)(val - (double)xs);
+    if (pick) pick[i] = (int8_t)a;
+    if (obj) {
+      for (int k = 0; k < 4; ++k) obj[5 * i + k] = c[k];
+      obj[5 * i + 4] = val - (double)xs;  // candidate 4 itself (Float64, before the store rounds it to R)
+    }
   }
 }
 
@@ -558,7 +567,11 @@ double prox_groupl2_unshifted(int64_t n, R* y, const R* x, int64_t ngroups, cons
 // bracket is two adjacent floats or an exact zero (third party, restated).
 template <class R>
 void prox_groupl2binf(int64_t n, R* y, R* sol, const R* xk, const R* sj, const R* q,
-                      int64_t ngroups, const int64_t* offs, const R* lambda, R sigma, R delta) {
+                      int64_t ngroups, const int64_t* offs, const R* lambda, R sigma, R delta,
+                      double* nroot_out = nullptr, int8_t* zero_out_g = nullptr, int64_t ulp_shift = 0) {
+  // nroot_out / zero_out_g / ulp_shift (tests only): the root each group's bisection ended on, whether the
+  // group was zeroed, and a shift of that root by whole ulps before the final formula -- the sensitivity of y
+  // to the last bit of the root, i.e. the conditioning a parity tolerance has to allow for
   const R eps = std::numeric_limits<R>::epsilon();
   for (int64_t i = 0; i < n; ++i) sol[i] = (q[i] + xk[i]) + sj[i];  // :80
   std::vector<R> tmp;
@@ -604,9 +617,13 @@ void prox_groupl2binf(int64_t n, R* y, R* sol, const R* xk, const R* sj, const R
         }
         nroot = (std::fabs(fa) <= std::fabs(fb)) ? a : bb;
       }
+      for (int64_t k = 0; k < ulp_shift; ++k) nroot = std::nextafter(nroot, std::numeric_limits<R>::infinity());
+      for (int64_t k = 0; k > ulp_shift; --k) nroot = std::nextafter(nroot, -std::numeric_limits<R>::infinity());
       step = cstep(nroot);
       if (std::fabs(nroot - sl) == R(0)) zero_out = true;  // `abs(n - σλ) ≈ 0`  (:107)
     }
+    if (nroot_out) nroot_out[g] = (fl * fm > R(0)) ? std::numeric_limits<double>::quiet_NaN() : (double)nroot;
+    if (zero_out_g) zero_out_g[g] = zero_out ? 1 : 0;
     if (zero_out) {
       for (int64_t i = b; i < e; ++i) y[i] = 0;
     } else {
@@ -813,6 +830,22 @@ double value_groupl2(int64_t n, const R* xk, const R* sj, const R* y, int64_t ng
                                           const R* q, int64_t ng, const int64_t* offs,            \
                                           const R* lambda, double sigma, double delta) {          \
     prox_groupl2binf<R>(n, y, sol, xk, sj, q, ng, offs, lambda, (R)sigma, (R)delta);              \
+  }                                                                                                \
+  ORC_API void orc_prox_groupl2binf_dbg_##SUF(int64_t n, R* y, R* sol, const R* xk, const R* sj,  \
+                                              const R* q, int64_t ng, const int64_t* offs,        \
+                                              const R* lambda, double sigma, double delta,        \
+                                              double* nroot, int8_t* zero_g, int64_t ulp_shift) { \
+    prox_groupl2binf<R>(n, y, sol, xk, sj, q, ng, offs, lambda, (R)sigma, (R)delta, nroot,        \
+                        zero_g, ulp_shift);                                                        \
+  }                                                                                                \
+  ORC_API void orc_prox_lhalfbox_dbg_##SUF(int64_t n, R* y, R* sol, const R* xk, const R* sj,     \
+                                           const R* q, const R* lvec, double lval, const R* uvec, \
+                                           double uval, int32_t sel_kind, const int64_t* sel_list,\
+                                           int64_t nsel, double lambda, double sigma,             \
+                                           int8_t* pick, double* obj) {                           \
+    Sel sel(sel_kind, sel_list, nsel, n);                                                         \
+    Bound<R> l{lvec, (R)lval}, u{uvec, (R)uval};                                                  \
+    prox_lhalfbox<R>(n, y, sol, xk, sj, q, l, u, sel, (R)lambda, (R)sigma, pick, obj);            \
   }                                                                                                \
   ORC_API void orc_prox_indballl0_##SUF(int64_t n, R* y, const R* xk, const R* sj, const R* q,    \
                                         int64_t r, int32_t binf, double delta) {                  \

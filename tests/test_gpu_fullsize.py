@@ -16,7 +16,7 @@ import numpy as np
 import pytest
 import torch
 
-from gpu_util import DEV, N, orc, sp
+from gpu_util import DEV, N, check_groupl2binf, check_lhalfbox, orc, sp
 from shiftedprox import _lib as L
 
 pytestmark = pytest.mark.gpu
@@ -74,7 +74,7 @@ def windows(n, w, count, rng):
 
 def test_c2_box_prox_iprox_at_2p28():
     """C2: L0Box prox!/iprox! (bit-exact: whole-vector checksum against the streamed oracle) and
-    RootNormLhalfBox prox! (windows, 4 ulp of the value scale), vector bounds, n = 2^28 Float64."""
+    RootNormLhalfBox prox! (five 4 Mi-element windows, every element: candidate choice + 4 ulp of the value scale), vector bounds, n = 2^28 Float64."""
     n = 1 << (28 - SHRINK)
     lam, sigma = 1.0, 0.1
     xk, sj, q = dev_uniform(n, 0, scale=4.0, shift=-2.0), dev_uniform(n, 1, shift=-0.5), dev_uniform(n, 2, scale=4.0, shift=-2.0)
@@ -104,17 +104,18 @@ def test_c2_box_prox_iprox_at_2p28():
     want = {"prox": 0, "iprox": 0}
     rng = np.random.default_rng(11)
     lh_windows = set(int(o) for o in rng.integers(0, n // chunk, size=3)) | {0, n // chunk - 1}
+    lh_flips = lh_checked = 0
     for c in range(n // chunk):
         i0 = c * chunk
         hxk, hsj, hq, hl, hu, hd = c2_host_inputs(i0, chunk)
         want["prox"] = (want["prox"] + host_checksum(orc.prox_box("l0", hxk, hsj, hq, hl, hu, lam, sigma), i0)) % (1 << 64)
         want["iprox"] = (want["iprox"] + host_checksum(orc.iprox_box("l0", hxk, hsj, hq, hd, hl, hu, lam), i0)) % (1 << 64)
         if c in lh_windows:
-            m = 1 << 16
-            ref = orc.prox_box("lhalf", hxk[:m], hsj[:m], hq[:m], hl[:m], hu[:m], lam, sigma)
-            tol = 4 * np.finfo(np.float64).eps * (np.abs(hxk[:m]) + np.abs(hsj[:m]) + np.abs(hq[:m]) + 1.0)
-            bad = np.abs(N(yh[i0:i0 + m]) - ref) > tol
-            assert bad.mean() <= 1e-4, (c, int(bad.sum()))
+            # LhalfBox: whole 4 Mi-element windows, every element -- same candidate as the oracle's findmin (true
+            # ties counted and logged), values to 4 ulp of the scale
+            lh_checked += chunk
+            lh_flips += check_lhalfbox(N(yh[i0:i0 + chunk]), hxk, hsj, hq, hl, hu, lam, sigma, label=f"2^28 window {c}")
+    print(f"[lhalfbox 2^{28 - SHRINK}] {lh_flips} tied picks fell on the other candidate in {lh_checked} checked elements")
     assert got == want
 
 
@@ -183,8 +184,8 @@ def test_c4_group_l2_and_binf_10m_groups_of_64():
         scale = np.abs(hxk) + np.abs(hsj) + np.abs(hq) + 1
         ref = orc.prox_groupl2(hxk, hsj, hq, ho, hlam, sigma)
         assert np.all(np.abs(N(y[i0:i0 + m]) - ref) <= 8 * np.finfo(np.float64).eps * scale)
-        refb = orc.prox_groupl2binf(hxk, hsj, hq, ho, hlam, sigma, delta)
-        assert np.all(np.abs(N(yb[i0:i0 + m]) - refb) <= 1e-9 * scale)
+        # support identical, 64 ulp of the value scale + the conditioning term (gpu_util.check_groupl2binf)
+        check_groupl2binf(N(yb[i0:i0 + m]), hxk, hsj, hq, ho, hlam, sigma, delta, label=f"C4 window at group {g0}")
 
 
 def test_c5_topr_batch_4096_problems():
