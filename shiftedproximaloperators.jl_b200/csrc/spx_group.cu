@@ -10,6 +10,8 @@
 // L1/L2; they run in a second launch of the same kernel (PART = 1) so that the register-resident rounds
 // and the deeply batched loads a lone warp needs to hide latency do not share one register budget.  Sums of squares are accumulated in Float64 whatever R is; the butterfly order is fixed, so
 // results are deterministic.
+#include <algorithm>
+
 #include "spx_elementwise.cuh"
 #include "spx_ops.cuh"
 
@@ -449,8 +451,8 @@ __device__ __forceinline__ void froot_term(float so, float xg, float sc, float s
   dot = __fma_rn(w, dw, dot);
 }
 
-template <class R> struct TileView {
-  const Tile<R, false>& t;
+template <class R, class TileT = Tile<R, false>> struct TileView {
+  const TileT& t;
   UDiv<R> by_sigma;
   // Σ f(sol_i, sol_i/σ, xk_i)² over the lane's group
   template <class F> __device__ __forceinline__ double sumsq(F f) const {
@@ -668,7 +670,9 @@ template <class R, int PART>
 __global__ void __launch_bounds__(kGroupThreads, PART == 0 ? SPX_GB_MINB : 2)
     group_l2binf_kernel(R* y, const R* xk, const R* sj, const R* q, long long ngroups,
                         const long long* __restrict__ offs, const R* __restrict__ lambda_g, R sigma, R delta,
-                        UDiv<R> by_sigma, unsigned long long* task_counter, unsigned* long_flag) {
+                        UDiv<R> by_sigma, unsigned long long* task_counter, unsigned* long_flag,
+                        const unsigned* __restrict__ uniform_flag) {
+  if (uniform_flag != nullptr && *uniform_flag != 0u) return;  // the uniform-layout kernels own this call
   if (PART == 1 && long_flag != nullptr && *long_flag == 0u) return;
   const int lane = threadIdx.x & 31;
   const long long warp = ((long long)blockIdx.x * kGroupThreads + threadIdx.x) >> 5;
@@ -761,6 +765,363 @@ __global__ void __launch_bounds__(kGroupThreads, PART == 0 ? SPX_GB_MINB : 2)
       pos += 32 >> k;
     }
   }
+}
+
+// ------------------------------------------- uniform layouts: the fast path --
+// Every group has m = 8 L elements (L = 2, 4, ..., 32 lanes; m = 16 ... 256; C4 of BASELINE.json: m = 64) and
+// the vector is 16-byte aligned.  No CSR planner, no per-element bounds tests: a warp round is 256 consecutive
+// elements (32/L whole groups), each lane holds 8 elements of its group as 128-bit packets, offsets from the
+// round base are compile-time constants.  spx_prox_groupl2binf_* takes this path when n == ngroups * m; a check
+// kernel verifies offs[g] == g m on the device first (no host synchronisation: a flag gates either path).
+//
+// The root search (shiftedGroupNormL2Binf.jl:87-107).  froot(n) = n - ||w(τ)||, τ = σ c(n) = n/(n - σλ), with
+// w_i = -τ (xk_i + Δ sign t_i) on the entries the soft threshold keeps and w_i = -sol_i on the others, i.e.
+// ||w||² = τ² A + B, piecewise in τ; froot' >= 1, so the root is unique.
+//   A  Float32 search (FP32 pipe, Float32 copies of sol and xk, Float32 sums): the three norms of :97-100, froot at
+//      both ends of the bracket, then Newton on h(n) = (n - σλ) froot(n)/n -- linear in n when B = 0, where plain
+//      Newton on froot crawls towards the pole of c(n) -- down to a step of 1e-5 n: three or four evaluations.
+//      The signs of froot(lmin), froot(lmax) (`fl*fm > 0`, :102) are only taken from Float32 values 1e-4 away from 0.
+//   B  one evaluation in R with Float64 sums; A and B of the current piece give froot', froot'' in closed form:
+//      a Halley step lands on the root to ~1 ulp (cubic: 1e-6 -> 1e-18).
+//   C  the final pass IS an evaluation: v = sol - σ softthres(sol/σ - c xk, Δc) = -w (:109), so ||v|| gives
+//      froot(n) = n - ||v|| in the reference's own arithmetic.  |froot(n)| <= max(4, min(32, 4/κ)) ulp(n),
+//      κ = σλ/(n - σλ), accepts n (froot' >= 1: n is within that many ulps of the root, the distance bisection to
+//      adjacent floats leaves between two summation orders).  Rounds that fail any check (NaN/Inf, magnitudes
+//      outside the Float32 range, no clear sign, ill-conditioned roots next to the pole, residual not met) are
+//      listed and redone by the bracketing search (binf_solve) in a second launch over the list.
+template <class R> struct UVec {
+  static constexpr int VEC = 16 / (int)sizeof(R);
+  static constexpr int NCH = kEPL / VEC;
+};
+constexpr int kRoundElems = 32 * kEPL;  // 256 consecutive elements per warp round
+
+template <class R, int L> struct UTile {
+  R sol[kEPL], xkr[kEPL];
+  int L_rt;  // == L (TileView reads a run-time width)
+  bool valid;
+  long long base;  // element index of the lane's first packet
+  static constexpr int VEC = UVec<R>::VEC, NCH = UVec<R>::NCH;
+  __device__ __forceinline__ void load(long long round, long long ngroups, int lane, const R* xk, const R* sj,
+                                       const R* q) {
+    constexpr int GPW = 32 / L;
+    const int gl = lane / L, sub = lane % L;
+    valid = round * GPW + gl < ngroups;
+    base = round * kRoundElems + (long long)gl * (kEPL * L) + sub * VEC;
+    L_rt = L;
+    Pack<R, VEC> pq[NCH], px[NCH], ps[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) pq[c].v[e] = px[c].v[e] = ps[c].v[e] = R(0);
+      if (valid) {
+        ld_stream(q + base + c * (L * VEC), pq[c]);
+        ld_stream(xk + base + c * (L * VEC), px[c]);
+        ld_stream(sj + base + c * (L * VEC), ps[c]);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < NCH; ++c)
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        sol[c * VEC + e] = (pq[c].v[e] + px[c].v[e]) + ps[c].v[e];  // :80
+        xkr[c * VEC + e] = px[c].v[e];
+      }
+  }
+};
+// TileView reads t.L
+template <class R> struct UTileRef {
+  const R (&sol)[kEPL];
+  const R (&xkr)[kEPL];
+  int L;
+};
+
+template <int L> __device__ __forceinline__ void usum2(float& a, float& b) {
+#pragma unroll
+  for (int o = L >> 1; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+}
+template <int L> __device__ __forceinline__ void usum2(double& a, double& b) {
+#pragma unroll
+  for (int o = L >> 1; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+}
+template <int L> __device__ __forceinline__ float usum(float a) {
+#pragma unroll
+  for (int o = L >> 1; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  return a;
+}
+template <int L> __device__ __forceinline__ double usum(double a) {
+#pragma unroll
+  for (int o = L >> 1; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  return a;
+}
+
+// ||w(τ)||² split into the thresholded entries (τ² A) and the others (B); T: arithmetic type, ACC: sum type
+__device__ __forceinline__ float fma_t(float a, float b, float c) { return fmaf(a, b, c); }
+__device__ __forceinline__ double fma_t(double a, double b, double c) { return __fma_rn(a, b, c); }
+__device__ __forceinline__ float abs_t(float a) { return fabsf(a); }
+__device__ __forceinline__ double abs_t(double a) { return fabs(a); }
+__device__ __forceinline__ float cps_t(float a, float b) { return copysignf(a, b); }
+__device__ __forceinline__ double cps_t(double a, double b) { return copysign(a, b); }
+template <class T, class ACC, int L>
+__device__ __forceinline__ void binf_eval(const T (&so)[kEPL], const T (&xg)[kEPL], T tau, T sdc, ACC& ssA, ACC& ssB) {
+  ACC a0 = 0, a1 = 0, b0 = 0, b1 = 0;
+#pragma unroll
+  for (int j = 0; j < kEPL; j += 2) {
+    {
+      const T t = fma_t(-tau, xg[j], so[j]);
+      const T a = abs_t(t) - sdc;
+      const T z = cps_t(a, t) - so[j];
+      const bool act = a > T(0);
+      const ACC u = (ACC)(act ? z : T(0)), v = (ACC)(act ? T(0) : so[j]);
+      a0 = fma_t(u, u, a0);
+      b0 = fma_t(v, v, b0);
+    }
+    {
+      const T t = fma_t(-tau, xg[j + 1], so[j + 1]);
+      const T a = abs_t(t) - sdc;
+      const T z = cps_t(a, t) - so[j + 1];
+      const bool act = a > T(0);
+      const ACC u = (ACC)(act ? z : T(0)), v = (ACC)(act ? T(0) : so[j + 1]);
+      a1 = fma_t(u, u, a1);
+      b1 = fma_t(v, v, b1);
+    }
+  }
+  ssA = a0 + a1;
+  ssB = b0 + b1;
+  usum2<L>(ssA, ssB);
+}
+
+__device__ __forceinline__ float rcp_f(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// 1/x to ~1e-12 (the Halley correction needs no more)
+__device__ __forceinline__ double rcp_d(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = __fma_rn(-x, y, 1.0);
+  y = __fma_rn(y, e, y);
+  e = __fma_rn(-x, y, 1.0);
+  return __fma_rn(y, e, y);
+}
+
+template <class R> struct LoCopy;
+template <> struct LoCopy<double> {
+  float so[kEPL], xg[kEPL];
+  __device__ __forceinline__ void set(const double (&sol)[kEPL], const double (&xkr)[kEPL]) {
+#pragma unroll
+    for (int j = 0; j < kEPL; ++j) {
+      so[j] = (float)sol[j];
+      xg[j] = (float)xkr[j];
+    }
+  }
+};
+
+// Phases A and B.  Returns false when the round has to go through the bracketing search.  On success: zero_out
+// (`fl*fm > 0`) and the root estimate n (R); fp_out = froot'(n).
+template <class R, int L>
+__device__ __forceinline__ bool binf_fast_search(const float (&so)[kEPL], const float (&xg)[kEPL],
+                                                 const R (&sol)[kEPL], const R (&xkr)[kEPL], bool valid, R lam,
+                                                 R sigma, R delta, R& n_out, double& fp_out, bool& zero_out) {
+  const R epsR = Eps<R>::value;
+  const R sl = lam * sigma;
+  const R lmin = sl * (R(1) + epsR);
+  const R ansatz = lmin + R(1);
+  const R step_a = ansatz / (sigma * (ansatz - sl));
+  const float slf = (float)sl, delf = (float)delta, lminf = (float)lmin;
+  // ---- A: the three norms of :97-100 at τa = σ step(ansatz)
+  const float tau_a = (float)sigma * (float)step_a;
+  float z2 = 0.f, s2 = 0.f, x2 = 0.f;
+  {
+    const float sdc = tau_a * delf;
+#pragma unroll
+    for (int j = 0; j < kEPL; ++j) {
+      const float t = fmaf(-tau_a, xg[j], so[j]);
+      const float a = fmaxf(fabsf(t) - sdc, 0.f);
+      z2 = fmaf(a, a, z2);
+      s2 = fmaf(so[j], so[j], s2);
+      x2 = fmaf(xg[j], xg[j], x2);
+    }
+    usum2<L>(z2, s2);
+    x2 = usum<L>(x2);
+  }
+  const float lmaxf = sqrt_approx(s2) + sqrt_approx(z2) + slf * sqrt_approx(x2);
+  // magnitudes the Float32 search is trusted with (squares neither overflow nor flush; NaN fails every test)
+  bool ok = (s2 > 1e-16f && s2 < 1e24f) && (x2 < 1e24f) && (z2 < 1e30f) && (delf < 1e12f) && (slf > 1e-12f && slf < 1e12f) &&
+            (lmaxf > lminf * 1.001f);
+  // ---- froot(lmin): τ = (1 + eps)/eps whatever σλ is
+  float fl;
+  {
+    const float tau_l = (float)((R(1) + epsR) / epsR);
+    float ssA, ssB;
+    binf_eval<float, float, L>(so, xg, tau_l, tau_l * delf, ssA, ssB);
+    const float nw = sqrt_approx(ssA + ssB);
+    fl = lminf - nw;
+    ok = ok && (fabsf(fl) > 1e-4f * fmaxf(lminf, nw));
+  }
+  // ---- froot(lmax), then Newton on h(n) = (n - σλ) froot(n) / n
+  float x = lmaxf, a_ = lminf, b_ = lmaxf;
+  bool done = !valid || !ok;
+  zero_out = false;
+#pragma unroll 1
+  for (int it = 0; it < 8; ++it) {
+    const float gap = x - slf;
+    const float rgap = rcp_f(gap), rx = rcp_f(x);
+    const float tau = x * rgap;
+    float ssA, ssB;
+    binf_eval<float, float, L>(so, xg, tau, tau * delf, ssA, ssB);
+    const float nw = sqrt_approx(ssA + ssB);
+    const float fx = x - nw;
+    // froot' = 1 + (Σ w dw/dτ) σλ / (||w|| gap²),  Σ w dw/dτ = τ A = ssA/τ
+    const float dfx = fmaf(ssA * slf, rx * rcp_f(nw) * rgap, 1.f);
+    if (it == 0) {
+      ok = ok && (fabsf(fx) > 1e-4f * x);
+      zero_out = (fl > 0.f) == (fx > 0.f);  // fl*fm > 0 (both are far from 0 here)
+      done = done || !ok || zero_out;
+    }
+    // h = gap fx / x,  h' = (fx + gap (froot' - fx/x)) / x
+    const float den = fmaf(gap, dfx - fx * rx, fx);
+    const float stp = gap * fx * rcp_f(den);
+    float xn = x - stp;
+    const bool conv = (fabsf(stp) <= 1e-5f * x) || (fx == 0.f);
+    a_ = (fx < 0.f) ? x : a_;
+    b_ = (fx < 0.f) ? b_ : x;
+    if (!(xn >= a_ && xn <= b_)) xn = 0.5f * (a_ + b_);  // also catches NaN
+    x = done ? x : xn;
+    done = done || conv;
+    if (!__any_sync(0xffffffffu, !done)) break;
+  }
+  ok = ok && done && (x == x);
+  // ---- B: one evaluation in R with Float64 sums, Halley step
+  const double xd = (double)x, sld = (double)sl;
+  const double gapd = xd - sld;
+  const double rg = rcp_d(gapd);
+  const double taud = xd * rg;
+  double ssA, ssB;
+  binf_eval<R, double, L>(sol, xkr, (R)taud, (R)((double)delta * taud), ssA, ssB);
+  const double ss = ssA + ssB;
+  const double phi = sqrt_fast(ss);
+  const double f = xd - phi;
+  // φ = ||w||:  φ'τ' = -ssA σλ/(x φ gap),  φ''τ'² = ssA ssB σλ²/(x² φ³ gap²),  φ'τ'' = 2 ssA σλ/(x φ gap²)
+  const double rD = rcp_d(xd * phi * gapd);
+  const double p1 = ssA * sld * rD;  // -φ'τ'
+  const double fp = 1.0 + p1;
+  const double fpp = -(p1 * (ssB * sld * rD) * (rD * xd * gapd) + 2.0 * p1 * rg);
+  const double n1 = xd - 2.0 * f * fp * rcp_d(__fma_rn(2.0 * fp, fp, -f * fpp));
+  n_out = (R)n1;
+  fp_out = fp;
+  // ill-conditioned roots (next to the pole of c) and anything non-finite go to the bracketing search
+  const double kap = sld * rcp_d(n1 - sld);
+  ok = ok && (zero_out || (n1 > (double)lmin && kap < 64.0 && n1 == n1));
+  return ok || !valid;
+}
+template <class R, int L>
+__device__ __forceinline__ bool binf_fast_search_entry(const UTile<R, L>& t, R lam, R sigma, R delta, R& n_out,
+                                                       double& fp_out, bool& zero_out);
+template <int L>
+__device__ __forceinline__ bool binf_fast_search_entry(const UTile<double, L>& t, double lam, double sigma, double delta,
+                                                       double& n_out, double& fp_out, bool& zero_out) {
+  LoCopy<double> lo;
+  lo.set(t.sol, t.xkr);
+  return binf_fast_search<double, L>(lo.so, lo.xg, t.sol, t.xkr, t.valid, lam, sigma, delta, n_out, fp_out, zero_out);
+}
+template <int L>
+__device__ __forceinline__ bool binf_fast_search_entry(const UTile<float, L>& t, float lam, float sigma, float delta,
+                                                       float& n_out, double& fp_out, bool& zero_out) {
+  return binf_fast_search<float, L>(t.sol, t.xkr, t.sol, t.xkr, t.valid, lam, sigma, delta, n_out, fp_out, zero_out);
+}
+
+#ifndef SPX_GU_MINB
+#define SPX_GU_MINB 2
+#endif
+// FAST: rounds grid-stride, failures appended to the work list.  !FAST: the listed rounds, bracketing search.
+template <class R, int L, bool FAST>
+__global__ void __launch_bounds__(kGroupThreads, FAST ? SPX_GU_MINB : 2)
+    group_l2binf_uniform_kernel(R* y, const R* xk, const R* sj, const R* q, long long ngroups,
+                                const R* __restrict__ lambda_g, R sigma, R delta, UDiv<R> by_sigma,
+                                const unsigned* __restrict__ uniform_flag, unsigned* wl_count, unsigned* wl_rounds) {
+  if (*uniform_flag == 0u) return;
+  constexpr int GPW = 32 / L;
+  constexpr int VEC = UVec<R>::VEC, NCH = UVec<R>::NCH;
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * kGroupThreads + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * kGroupThreads) >> 5;
+  const long long nrounds = FAST ? (ngroups + GPW - 1) / GPW : (long long)*wl_count;
+  for (long long it = warp; it < nrounds; it += nwarps) {
+    const long long round = FAST ? it : (long long)wl_rounds[it];
+    UTile<R, L> t;
+    t.load(round, ngroups, lane, xk, sj, q);
+    const R lam = t.valid ? lambda_g[round * GPW + lane / L] : R(1);
+    const R sl = lam * sigma;
+    R nroot = R(0), step = R(0);
+    double fp = 1.0;
+    bool zero_out = false;
+    if constexpr (FAST) {
+      const bool ok = binf_fast_search_entry<L>(t, lam, sigma, delta, nroot, fp, zero_out);
+      if (__any_sync(0xffffffffu, !ok)) {
+        if (lane == 0) wl_rounds[atomicAdd(wl_count, 1u)] = (unsigned)round;
+        continue;
+      }
+    } else {
+      UTileRef<R> ref{t.sol, t.xkr, L};
+      TileView<R, UTileRef<R>> gv{ref, by_sigma};
+      zero_out = binf_solve<R>(gv, t.valid, lam, sigma, delta, step);
+    }
+    // ---- C: y_g = l2prox(sol - σ softthres(sol/σ - step xk, Δ step), σλ) - (xk + sj)   (:109-116)
+    R w[kEPL];
+    if (FAST) step = nroot / (sigma * (nroot - sl));  // c(n)  (:85)
+    const R dstep2 = delta * step;
+    double ss = 0.0;
+#pragma unroll
+    for (int j = 0; j < kEPL; ++j) {
+      w[j] = t.sol[j] - sigma * softthres_sel(by_sigma(t.sol[j]) - step * t.xkr[j], dstep2);
+      ss = __fma_rn((double)w[j], (double)w[j], ss);
+    }
+    ss = usum<L>(ss);
+    const R nv = (R)sqrt_fast(ss);
+    const R alpha = zero_out ? R(0) : jl_max(R(0), R(1) - sl / nv);
+    if (FAST) {
+      // froot(nroot) = nroot - ||v|| in the reference's arithmetic: the acceptance test of the fast search
+      const R res = nroot - nv;
+      const R gap = nroot - sl;
+      // max(4, min(32, 4/κ)) ulps, κ = σλ/gap:  4/κ = 4 gap/σλ
+      const R ulps = jl_max(R(4), jl_min(R(32), R(4) * gap * (R)(1.0 / (double)sl)));
+      const bool accepted = zero_out || !t.valid || (jl_abs(res) <= ulps * Eps<R>::value * nroot);
+      if (__any_sync(0xffffffffu, !accepted)) {
+        if (lane == 0) wl_rounds[atomicAdd(wl_count, 1u)] = (unsigned)round;
+        continue;
+      }
+    }
+    if (t.valid) {
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        Pack<R, VEC> ps, po;
+        ld_stream(sj + t.base + c * (L * VEC), ps);  // an L2 hit: read a moment ago by this warp
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+          const int j = c * VEC + e;
+          const R o = zero_out ? R(0) : alpha * w[j];
+          po.v[e] = o - (t.xkr[j] + ps.v[e]);
+        }
+        st_stream(y + t.base + c * (L * VEC), po);
+      }
+    }
+  }
+}
+
+// flag = 1 iff offs[g] == g m for every g <= ngroups (grid-stride; the flag starts at 1)
+__global__ void __launch_bounds__(256) group_uniform_check_kernel(const long long* __restrict__ offs, long long ngroups,
+                                                                  long long m, unsigned* flag) {
+  bool bad = false;
+  for (long long g = (long long)blockIdx.x * 256 + threadIdx.x; g <= ngroups; g += (long long)gridDim.x * 256)
+    bad = bad || (offs[g] != g * m);
+  if (__syncthreads_or(bad) && threadIdx.x == 0) *flag = 0u;
 }
 
 // ----------------------------------------------------- group values (ψ(y)) --
@@ -1041,6 +1402,38 @@ static int32_t launch_group_l2(spx_ctx* ctx, int64_t n, R* y, const R* xk, const
   return SPX_OK;
 }
 
+template <class R, int L>
+static void launch_uniform_binf_L(spx_ctx* ctx, R* y, const R* xk, const R* sj, const R* q, int64_t ngroups,
+                                  const R* lambda_g, R sigma, R delta, UDiv<R> by_sigma, const unsigned* uniform_flag,
+                                  unsigned* wl_count, unsigned* wl_rounds) {
+  const long long nrounds = (ngroups + (32 / L) - 1) / (32 / L);
+  const long long want = (nrounds + (kGroupThreads / 32) - 1) / (kGroupThreads / 32);
+  auto grid_of = [&](const void* k) {
+    int per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kGroupThreads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    const long long cap = (long long)ctx->sm_count * per_sm;
+    return (int)std::max<long long>(1, std::min(want, cap));
+  };
+  group_l2binf_uniform_kernel<R, L, true>
+      <<<grid_of((const void*)group_l2binf_uniform_kernel<R, L, true>), kGroupThreads, 0, ctx->stream>>>(
+          y, xk, sj, q, ngroups, lambda_g, sigma, delta, by_sigma, uniform_flag, wl_count, wl_rounds);
+  group_l2binf_uniform_kernel<R, L, false>
+      <<<grid_of((const void*)group_l2binf_uniform_kernel<R, L, false>), kGroupThreads, 0, ctx->stream>>>(
+          y, xk, sj, q, ngroups, lambda_g, sigma, delta, by_sigma, uniform_flag, wl_count, wl_rounds);
+}
+template <class R>
+static void launch_uniform_binf(spx_ctx* ctx, int L, R* y, const R* xk, const R* sj, const R* q, int64_t ngroups,
+                                const R* lambda_g, R sigma, R delta, UDiv<R> by_sigma, const unsigned* uniform_flag,
+                                unsigned* wl_count, unsigned* wl_rounds) {
+  switch (L) {
+#define SPX_UL(LL) \
+  case LL: launch_uniform_binf_L<R, LL>(ctx, y, xk, sj, q, ngroups, lambda_g, sigma, delta, by_sigma, uniform_flag, wl_count, wl_rounds); break;
+    SPX_UL(2) SPX_UL(4) SPX_UL(8) SPX_UL(16) SPX_UL(32)
+#undef SPX_UL
+    default: break;
+  }
+}
+
 template <class R>
 static int32_t prox_group(spx_ctx* ctx, bool binf, int64_t n, R* y, const R* xk, const R* sj, const R* q,
                           int64_t ngroups, const int64_t* offs, const R* lambda_g, double sigma, double delta,
@@ -1061,15 +1454,34 @@ static int32_t prox_group(spx_ctx* ctx, bool binf, int64_t n, R* y, const R* xk,
     by_sigma.set((R)sigma);
     const int grid0 = group_grid(ctx, ngroups, (const void*)group_l2binf_kernel<R, 0>);
     const int grid1 = group_grid(ctx, ngroups, (const void*)group_l2binf_kernel<R, 1>);
-    int32_t st0 = ensure_scratch(ctx, 4096);
+    // uniform layout candidate: n == ngroups m, m = 8 L, 16-byte aligned vectors.  Whether offs really is
+    // {0, m, 2m, ...} is checked on the device; the flag gates the uniform kernels and the generic ones.
+    const int64_t m = ngroups > 0 && n % ngroups == 0 ? n / ngroups : 0;
+    const bool aligned = (((uintptr_t)y | (uintptr_t)xk | (uintptr_t)sj | (uintptr_t)q) & 15u) == 0;
+    const bool uni = aligned && (m == 16 || m == 32 || m == 64 || m == 128 || m == 256) && n < (int64_t(1) << 39);
+    const int64_t nrounds = uni ? (n + kRoundElems - 1) / kRoundElems : 0;
+    int32_t st0 = ensure_scratch(ctx, 4096 + (size_t)nrounds * sizeof(unsigned));
     if (st0 != SPX_OK) return st0;
     unsigned long long* counter = (unsigned long long*)ctx->d_scratch;  // long groups: dynamic task hand-out
     unsigned* long_flag = (unsigned*)((char*)ctx->d_scratch + 8);
-    SPX_CUDA(cudaMemsetAsync(ctx->d_scratch, 0, 16, ctx->stream));
+    unsigned* uniform_flag = (unsigned*)((char*)ctx->d_scratch + 12);
+    unsigned* wl_count = (unsigned*)((char*)ctx->d_scratch + 16);
+    unsigned* wl_rounds = (unsigned*)((char*)ctx->d_scratch + 4096);
+    SPX_CUDA(cudaMemsetAsync(ctx->d_scratch, 0, 32, ctx->stream));
+    if (uni) {
+      SPX_CUDA(cudaMemsetAsync(uniform_flag, 1, sizeof(unsigned), ctx->stream));
+      const int cgrid = (int)std::min<int64_t>((ngroups + 256) / 256, (int64_t)ctx->sm_count * 8);
+      group_uniform_check_kernel<<<cgrid, 256, 0, ctx->stream>>>((const long long*)offs, ngroups, m, uniform_flag);
+      launch_uniform_binf<R>(ctx, (int)(m / kEPL), y, xk, sj, q, ngroups, lambda_g, (R)sigma, (R)delta, by_sigma,
+                             uniform_flag, wl_count, wl_rounds);
+      ctx->launches += 3;
+    }
     group_l2binf_kernel<R, 0><<<grid0, kGroupThreads, 0, ctx->stream>>>(
-        y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, (R)sigma, (R)delta, by_sigma, nullptr, long_flag);
+        y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, (R)sigma, (R)delta, by_sigma, nullptr, long_flag,
+        uni ? uniform_flag : nullptr);
     group_l2binf_kernel<R, 1><<<grid1, kGroupThreads, 0, ctx->stream>>>(
-        y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, (R)sigma, (R)delta, by_sigma, counter, long_flag);
+        y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, (R)sigma, (R)delta, by_sigma, counter, long_flag,
+        uni ? uniform_flag : nullptr);
     ctx->launches += 2;
     SPX_CUDA(cudaGetLastError());
   }

@@ -82,7 +82,7 @@ def check_lhalfbox(got, xk, sj, q, l, u, lam, sigma, selected=None, label=""):
          the un-shifted value scale, on EVERY element (a flipped pick is compared with the candidate it picked).
 
     Returns the number of flipped picks (logged by the callers; 0 on every seeded input of the suite)."""
-    dt = q.dtype
+    dt = q.dtype.type
     n = q.size
     ref, pick, obj = orc.prox_lhalfbox_dbg(xk, sj, q, l, u, lam, sigma, selected=selected)
     lv = np.broadcast_to(np.asarray(l, dt), (n,))
@@ -130,7 +130,7 @@ def check_groupl2binf(got, xk, sj, q, offs, lam_g, sigma, delta, label="", floor
           |y_gpu - y_orc|_i <= eps(R) [ 64 scale_i + 16 κ_g (scale_i + n*_g) ]
       i.e. 64 ulp of the value scale plus 16 ulps of root displacement through the conditioning term; and the
       99.9th percentile of the error over well-conditioned groups (κ_g <= 1) must be <= 64 eps·scale outright."""
-    dt = q.dtype
+    dt = q.dtype.type
     n = q.size
     offs = np.asarray(offs, np.int64)
     ref, nroot, zeroed = orc.prox_groupl2binf_dbg(xk, sj, q, offs, lam_g, sigma, delta)

@@ -727,18 +727,41 @@ def test_indballl0binf_value_against_oracle(dt, n):
     delta = 0.7
     r = max(1, n // 10)
     psi = sp.shifted(sp.shifted(sp.IndBallL0(r), T(xk), delta, sp.NormLinf(1.0)), T(sj))
-    # (1) at the prox output: feasible, exactly r non-zeros -> 0
+    # (1) at the prox outputs (once and twice shifted).  The reference clamps y (shiftedIndBallL0BInf.jl:91) AFTER the
+    # top-r mask, so a dropped entry with |xk + sj| > Δ ends non-zero and the value can be Inf at the operator's own
+    # prox output -- whatever it is, both sides must agree; want_value returns the same number
+    psi1 = sp.shifted(sp.IndBallL0(r), T(xk), delta, sp.NormLinf(1.0))
+    y1 = N(sp.prox(psi1, T(q), 1.0)).copy()
+    z = np.zeros(n, dt)
+    assert psi1(T(y1)) == orc.value_binf("indballl0", xk, z, y1, delta, r=r)
+    yy = torch.empty(n, dtype=T(q).dtype, device=DEV)
+    _, val = sp.prox_(yy, psi1, T(q), 1.0, want_value=True)
+    assert val == orc.value_binf("indballl0", xk, z, N(yy), delta, r=r)
     y = N(sp.prox(psi, T(q), 1.0)).copy()
-    assert orc.value_binf("indballl0", xk, sj, y, delta, r=r) == 0.0
-    assert psi(T(y)) == 0.0
-    # (2) one more non-zero than r -> Inf; exactly r -> 0 (count <= r)
-    v = (xk + sj) + y
-    dropped = np.flatnonzero(v == 0)
-    if dropped.size:
-        y2 = y.copy()
-        y2[dropped[0]] += dt(1e-3)
-        want = orc.value_binf("indballl0", xk, sj, y2, delta, r=r)
-        assert want == np.inf and psi(T(y2)) == np.inf
+    assert psi(T(y)) == orc.value_binf("indballl0", xk, sj, y, delta, r=r)
+    # with |xk| <= 0.3 Δ nothing is clamped: exactly min(r, n) non-zeros, inside the ball -> 0
+    xs_ = (xk * dt(0.1)).astype(dt)
+    psi2 = sp.shifted(sp.IndBallL0(r), T(xs_), delta, sp.NormLinf(1.0))
+    qs_ = (q * dt(0.1)).astype(dt)
+    y2 = N(sp.prox(psi2, T(qs_), 1.0)).copy()
+    assert orc.value_binf("indballl0", xs_, z, y2, delta, r=r) == 0.0 == psi2(T(y2))
+    # (2) feasible point (sj + y inside the ball; xk scaled so that the entries with v_i = 0, where w_i = -xk_i, are
+    # inside as well): count <= r -> 0, r one short of the count -> Inf
+    xk = (xk * dt(0.15)).astype(dt)
+    keep = np.zeros(n, bool); keep[:: n // r + 1] = True  # at most r entries of v = xk + w stay non-zero
+    sj = np.where(keep, sj, dt(0)).astype(dt)             # elsewhere sj = 0, y = -xk: w = -xk and v = 0 exactly
+    psi = sp.shifted(sp.shifted(sp.IndBallL0(r), T(xk), delta, sp.NormLinf(1.0)), T(sj))
+    w = (dt(delta) * orc.uniform(n, 21, dt, 2.0, -1.0)).astype(dt)
+    y = np.where(keep, w - sj, -xk).astype(dt)
+    ynz = np.count_nonzero((sj + y) + xk)
+    assert 0 < ynz <= r and np.all(np.abs((sj + y).astype(np.float64)) <= 1.1 * float(dt(delta)))
+    assert orc.value_binf("indballl0", xk, sj, y, delta, r=r) == 0.0 == psi(T(y))
+    assert orc.value_binf("indballl0", xk, sj, y, delta, r=ynz) == 0.0
+    psi_eq = sp.shifted(sp.shifted(sp.IndBallL0(ynz), T(xk), delta, sp.NormLinf(1.0)), T(sj))
+    assert psi_eq(T(y)) == 0.0  # count == r
+    if ynz > 1:
+        psi_tight = sp.shifted(sp.shifted(sp.IndBallL0(ynz - 1), T(xk), delta, sp.NormLinf(1.0)), T(sj))
+        assert orc.value_binf("indballl0", xk, sj, y, delta, r=ynz - 1) == np.inf == psi_tight(T(y))
     # (3) the edge of the ball: w = sj + y on either side of the Float64 radius 1.1Δ (strict test, Float64 compare)
     rad = 1.1 * float(dt(delta))
     inside = np.nextafter(dt(rad), dt(0)) if float(dt(rad)) > rad else dt(rad)  # largest R value <= rad
@@ -757,10 +780,6 @@ def test_indballl0binf_value_against_oracle(dt, n):
     # (4) far outside
     y4 = y.copy(); y4[n // 2] += dt(10.0)
     assert psi(T(y4)) == np.inf == orc.value_binf("indballl0", xk, sj, y4, delta, r=r)
-    # want_value of the prox
-    yy = torch.empty(n, dtype=T(q).dtype, device=DEV)
-    _, val = sp.prox_(yy, psi, T(q), 1.0, want_value=True)
-    assert val == 0.0
 
 
 @pytest.mark.parametrize("dt", DT)
@@ -808,3 +827,77 @@ def test_groupl2binf_value_against_oracle(dt, layout):
     _, val = sp.prox_(yy, psi, T(q), sigma, want_value=True)
     want = orc.value_binf("groupl2", xk, sj, N(yy), delta, offs=offs, lam_g=lam_g)
     assert np.isfinite(want) and val == pytest.approx(want, rel=rtol)
+
+
+# ------------------------------------- uniform layouts: the fast path of GroupNormL2Binf ---
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("m", [16, 32, 64, 128, 256])
+@pytest.mark.parametrize("regime", ["base", "mid_lambda", "big_lambda", "tiny_delta", "huge_delta", "tiny_shift", "zeroed"])
+def test_group_l2binf_uniform_layout(dt, m, regime):
+    """n == ngroups * m with m = 8 L: spx_prox_groupl2binf_* takes the uniform-layout kernels (Float32 search, one
+    Float64 evaluation + Halley step, the final pass as the acceptance test; failing rounds redone by the bracketing
+    search).  ngroups is not a multiple of 32/L: the last round is partial."""
+    ng = 1203
+    n = ng * m
+    offs = np.arange(0, n + 1, m)
+    xk, sj, q = inputs(n, dt)
+    lam_g = (dt(0.5) + orc.uniform(ng, 12, dt)).astype(dt)
+    sigma, delta = 0.3, 0.5
+    floor = 1.0
+    if regime == "mid_lambda":
+        lam_g = (lam_g * dt(20)).astype(dt)
+    elif regime == "big_lambda":
+        lam_g = (lam_g * dt(200)).astype(dt)
+    elif regime == "tiny_delta":
+        delta = 1e-4
+    elif regime == "huge_delta":
+        delta = 50.0
+    elif regime == "tiny_shift":
+        xk = (xk * dt(1e-3)).astype(dt); sj = (sj * dt(1e-3)).astype(dt); q = (q * dt(1e-3)).astype(dt)
+        lam_g = (lam_g * dt(5)).astype(dt)
+        floor = 1e-3
+    elif regime == "zeroed":  # σλ_g > ||sol_g|| and |xk| <= Δ on half of the groups: fl*fm > 0 -> y_g = 0
+        half = np.repeat(np.arange(ng) % 2 == 0, m)
+        xk = np.where(half, xk * dt(0.2), xk).astype(dt)
+        q = np.where(half, q * dt(0.05), q).astype(dt)
+        sj = np.where(half, sj * dt(0.05), sj).astype(dt)
+        lam_g = np.where(np.arange(ng) % 2 == 0, lam_g * dt(40), lam_g).astype(dt)
+    h = sp.GroupNormL2(T(lam_g), None, offsets=T(offs))
+    psi = sp.shifted(sp.shifted(h, T(xk), delta, sp.NormLinf(1.0)), T(sj))
+    y = torch.empty(n, dtype=T(q).dtype, device=DEV)
+    sp.prox_(y, psi, T(q), sigma)
+    check_groupl2binf(N(y), xk, sj, q, offs, lam_g, sigma, delta, label=f"uniform m={m} {dt.__name__} {regime}", floor=floor)
+
+
+@pytest.mark.parametrize("dt", DT)
+def test_group_l2binf_uniform_candidates_that_are_not_uniform(dt):
+    """n == ngroups * 64 but the groups are NOT all of 64 elements (the device-side check of offs must send the call
+    to the generic kernels), and a uniform layout at a 16-byte-misaligned base (host-side test, generic kernels)."""
+    m, ng = 64, 500
+    sizes = np.full(ng, m)
+    sizes[10] -= 3; sizes[11] += 3; sizes[300] += 20; sizes[301] -= 20
+    offs = np.concatenate([[0], np.cumsum(sizes)])
+    n = int(offs[-1])
+    assert n == ng * m
+    xk, sj, q = inputs(n, dt)
+    lam_g = (dt(0.5) + orc.uniform(ng, 12, dt)).astype(dt)
+    sigma, delta = 0.3, 0.5
+    h = sp.GroupNormL2(T(lam_g), None, offsets=T(offs))
+    psi = sp.shifted(sp.shifted(h, T(xk), delta, sp.NormLinf(1.0)), T(sj))
+    y = torch.empty(n, dtype=T(q).dtype, device=DEV)
+    sp.prox_(y, psi, T(q), sigma)
+    check_groupl2binf(N(y), xk, sj, q, offs, lam_g, sigma, delta, label=f"almost uniform {dt.__name__}")
+    # misaligned base: every vector starts one element into its allocation
+    offs = np.arange(0, n + 1, m)
+    pad = lambda a: T(np.concatenate([[0], a]).astype(dt))[1:]  # noqa: E731
+    txk, tsj, tq = pad(xk), pad(sj), pad(q)
+    ybuf = torch.empty(n + 1, dtype=tq.dtype, device=DEV)[1:]
+    h = sp.GroupNormL2(T(lam_g), None, offsets=T(offs))
+    psi = sp.shifted(sp.shifted(h, txk, delta, sp.NormLinf(1.0)), tsj)
+    sp.prox_(ybuf, psi, tq, sigma)
+    check_groupl2binf(N(ybuf), xk, sj, q, offs, lam_g, sigma, delta, label=f"uniform misaligned {dt.__name__}")
+    # y aliases q (test/test_allocs.jl:108 calls prox!(y, ψ, y, σ))
+    psi = sp.shifted(sp.shifted(h, T(xk), delta, sp.NormLinf(1.0)), T(sj))
+    yq = T(q).clone()
+    sp.prox_(yq, psi, yq, sigma)
+    check_groupl2binf(N(yq), xk, sj, q, offs, lam_g, sigma, delta, label=f"uniform aliased {dt.__name__}")
