@@ -99,6 +99,29 @@ int32_t spx_ctx_sm_count(spx_ctx* ctx, int32_t* out);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 int32_t spx_ctx_launch_count(spx_ctx* ctx, int64_t* out);
 
+/* ------------------------------------------- multi-GPU (one process per GPU) ---
+ * The reference is single-process; SURVEY.md §8e shards a vector (or a batch) contiguously over the GPUs of a box.
+ * The path's only exchanges are scalars -- ψ(y) partial sums + infeasibility flag
+ * (ShiftedProximalOperators.jl:51-54 and the Box / BInf overrides), the partial sums of every pass of the ℓ2
+ * trust-region search (shiftedNormL1B2.jl:53-62), the fused step's three scalars -- and the digit histograms of a
+ * single-vector top-r (shiftedIndBallL0.jl:66-70).  With a communicator attached to the context they are
+ * all-reduced ON THE DEVICE (ncclAllReduce over NVLink on the context's stream, directly on the folded slots, sum
+ * for Σ and max for the flag so `Inf` survives) before the one D2H copy of the call.  NCCL is bound at run time
+ * (dlopen); rank 0 creates the id, the host passes its 128 bytes to the other ranks by any means. */
+#define SPX_COMM_ID_BYTES 128
+int32_t spx_comm_available(void);              /* 1 if libnccl.so.2 could be bound */
+int32_t spx_comm_unique_id(void* id_out128);   /* ncclGetUniqueId */
+int32_t spx_comm_init(spx_ctx* ctx, int32_t nranks, int32_t rank, const void* id128);
+int32_t spx_comm_destroy(spx_ctx* ctx);
+/* on != 0: every scalar a call hands back (psi_out, *_out of the value entry points, out3_host of the fused step,
+ * the decisions of spx_prox_l1b2_*) is the value over ALL shards, identical on every rank; every rank must then
+ * make the same calls in the same order.  on == 0: per-shard values (the default). */
+int32_t spx_comm_reduce_scalars(spx_ctx* ctx, int32_t on);
+int32_t spx_comm_info(spx_ctx* ctx, int32_t* nranks_out, int32_t* rank_out, int64_t* collectives_out);
+/* building block: in-place all-reduce of `count` doubles in device memory, enqueued on the context's stream
+ * (op 0 = sum, 1 = max); a context without communicator leaves the buffer as is */
+int32_t spx_comm_allreduce_f64(spx_ctx* ctx, double* dev_buf, int64_t count, int32_t op);
+
 /* ----------------------------------------- device buffers (Julia owns) --- */
 /* replaces `similar(xk)` / `zero(xk)` in the constructors, e.g. shiftedNormL1.jl:16-29 */
 int32_t spx_malloc(spx_ctx* ctx, size_t bytes, void** out);

@@ -67,6 +67,12 @@ struct spx_ctx {
   size_t pipe_bytes = 0;
   cudaEvent_t pipe_events[16] = {};
   long long launches = 0;
+  // multi-GPU (spx_comm.cu): an NCCL communicator bound to this context's device and stream
+  void* comm = nullptr;  // ncclComm_t
+  int comm_nranks = 1, comm_rank = 0;
+  bool reduce_scalars = false;  // every folded reduction is all-reduced on the device before it reaches the host
+  double* d_comm = nullptr;     // packed scalars of a multi-slot reduction
+  long long collectives = 0;
 };
 
 namespace spx {
@@ -252,6 +258,11 @@ int32_t make_sel(const spx_sel* s, int64_t n, DevSel* out);
 // fold `nblocks` partials (slot stride `stride`, `nslot` independent slots) into
 // ctx->d_result[slot], copy to the pinned mirror, synchronise
 int32_t finalize_partials(spx_ctx* ctx, int nblocks, int nslot, bool bad_is_min);
+// spx_comm.cu: is the context in "scalars are global" mode; all-reduce ctx->d_result[0..nslot) on ctx->stream
+bool comm_active(const spx_ctx* ctx);
+int32_t comm_neutral_result(spx_ctx* ctx, int nslot);
+int32_t comm_allreduce_result(spx_ctx* ctx, int nslot);
+int32_t comm_allreduce_raw(spx_ctx* ctx, void* buf, size_t count, int nccl_dtype, int nccl_op);
 // enqueue only: fold `nblocks` partials at `partials` into *result on `stream`
 int32_t enqueue_fold(spx_ctx* ctx, cudaStream_t stream, const Partial* partials, int nblocks, Partial* result);
 

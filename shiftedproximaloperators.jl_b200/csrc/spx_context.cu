@@ -93,7 +93,8 @@ int32_t enqueue_fold(spx_ctx* ctx, cudaStream_t stream, const Partial* partials,
 }
 
 int32_t finalize_partials(spx_ctx* ctx, int nblocks, int nslot, bool) {
-  if (nblocks <= 0) {
+  const bool global = comm_active(ctx);  // sharded vector: the folded slots are all-reduced on the device
+  if (nblocks <= 0 && !global) {
     for (int k = 0; k < nslot; ++k) {
       ctx->h_result[k].s = 0.0;
       ctx->h_result[k].s2 = 0.0;
@@ -101,9 +102,18 @@ int32_t finalize_partials(spx_ctx* ctx, int nblocks, int nslot, bool) {
     }
     return SPX_OK;
   }
-  fold_kernel<<<nslot, 256, 0, ctx->stream>>>(ctx->d_partials, nblocks, ctx->d_result);
-  ctx->launches++;
-  SPX_CUDA(cudaGetLastError());
+  if (nblocks > 0) {
+    fold_kernel<<<nslot, 256, 0, ctx->stream>>>(ctx->d_partials, nblocks, ctx->d_result);
+    ctx->launches++;
+    SPX_CUDA(cudaGetLastError());
+  } else {  // an empty shard still takes part in the collective
+    int32_t st = comm_neutral_result(ctx, nslot);
+    if (st != SPX_OK) return st;
+  }
+  if (global) {
+    int32_t st = comm_allreduce_result(ctx, nslot);
+    if (st != SPX_OK) return st;
+  }
   SPX_CUDA(cudaMemcpyAsync(ctx->h_result, ctx->d_result, sizeof(Partial) * nslot, cudaMemcpyDeviceToHost,
                            ctx->stream));
   SPX_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -286,6 +296,8 @@ int32_t spx_ctx_destroy(spx_ctx* c) {
     if (c->pipe_events[i]) cudaEventDestroy(c->pipe_events[i]);
   if (c->pipe_buf) cudaFree(c->pipe_buf);
   if (c->d_scratch) cudaFree(c->d_scratch);
+  spx_comm_destroy(c);
+  if (c->d_comm) cudaFree(c->d_comm);
   cudaFree(c->d_partials);
   cudaFree(c->d_result);
   cudaFreeHost(c->h_result);

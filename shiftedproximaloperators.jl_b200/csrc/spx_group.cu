@@ -795,18 +795,46 @@ template <class R> struct UVec {
 };
 constexpr int kRoundElems = 32 * kEPL;  // 256 consecutive elements per warp round
 
+// Each warp owns a private slice of shared memory -- planes q | xk | sj (even rounds) | sj (odd rounds), one round
+// (256 elements) each -- that it fills with 16-byte cp.async copies one round AHEAD: while a round is being solved
+// the next one is in flight, so the warp never waits on HBM between rounds (with three resident CTAs of eight
+// warps, 144 KB per SM are in flight or staged).  A lane reads back exactly the 16-byte slots it copied itself:
+// cp.async.wait_group is the only synchronisation.  sj has two planes because the current round still needs it
+// for the store (y = ... - (xk + sj)) after the next round's copies have been issued.
 template <class R, int L> struct UTile {
   R sol[kEPL], xkr[kEPL];
   int L_rt;  // == L (TileView reads a run-time width)
   bool valid;
   long long base;  // element index of the lane's first packet
   static constexpr int VEC = UVec<R>::VEC, NCH = UVec<R>::NCH;
-  __device__ __forceinline__ void load(long long round, long long ngroups, int lane, const R* xk, const R* sj,
-                                       const R* q) {
-    constexpr int GPW = 32 / L;
-    const int gl = lane / L, sub = lane % L;
-    valid = round * GPW + gl < ngroups;
-    base = round * kRoundElems + (long long)gl * (kEPL * L) + sub * VEC;
+  static constexpr uint32_t kPlane = kRoundElems * sizeof(R);  // bytes of one plane of one warp
+  static constexpr uint32_t kWarpBytes = 4 * kPlane;
+  static __device__ __forceinline__ bool lane_valid(long long round, long long ngroups, int lane) {
+    return round * (32 / L) + lane / L < ngroups;
+  }
+  static __device__ __forceinline__ long long lane_base(long long round, int lane) {
+    return round * kRoundElems + (long long)(lane / L) * (kEPL * L) + (lane % L) * VEC;
+  }
+  // enqueue the copies of `round` (every lane commits a group, possibly empty)
+  static __device__ __forceinline__ void prefetch(long long round, long long ngroups, int lane, const R* xk, const R* sj,
+                                                  const R* q, uint32_t sbase, int sjbuf) {
+    if (lane_valid(round, ngroups, lane)) {
+      const long long b = lane_base(round, lane);
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        const uint32_t slot = sbase + (uint32_t)(c * 32 + lane) * 16u;
+        cp_async16(slot, q + b + c * (L * VEC));
+        cp_async16(slot + kPlane, xk + b + c * (L * VEC));
+        cp_async16(slot + (2u + (uint32_t)sjbuf) * kPlane, sj + b + c * (L * VEC));
+      }
+    }
+    cp_async_commit();
+  }
+  // the round whose copies were enqueued last
+  __device__ __forceinline__ void take(long long round, long long ngroups, int lane, uint32_t sbase, int sjbuf) {
+    cp_async_wait<0>();
+    valid = lane_valid(round, ngroups, lane);
+    base = lane_base(round, lane);
     L_rt = L;
     Pack<R, VEC> pq[NCH], px[NCH], ps[NCH];
 #pragma unroll
@@ -814,9 +842,10 @@ template <class R, int L> struct UTile {
 #pragma unroll
       for (int e = 0; e < VEC; ++e) pq[c].v[e] = px[c].v[e] = ps[c].v[e] = R(0);
       if (valid) {
-        ld_stream(q + base + c * (L * VEC), pq[c]);
-        ld_stream(xk + base + c * (L * VEC), px[c]);
-        ld_stream(sj + base + c * (L * VEC), ps[c]);
+        const uint32_t slot = sbase + (uint32_t)(c * 32 + lane) * 16u;
+        lds16(slot, pq[c]);
+        lds16(slot + kPlane, px[c]);
+        lds16(slot + (2u + (uint32_t)sjbuf) * kPlane, ps[c]);
       }
     }
 #pragma unroll
@@ -867,29 +896,36 @@ __device__ __forceinline__ float abs_t(float a) { return fabsf(a); }
 __device__ __forceinline__ double abs_t(double a) { return fabs(a); }
 __device__ __forceinline__ float cps_t(float a, float b) { return copysignf(a, b); }
 __device__ __forceinline__ double cps_t(double a, double b) { return copysign(a, b); }
+// accA += z² where the threshold keeps the entry (a > 0), accB += so² elsewhere: ONE predicated FMA each way (written
+// in PTX: the compiler turns the C form into two FMAs and two selects).  A NaN excess counts as "not kept": it then
+// poisons B through so or, for a finite so, is caught by the magnitude guards of the caller.
+__device__ __forceinline__ void acc_pred(float a, float z, float so, float& accA, float& accB) {
+  asm("{\n\t.reg .pred p;\n\tsetp.gt.f32 p, %2, 0f00000000;\n\t@p fma.rn.f32 %0, %3, %3, %0;\n\t@!p fma.rn.f32 %1, %4, %4, %1;\n\t}"
+      : "+f"(accA), "+f"(accB)
+      : "f"(a), "f"(z), "f"(so));
+}
+__device__ __forceinline__ void acc_pred(double a, double z, double so, double& accA, double& accB) {
+  asm("{\n\t.reg .pred p;\n\tsetp.gt.f64 p, %2, 0d0000000000000000;\n\t@p fma.rn.f64 %0, %3, %3, %0;\n\t@!p fma.rn.f64 %1, %4, %4, %1;\n\t}"
+      : "+d"(accA), "+d"(accB)
+      : "d"(a), "d"(z), "d"(so));
+}
+__device__ __forceinline__ void acc_pred(float a, float z, float so, double& accA, double& accB) {
+  acc_pred((double)a, (double)z, (double)so, accA, accB);
+}
+template <class T, class ACC>
+__device__ __forceinline__ void binf_term(T so, T xg, T tau, T sdc, ACC& accA, ACC& accB) {
+  const T t = fma_t(-tau, xg, so);
+  const T a = abs_t(t) - sdc;
+  const T z = cps_t(a, t) - so;
+  acc_pred(a, z, so, accA, accB);
+}
 template <class T, class ACC, int L>
 __device__ __forceinline__ void binf_eval(const T (&so)[kEPL], const T (&xg)[kEPL], T tau, T sdc, ACC& ssA, ACC& ssB) {
   ACC a0 = 0, a1 = 0, b0 = 0, b1 = 0;
 #pragma unroll
   for (int j = 0; j < kEPL; j += 2) {
-    {
-      const T t = fma_t(-tau, xg[j], so[j]);
-      const T a = abs_t(t) - sdc;
-      const T z = cps_t(a, t) - so[j];
-      const bool act = a > T(0);
-      const ACC u = (ACC)(act ? z : T(0)), v = (ACC)(act ? T(0) : so[j]);
-      a0 = fma_t(u, u, a0);
-      b0 = fma_t(v, v, b0);
-    }
-    {
-      const T t = fma_t(-tau, xg[j + 1], so[j + 1]);
-      const T a = abs_t(t) - sdc;
-      const T z = cps_t(a, t) - so[j + 1];
-      const bool act = a > T(0);
-      const ACC u = (ACC)(act ? z : T(0)), v = (ACC)(act ? T(0) : so[j + 1]);
-      a1 = fma_t(u, u, a1);
-      b1 = fma_t(v, v, b1);
-    }
+    binf_term<T, ACC>(so[j], xg[j], tau, sdc, a0, b0);
+    binf_term<T, ACC>(so[j + 1], xg[j + 1], tau, sdc, a1, b1);
   }
   ssA = a0 + a1;
   ssB = b0 + b1;
@@ -910,6 +946,17 @@ __device__ __forceinline__ double rcp_d(double x) {
   e = __fma_rn(-x, y, 1.0);
   return __fma_rn(y, e, y);
 }
+
+// sol/σ for a warp-uniform σ without the out-of-range branch of div_uniform (callers guarantee normal operands;
+// a zero numerator yields a zero of either sign, which the soft threshold maps to the same result)
+__device__ __forceinline__ double quot_uniform(double a, const UDiv<double>& d) {
+  const double q0 = a * d.y;
+  const double r0 = __fma_rn(-d.s, q0, a);
+  const double q1 = __fma_rn(r0, d.y, q0);
+  const double r1 = __fma_rn(-d.s, q1, a);
+  return __fma_rn(r1, d.y, q1);
+}
+__device__ __forceinline__ float quot_uniform(float a, const UDiv<float>& d) { return a / d.s; }
 
 template <class R> struct LoCopy;
 template <> struct LoCopy<double> {
@@ -937,7 +984,7 @@ __device__ __forceinline__ bool binf_fast_search(const float (&so)[kEPL], const 
   const float slf = (float)sl, delf = (float)delta, lminf = (float)lmin;
   // ---- A: the three norms of :97-100 at τa = σ step(ansatz)
   const float tau_a = (float)sigma * (float)step_a;
-  float z2 = 0.f, s2 = 0.f, x2 = 0.f;
+  float z2 = 0.f, s2 = 0.f, x2 = 0.f, xmax = 0.f;
   {
     const float sdc = tau_a * delf;
 #pragma unroll
@@ -947,23 +994,33 @@ __device__ __forceinline__ bool binf_fast_search(const float (&so)[kEPL], const 
       z2 = fmaf(a, a, z2);
       s2 = fmaf(so[j], so[j], s2);
       x2 = fmaf(xg[j], xg[j], x2);
+      xmax = fmaxf(xmax, fabsf(xg[j]));
     }
     usum2<L>(z2, s2);
     x2 = usum<L>(x2);
+#pragma unroll
+    for (int o = L >> 1; o > 0; o >>= 1) xmax = fmaxf(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
   }
-  const float lmaxf = sqrt_approx(s2) + sqrt_approx(z2) + slf * sqrt_approx(x2);
+  const float nsolf = sqrt_approx(s2);
+  const float lmaxf = nsolf + sqrt_approx(z2) + slf * sqrt_approx(x2);
   // magnitudes the Float32 search is trusted with (squares neither overflow nor flush; NaN fails every test)
   bool ok = (s2 > 1e-16f && s2 < 1e24f) && (x2 < 1e24f) && (z2 < 1e30f) && (delf < 1e12f) && (slf > 1e-12f && slf < 1e12f) &&
             (lmaxf > lminf * 1.001f);
-  // ---- froot(lmin): τ = (1 + eps)/eps whatever σλ is
-  float fl;
-  {
-    const float tau_l = (float)((R(1) + epsR) / epsR);
+  // ---- froot(lmin): τ = (1 + eps)/eps whatever σλ is.  An entry with |xk_i| clearly above Δ is thresholded there
+  // and contributes τ (|xk_i| - Δ) -- orders of magnitude above lmin: froot(lmin) < 0 without evaluating it.
+  const float tau_l = (float)((R(1) + epsR) / epsR);
+  const float excess = xmax - delf;
+  const bool fl_neg = (excess > 1e-4f * (xmax + delf)) && (excess * tau_l > 1e4f * (lminf + nsolf));
+  float fl = -1.f;
+  if (__any_sync(0xffffffffu, valid && ok && !fl_neg)) {
     float ssA, ssB;
     binf_eval<float, float, L>(so, xg, tau_l, tau_l * delf, ssA, ssB);
     const float nw = sqrt_approx(ssA + ssB);
-    fl = lminf - nw;
-    ok = ok && (fabsf(fl) > 1e-4f * fmaxf(lminf, nw));
+    const float fle = lminf - nw;
+    if (!fl_neg) {
+      fl = fle;
+      ok = ok && (fabsf(fl) > 1e-4f * fmaxf(lminf, nw));
+    }
   }
   // ---- froot(lmax), then Newton on h(n) = (n - σλ) froot(n) / n
   float x = lmaxf, a_ = lminf, b_ = lmaxf;
@@ -1038,7 +1095,7 @@ __device__ __forceinline__ bool binf_fast_search_entry(const UTile<float, L>& t,
 }
 
 #ifndef SPX_GU_MINB
-#define SPX_GU_MINB 2
+#define SPX_GU_MINB 3
 #endif
 // FAST: rounds grid-stride, failures appended to the work list.  !FAST: the listed rounds, bracketing search.
 template <class R, int L, bool FAST>
@@ -1053,10 +1110,18 @@ __global__ void __launch_bounds__(kGroupThreads, FAST ? SPX_GU_MINB : 2)
   const long long warp = ((long long)blockIdx.x * kGroupThreads + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * kGroupThreads) >> 5;
   const long long nrounds = FAST ? (ngroups + GPW - 1) / GPW : (long long)*wl_count;
-  for (long long it = warp; it < nrounds; it += nwarps) {
-    const long long round = FAST ? it : (long long)wl_rounds[it];
+  extern __shared__ __align__(16) unsigned char uni_smem[];
+  const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(uni_smem) + (uint32_t)(threadIdx.x >> 5) * UTile<R, L>::kWarpBytes;
+  auto round_of = [&](long long i) -> long long { return FAST ? i : (long long)wl_rounds[i]; };
+  int sjbuf = 0;
+  if (warp < nrounds) UTile<R, L>::prefetch(round_of(warp), ngroups, lane, xk, sj, q, sbase, 0);
+  for (long long it = warp; it < nrounds; it += nwarps, sjbuf ^= 1) {
+    const long long round = round_of(it);
     UTile<R, L> t;
-    t.load(round, ngroups, lane, xk, sj, q);
+    t.take(round, ngroups, lane, sbase, sjbuf);
+    // the next round's copies go out now and land while this one is solved (q and xk planes are free again: their
+    // contents sit in registers; sj goes to the other sj plane)
+    if (it + nwarps < nrounds) UTile<R, L>::prefetch(round_of(it + nwarps), ngroups, lane, xk, sj, q, sbase, sjbuf ^ 1);
     const R lam = t.valid ? lambda_g[round * GPW + lane / L] : R(1);
     const R sl = lam * sigma;
     R nroot = R(0), step = R(0);
@@ -1075,17 +1140,21 @@ __global__ void __launch_bounds__(kGroupThreads, FAST ? SPX_GU_MINB : 2)
     }
     // ---- C: y_g = l2prox(sol - σ softthres(sol/σ - step xk, Δ step), σλ) - (xk + sj)   (:109-116)
     R w[kEPL];
-    if (FAST) step = nroot / (sigma * (nroot - sl));  // c(n)  (:85)
+    // the fast rounds hold magnitudes far inside the normal range (guards of binf_fast_search): their scalar
+    // quotients take the branch-free ~1 ulp division, their sol/σ the correctly rounded quotient without its
+    // out-of-range test
+    if (FAST) step = div_fast(nroot, sigma * (nroot - sl));  // c(n)  (:85)
     const R dstep2 = delta * step;
     double ss = 0.0;
 #pragma unroll
     for (int j = 0; j < kEPL; ++j) {
-      w[j] = t.sol[j] - sigma * softthres_sel(by_sigma(t.sol[j]) - step * t.xkr[j], dstep2);
+      const R u = FAST ? quot_uniform(t.sol[j], by_sigma) : by_sigma(t.sol[j]);
+      w[j] = t.sol[j] - sigma * softthres_sel(u - step * t.xkr[j], dstep2);
       ss = __fma_rn((double)w[j], (double)w[j], ss);
     }
     ss = usum<L>(ss);
     const R nv = (R)sqrt_fast(ss);
-    const R alpha = zero_out ? R(0) : jl_max(R(0), R(1) - sl / nv);
+    const R alpha = zero_out ? R(0) : jl_max(R(0), R(1) - (FAST ? div_fast(sl, nv) : sl / nv));
     if (FAST) {
       // froot(nroot) = nroot - ||v|| in the reference's arithmetic: the acceptance test of the fast search
       const R res = nroot - nv;
@@ -1102,7 +1171,7 @@ __global__ void __launch_bounds__(kGroupThreads, FAST ? SPX_GU_MINB : 2)
 #pragma unroll
       for (int c = 0; c < NCH; ++c) {
         Pack<R, VEC> ps, po;
-        ld_stream(sj + t.base + c * (L * VEC), ps);  // an L2 hit: read a moment ago by this warp
+        lds16(sbase + (2u + (uint32_t)sjbuf) * UTile<R, L>::kPlane + (uint32_t)(c * 32 + lane) * 16u, ps);
 #pragma unroll
         for (int e = 0; e < VEC; ++e) {
           const int j = c * VEC + e;
@@ -1408,17 +1477,20 @@ static void launch_uniform_binf_L(spx_ctx* ctx, R* y, const R* xk, const R* sj, 
                                   unsigned* wl_count, unsigned* wl_rounds) {
   const long long nrounds = (ngroups + (32 / L) - 1) / (32 / L);
   const long long want = (nrounds + (kGroupThreads / 32) - 1) / (kGroupThreads / 32);
-  auto grid_of = [&](const void* k) {
+  auto grid_of = [&](const void* k, size_t smem_bytes) {
     int per_sm = 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kGroupThreads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kGroupThreads, smem_bytes) != cudaSuccess || per_sm < 1) per_sm = 1;
     const long long cap = (long long)ctx->sm_count * per_sm;
     return (int)std::max<long long>(1, std::min(want, cap));
   };
+  const size_t smem = (size_t)(kGroupThreads / 32) * UTile<R, L>::kWarpBytes;
+  cudaFuncSetAttribute((const void*)group_l2binf_uniform_kernel<R, L, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute((const void*)group_l2binf_uniform_kernel<R, L, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   group_l2binf_uniform_kernel<R, L, true>
-      <<<grid_of((const void*)group_l2binf_uniform_kernel<R, L, true>), kGroupThreads, 0, ctx->stream>>>(
+      <<<grid_of((const void*)group_l2binf_uniform_kernel<R, L, true>, smem), kGroupThreads, smem, ctx->stream>>>(
           y, xk, sj, q, ngroups, lambda_g, sigma, delta, by_sigma, uniform_flag, wl_count, wl_rounds);
   group_l2binf_uniform_kernel<R, L, false>
-      <<<grid_of((const void*)group_l2binf_uniform_kernel<R, L, false>), kGroupThreads, 0, ctx->stream>>>(
+      <<<grid_of((const void*)group_l2binf_uniform_kernel<R, L, false>, smem), kGroupThreads, smem, ctx->stream>>>(
           y, xk, sj, q, ngroups, lambda_g, sigma, delta, by_sigma, uniform_flag, wl_count, wl_rounds);
 }
 template <class R>

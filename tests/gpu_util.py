@@ -127,9 +127,11 @@ def check_groupl2binf(got, xk, sj, q, offs, lam_g, sigma, delta, label="", floor
       any other summation order moves that sign change by a few ulps of the root n*.  y depends on n* through
       c(n) = n/(σ(n-σλ)):  δy_i = κ_g (|xk_i| + Δ + |v_i|) δn/n with κ_g = σλ_g/(n*-σλ_g) the conditioning of the
       group (SURVEY.md §8c "ill-conditioned groups": κ -> ∞ as the root approaches the pole of c at σλ).  Bound:
-          |y_gpu - y_orc|_i <= eps(R) [ 64 scale_i + 16 κ_g (scale_i + n*_g) ]
-      i.e. 64 ulp of the value scale plus 16 ulps of root displacement through the conditioning term; and the
-      99.9th percentile of the error over well-conditioned groups (κ_g <= 1) must be <= 64 eps·scale outright."""
+          |y_gpu - y_orc|_i <= eps(R) [ 8 scale_i + 2 κ_g (scale_i + n*_g) ]
+      i.e. 8 ulp of the value scale plus 2 ulps of root displacement through the conditioning term; and the
+      99.9th percentile of the error over well-conditioned groups (κ_g <= 1) must be <= 4 eps·scale outright.
+      Measured (profiles/r02_parity_stats.jsonl): max 1.6 eps·scale on C4, 99.9th percentile <= 1 for κ <= 1, and
+      never more than 25 % of this bound in any regime, the ill-conditioned ones (κ up to 65) included."""
     dt = q.dtype.type
     n = q.size
     offs = np.asarray(offs, np.int64)
@@ -144,7 +146,7 @@ def check_groupl2binf(got, xk, sj, q, offs, lam_g, sigma, delta, label="", floor
     kappa = np.nan_to_num(kappa, nan=0.0, posinf=1e300)
     nr = np.nan_to_num(np.where(zeroed, 0.0, nroot), nan=0.0, posinf=0.0)
     err = np.abs(got.astype(np.float64) - ref.astype(np.float64))
-    tol = eps * (64.0 * scale + 16.0 * kappa[gid] * (scale + nr[gid]))
+    tol = eps * (8.0 * scale + 2.0 * kappa[gid] * (scale + nr[gid]))
     zero_pat = np.zeros(n, dt) - (xk + sj)
     zr, zg = ref == zero_pat, got == zero_pat
     assert np.array_equal(zr, zg), (label, "support differs", np.flatnonzero(zr != zg)[:5])
@@ -153,7 +155,7 @@ def check_groupl2binf(got, xk, sj, q, offs, lam_g, sigma, delta, label="", floor
     rel = err / (eps * scale)
     well = kappa[gid] <= 1.0
     p999 = float(np.percentile(rel[well], 99.9)) if well.any() else 0.0
-    assert p999 <= 64.0, (label, "99.9th percentile of the error over well-conditioned groups", p999)
+    assert p999 <= 4.0, (label, "99.9th percentile of the error over well-conditioned groups", p999)
     log_stat("groupl2binf_ulp", label=label, dtype=np.dtype(dt).name, n=int(n), groups=int(sizes.size),
              err_over_eps_scale={"p50": float(np.percentile(rel, 50)), "p99": float(np.percentile(rel, 99)),
                                  "p99.9": float(np.percentile(rel, 99.9)), "max": float(rel.max())},

@@ -184,7 +184,7 @@ def test_c4_group_l2_and_binf_10m_groups_of_64():
         scale = np.abs(hxk) + np.abs(hsj) + np.abs(hq) + 1
         ref = orc.prox_groupl2(hxk, hsj, hq, ho, hlam, sigma)
         assert np.all(np.abs(N(y[i0:i0 + m]) - ref) <= 8 * np.finfo(np.float64).eps * scale)
-        # support identical, 64 ulp of the value scale + the conditioning term (gpu_util.check_groupl2binf)
+        # support identical, 8 ulp of the value scale + the conditioning term (gpu_util.check_groupl2binf)
         check_groupl2binf(N(yb[i0:i0 + m]), hxk, hsj, hq, ho, hlam, sigma, delta, label=f"C4 window at group {g0}")
 
 

@@ -496,8 +496,8 @@ def test_group_l2binf_against_oracle(dt, layout):
     psi = sp.shifted(sp.shifted(h, T(xk), delta, sp.NormLinf(1.0)), T(sj))
     y = torch.empty(n, dtype=T(q).dtype, device=DEV)
     sp.prox_(y, psi, T(q), sigma)
-    # support identical; values within 64 ulp of the value scale + 16 ulps of root displacement through the group's
-    # conditioning κ_g = σλ_g/(n* - σλ_g) (see check_groupl2binf); 99.9th percentile over κ_g <= 1 within 64 ulp
+    # support identical; values within 8 ulp of the value scale + 2 ulps of root displacement through the group's
+    # conditioning κ_g = σλ_g/(n* - σλ_g) (see check_groupl2binf); 99.9th percentile over κ_g <= 1 within 4 ulp
     check_groupl2binf(N(y), xk, sj, q, offs, lam_g, sigma, delta, label=f"{dt.__name__} {layout}")
 
 

@@ -145,7 +145,9 @@ def main():
         timeit("prox_l1b2_inactive", lambda: sp.prox_(y, psi0, q, sigma), 7 * R, note="1 norm pass + finish")
     # groups of 64 (and ragged)
     for gname in ("g64", "ragged"):
-        if not re.search(args.only, f"prox_groupl2_{gname}"):
+        names = [f"prox_groupl2_{gname}", f"value_groupl2_{gname}", f"prox_groupl2binf_{gname}",
+                 "prox_groupl2binf_g64_biglambda"]
+        if not any(re.search(args.only, nm) for nm in names):
             continue
         if gname == "g64":
             ng = n // 64
