@@ -3,10 +3,15 @@
 
 Workload = BASELINE.json configs[1] ("C2"): ShiftedNormL0Box prox!, ShiftedRootNormLhalfBox prox! (vector
 l/u bounds) and ShiftedNormL0Box iprox! (diagonal d), n = 2^28 Float64 per GPU.  One step = those three
-launches over the batch.  `value` = elements/s over all ranks (3·n prox evaluations per step and rank) with
-operands resident in HBM; `e2e` = the same through the host-buffer C-ABI entry point (pinned host vectors,
-H2D and D2H inside the timed region); `roofline` = the dominant kernel against the measured HBM peak;
-`cpu_baseline` = the oracle port (one thread: the reference is single-threaded) on a bounded sample.
+launches over the batch, the first one with ψ(y) fused into its pass (the model decrease a solver reads after
+its prox!); on N > 1 GPUs that scalar is all-reduced inside libshiftedprox (ncclAllReduce on the device slot,
+spx_comm_*), so every step of the scaling run carries a collective.  `value` = elements/s over all ranks
+(3·n prox evaluations per step and rank) with operands resident in HBM; `e2e` = the same through the
+host-buffer C-ABI entry point (pinned host vectors, H2D and D2H inside the timed region); `roofline` = the
+dominant kernel against the measured HBM peak; `cpu_baseline` = the oracle port (one thread: the reference is
+single-threaded) on a bounded sample; `configs` = every configuration of BASELINE.json (C1 ... C5) timed on its
+own after the headline step (CUDA events, median of a few launches), sharded over the ranks with their
+collectives at N > 1.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
@@ -45,6 +50,8 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-configs", action="store_true")
+    ap.add_argument("--config-reps", type=int, default=5)
     return ap.parse_args()
 
 
@@ -54,6 +61,19 @@ def measured_peak():
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def kernel_sources_hash() -> str:
+    """sha256 over the CUDA sources of libshiftedprox (what an ncu capture under profiles/ was taken from)."""
+    import glob
+    import hashlib
+
+    h = hashlib.sha256()
+    for f in sorted(glob.glob(os.path.join(PKG, "csrc", "*.cu")) + glob.glob(os.path.join(PKG, "csrc", "*.cuh"))):
+        h.update(os.path.basename(f).encode())
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
 
 
 # ------------------------------------------------------------ CPU reference arm ---
@@ -138,9 +158,12 @@ def workload_config(log2n, **extra):
                     f"lambda={LAMBDA}, sigma={SIGMA}",
         "n_per_gpu": 1 << log2n,
         "launches_per_step": 3,
+        "fused_value": "psi(y) fused into the L0Box prox! pass of every step (want_value); at N > 1 its scalar is "
+                       "all-reduced on the device by libshiftedprox (NCCL) before the one D2H copy",
         "alg_bytes_per_element": ALG_BYTES,
         "l2_policy": "operands larger than L2: each of the 7 streamed vectors is n*8 B (2 GiB at 2^28) vs 126 MB L2",
-        "sharding": "contiguous shards, one process per GPU, no data-path collective",
+        "sharding": "contiguous shards, one process per GPU; no data-path collective, one scalar all-reduce "
+                    "(sum + infeasibility flag) per step for psi(y)",
     }
     cfg.update(extra)
     return cfg
@@ -232,10 +255,16 @@ def run_ours(args, rank, local_rank, world):
     psi_l0 = sp.shifted(sp.shifted(sp.NormL0(LAMBDA), xk, l, u), sj)
     psi_lh = sp.shifted(sp.shifted(sp.RootNormLhalf(LAMBDA), xk, l, u), sj)
 
+    from shiftedprox import sharded as shd
+
+    if world > 1:  # collectives inside the library: ncclAllReduce on the device slots, on the context's stream
+        shd.comm_init(dev)
+        shd.reduce_scalars(True, dev)
+
     def step(ev=None):
         if ev is not None:
             ev[0].record()
-        sp.prox_(y, psi_l0, q, SIGMA)
+        sp.prox_(y, psi_l0, q, SIGMA, want_value=True)  # fused ψ(y) (+ all-reduce of its scalar at N > 1)
         if ev is not None:
             ev[1].record()
         sp.prox_(y, psi_lh, q, SIGMA)
@@ -271,6 +300,7 @@ def run_ours(args, rank, local_rank, world):
         sampler.poll()
     barrier()
     launches = sp.launch_count(dev) - launches0
+    collectives = shd.comm_info(dev)[2] if world > 1 else 0
     clocks = sampler.stop()
     ms_total = t_start.elapsed_time(t_end)
     per_op_ms = {op: sum(evs[k][i].elapsed_time(evs[k][i + 1]) for k in range(K)) / K for i, op in enumerate(OPS)}
@@ -286,16 +316,20 @@ def run_ours(args, rank, local_rank, world):
     peak, peak_src = measured_peak()
     dom = max(per_op_ms, key=per_op_ms.get)
     achieved = ALG_BYTES[dom] * n / (per_op_ms[dom] * 1e-3) / 1e9
-    traffic = None
+    # DRAM bytes of the dominant kernel from the committed `ncu --set full` capture -- only while the kernel sources
+    # are the ones that capture was taken from (profiles/traffic.json records their hash; a stale entry reads null)
+    traffic, traffic_note = None, None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             tj = json.load(f)
-        if dom in tj and tj[dom].get("log2n") == args.log2n:
+        if tj.get("src_sha256") != kernel_sources_hash():
+            traffic_note = "profiles/traffic.json was captured from other kernel sources (hash differs): not reported"
+        elif dom in tj and tj[dom].get("log2n") == args.log2n:
             traffic = tj[dom]["dram_bytes_per_launch"]
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src,
                 "frac_of_nominal_8000": achieved / 8000.0,
                 "per_kernel": {o: {"ms": per_op_ms[o], "GBps": ALG_BYTES[o] * n / (per_op_ms[o] * 1e-3) / 1e9,
                                    "frac": ALG_BYTES[o] * n / (per_op_ms[o] * 1e-3) / 1e9 / peak} for o in OPS}}
@@ -304,6 +338,14 @@ def run_ours(args, rank, local_rank, world):
     e2e = None
     if not args.no_e2e:
         e2e = run_e2e(args, sp, L, dev, dist, world, n, (xk, sj, q, d, l, u))
+
+    # every BASELINE.json configuration on its own (frees the C2 operands first)
+    configs = None
+    if not args.no_configs:
+        c2 = {o: dict(roofline["per_kernel"][o], alg_bytes_per_element=ALG_BYTES[o]) for o in OPS}
+        del psi_l0, psi_lh, xk, sj, q, l, u, d, y
+        torch.cuda.empty_cache()
+        configs = run_configs(args, sp, L, shd, dev, dist, world, rank, peak, c2)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -317,12 +359,174 @@ def run_ours(args, rank, local_rank, world):
             "hbm_gbs": world * step_bytes / (ms_step * 1e-3) / 1e9,
             "hbm_frac_of_measured_peak": step_bytes / (ms_step * 1e-3) / 1e9 / peak,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-            "host_cores": os.cpu_count(),
+            "collectives_in_timed_region": collectives, "configs": configs, "host_cores": os.cpu_count(),
         }
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
+        shd.comm_destroy(dev)
         dist.destroy_process_group()
+
+
+# ------------------------------------------------- every BASELINE.json configuration ---
+def run_configs(args, sp, L, shd, dev, dist, world, rank, peak, c2):
+    """C1 ... C5 of BASELINE.json, each timed on its own: CUDA events around single calls, 3 warm-ups, median of
+    `--config-reps` launches, operands far larger than L2 (C1's n = 10^6 excepted: it is the reference's own
+    CPU-sized case and is launch-bound here).  At N > 1 the vector / the groups / the batch of every configuration
+    is split over the ranks (`strong`: C3 and C5 keep their total size, as BASELINE.json defines them; the others
+    keep the size per GPU), collectives included: ψ(y) all-reduced on the device, the per-pass sums of the L1B2
+    search.  Times are the max over ranks."""
+    import torch
+
+    f64, f32 = torch.float64, torch.float32
+    reps = max(3, args.config_reps)
+    shrink = max(0, 28 - args.log2n)  # --log2n below 28 shrinks every configuration alike (smoke runs)
+
+    def uniform(n, stream, dt=f64, scale=1.0, shift=0.0, i0=0):
+        t = torch.empty(n, dtype=dt, device=dev)
+        suf, ct = ("f64", C.c_double) if dt == f64 else ("f32", C.c_float)
+        L.call(f"spx_fill_uniform_{suf}", sp.context(dev), C.c_void_p(t.data_ptr()), C.c_int64(n), C.c_int64(i0),
+               C.c_uint64(SEED), C.c_uint64(stream), ct(scale), ct(shift))
+        return t
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+        for a, b in ev:
+            a.record()
+            fn()
+            b.record()
+        torch.cuda.synchronize()
+        ts = sorted(a.elapsed_time(b) for a, b in ev)
+        ms = ts[len(ts) // 2]
+        if dist is not None:
+            tt = torch.tensor([ms], dtype=f64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt.item())
+        return ms
+
+    def entry(ms, elems_all_ranks, bytes_per_elt, **extra):
+        gbs = bytes_per_elt * elems_all_ranks / (ms * 1e-3) / 1e9
+        e = {"ms": ms, "elements_per_s": elems_all_ranks / (ms * 1e-3), "alg_bytes_per_element": bytes_per_elt,
+             "GBps": gbs, "frac": gbs / (peak * world), "frac_of_nominal_8000": gbs / (8000.0 * world)}
+        e.update(extra)
+        return e
+
+    out = {"peak_GBps_per_gpu": peak, "n_gpus": world, "timing": f"CUDA events, median of {reps} after 3 warm-ups, max over ranks"}
+
+    # ---- C1: ShiftedNormL1 prox! Float64, sigma = 0.1 (n = 10^6: the reference's CPU case; n = 2^28: the roofline case)
+    c1 = {"workload": "ShiftedNormL1 prox! Float64, lambda=1, sigma=0.1, random q/x/s"}
+    for name, n in (("n=1e6", 1_000_000), (f"n=2^{28 - shrink}_per_gpu", 1 << (28 - shrink))):
+        xk, sj, q = uniform(n, 0, f64, 4.0, -2.0, rank * n), uniform(n, 1, f64, 1.0, -0.5, rank * n), uniform(n, 2, f64, 4.0, -2.0, rank * n)
+        y = torch.empty_like(q)
+        psi = sp.shifted(sp.shifted(sp.NormL1(1.0), xk), sj)
+        c1[name] = entry(timed(lambda: sp.prox_(y, psi, q, SIGMA)), world * n, 32)
+        c1[name + "+psi"] = entry(timed(lambda: sp.prox_(y, psi, q, SIGMA, want_value=True)), world * n, 32,
+                                  note="psi(y) fused" + (", scalar all-reduced (NCCL)" if world > 1 else ""))
+        del xk, sj, q, y, psi
+    out["C1"] = c1
+    torch.cuda.empty_cache()
+
+    # ---- C2: from the headline step
+    out["C2"] = {"workload": "the headline step (see config.workload); per-kernel split by CUDA events inside the timed region",
+                 **c2}
+
+    # ---- C3: L1 BInf (= L1Box with ±Delta) and L1B2, Float32, psi(y) all-reduced
+    n3_total = 1 << (30 - shrink) if world > 1 else 1 << (29 - shrink)
+    n3 = n3_total // world
+    i0 = rank * n3
+    xk, sj, q = uniform(n3, 0, f32, 4.0, -2.0, i0), uniform(n3, 1, f32, 1.0, -0.5, i0), uniform(n3, 2, f32, 4.0, -2.0, i0)
+    y = torch.empty_like(q)
+    c3 = {"workload": f"ShiftedNormL1 BInf trust region (L1Box, scalar bounds ±0.75) and ShiftedNormL1B2 (ball active) prox! "
+                      f"Float32, n=2^{n3_total.bit_length() - 1} in total over {world} GPU(s), psi(y) fused and all-reduced",
+          "n_total": n3_total, "scaling": "strong" if world > 1 else "single GPU (2^30 Float32 x 4 vectors does not leave room for C3 at N=1 next to nothing else: 2^29)"}
+    box = sp.shifted(sp.shifted(sp.NormL1(1.0), xk, -0.75, 0.75), sj)
+    c3["prox_l1binf"] = entry(timed(lambda: sp.prox_(y, box, q, SIGMA)), n3_total, 16)
+    c3["prox_l1binf+psi"] = entry(timed(lambda: sp.prox_(y, box, q, SIGMA, want_value=True)), n3_total, 16,
+                                  note="psi(y) fused" + (", scalar all-reduced (NCCL)" if world > 1 else ""))
+    pb0 = sp.shifted(sp.shifted(sp.NormL1(1.0), xk, 1.0e9, sp.NormL2(1.0)), sj)
+    sp.prox_(y, pb0, q, SIGMA)  # inactive ball: y = ProjB(-xk) - sj
+    ss = (sj + y).double().square_().sum()
+    if dist is not None:
+        dist.all_reduce(ss)
+    full = float(ss.sqrt().item())
+    del ss
+    pb = sp.shifted(sp.shifted(sp.NormL1(1.0), xk, 0.5 * full, sp.NormL2(1.0)), sj)
+    ms = timed(lambda: sp.prox_(y, pb, q, SIGMA, want_value=True))
+    passes = pb.last_passes
+    nsearch = max(passes - 2, 0)
+    b_l1b2 = 4 * (3 + (4 if nsearch else 0) + 2 * max(nsearch - 1, 0) + 4)
+    c3["prox_l1b2+psi"] = entry(ms, n3_total, b_l1b2, passes=passes,
+                                note=f"{passes - 1} norm passes (3R, 3R+1W, then 2R each) + finish (4R); every pass ends in one "
+                                     f"all-reduce of its partial sums" if world > 1 else f"{passes - 1} norm passes + finish")
+    c3["prox_l1b2+psi"]["frac_single_pass_16B"] = 16 * n3_total / (ms * 1e-3) / 1e9 / (peak * world)
+    del xk, sj, q, y, box, pb0, pb
+    out["C3"] = c3
+    torch.cuda.empty_cache()
+
+    # ---- C4: groups of 64 (10^7 groups) and ragged groups 1..4096, Float64
+    ng = (10_000_000 >> shrink)
+    n4 = ng * 64
+    g0 = rank * ng
+    xk, sj, q = uniform(n4, 0, f64, 4.0, -2.0, g0 * 64), uniform(n4, 1, f64, 1.0, -0.5, g0 * 64), uniform(n4, 2, f64, 4.0, -2.0, g0 * 64)
+    lam_g = uniform(ng, 12, f64, 1.0, 0.5, g0)
+    offs = torch.arange(0, n4 + 1, 64, dtype=torch.int64, device=dev)
+    y = torch.empty_like(q)
+    h = sp.GroupNormL2(lam_g, None, offsets=offs)
+    c4 = {"workload": f"ShiftedGroupNormL2 / ShiftedGroupNormL2Binf prox! Float64, {ng} groups of 64 per GPU (lambda_g = 0.5+u, "
+                      f"sigma=0.3, Delta=0.5), plus ragged groups 1..4096 (log-uniform sizes) over the same vector",
+          "groups_per_gpu": ng, "scaling": "weak (groups split at group boundaries, no data-path collective)"}
+    bpe = 32 + 16.0 / 64
+    psi = sp.shifted(sp.shifted(h, xk), sj)
+    c4["prox_groupl2_g64"] = entry(timed(lambda: sp.prox_(y, psi, q, 0.3)), world * n4, bpe)
+    c4["prox_groupl2_g64+psi"] = entry(timed(lambda: sp.prox_(y, psi, q, 0.3, want_value=True)), world * n4, bpe,
+                                       note="psi(y) fused" + (", scalar all-reduced (NCCL)" if world > 1 else ""))
+    psib = sp.shifted(sp.shifted(h, xk, 0.5, sp.NormLinf(1.0)), sj)
+    c4["prox_groupl2binf_g64"] = entry(timed(lambda: sp.prox_(y, psib, q, 0.3)), world * n4, bpe)
+    import numpy as np
+
+    rng = np.random.default_rng(3)
+    sizes = np.floor(np.exp(rng.uniform(0, np.log(4097), n4 // 400))).astype(np.int64).clip(1, 4096)
+    cs = np.concatenate([[0], np.cumsum(sizes)])
+    cs = cs[cs <= n4]
+    if cs[-1] != n4:
+        cs = np.concatenate([cs, [n4]])
+    offs_r = torch.from_numpy(cs).to(dev)
+    ngr = offs_r.numel() - 1
+    lam_r = uniform(ngr, 12, f64, 1.0, 0.5, 0)
+    hr = sp.GroupNormL2(lam_r, None, offsets=offs_r)
+    bper = 32 + 16.0 * ngr / n4
+    psi = sp.shifted(sp.shifted(hr, xk), sj)
+    c4["prox_groupl2_ragged"] = entry(timed(lambda: sp.prox_(y, psi, q, 0.3)), world * n4, bper, groups_per_gpu=ngr)
+    psib = sp.shifted(sp.shifted(hr, xk, 0.5, sp.NormLinf(1.0)), sj)
+    c4["prox_groupl2binf_ragged"] = entry(timed(lambda: sp.prox_(y, psib, q, 0.3)), world * n4, bper, groups_per_gpu=ngr)
+    del xk, sj, q, y, psi, psib, h, hr, offs, offs_r, lam_g, lam_r
+    out["C4"] = c4
+    torch.cuda.empty_cache()
+
+    # ---- C5: top-r batch, 4096 problems of 65536, r = 1024, Float64; the batch is split over the ranks
+    nprob_total = max(world, 4096 >> shrink)
+    lo, hi = shd.shard_problems(nprob_total, world, rank)
+    npr, pn = hi - lo, 65536
+    n5 = npr * pn
+    xk, sj, q = uniform(n5, 0, f64, 4.0, -2.0, lo * pn), uniform(n5, 1, f64, 1.0, -0.5, lo * pn), uniform(n5, 2, f64, 4.0, -2.0, lo * pn)
+    y = torch.empty_like(q)
+    c5 = {"workload": f"ShiftedIndBallL0BInf / ShiftedIndBallL0 prox! Float64, batch of {nprob_total} independent problems of "
+                      f"n=65536, r=1024, Delta=1, split over {world} GPU(s) ({npr} problems on rank 0)",
+          "scaling": "strong (the batch keeps its size)" if world > 1 else "single GPU"}
+    hb = sp.IndBallL0(1024)
+    psi = sp.shifted(sp.shifted(hb, xk, 1.0, sp.NormLinf(1.0), nprob=npr), sj)
+    c5["prox_indballl0binf_batch"] = entry(timed(lambda: sp.prox_(y, psi, q, 1.0)), nprob_total * pn, 32)
+    psi = sp.shifted(sp.shifted(hb, xk, nprob=npr), sj)
+    c5["prox_indballl0_batch"] = entry(timed(lambda: sp.prox_(y, psi, q, 1.0)), nprob_total * pn, 32)
+    del xk, sj, q, y, psi
+    out["C5"] = c5
+    torch.cuda.empty_cache()
+    return out
 
 
 def run_e2e(args, sp, L, dev, dist, world, n, dev_inputs):

@@ -3,7 +3,17 @@
 Nothing here touches the data path: elementwise / Box / group / batched top-r proxes run on each rank's
 contiguous shard with no collective.  Collectives exist only where the path has a real
 exchange: the scalar ψ(y) (sum + infeasibility flag) and the K partial sums per pass of the ℓ2 trust-region
-root search (ShiftedNormL1B2).  `torch.distributed` is plumbing (NCCL on GPUs, gloo in the CPU tests).
+root search (ShiftedNormL1B2).
+
+Two ways to run them:
+
+* `comm_init()` + `reduce_scalars(True)`: the collectives run INSIDE libshiftedprox -- ncclAllReduce over NVLink on
+  the context's stream, directly on the device slots the kernels fold into, before the one D2H copy of the call.
+  Every verb of the host mirror (`ψ(y)`, `prox_(..., want_value=True)`, `step_`, ShiftedNormL1B2's `prox_`) then
+  returns whole-vector scalars, identical on every rank, with no host staging.  `torch.distributed` only carries
+  the 128-byte NCCL id to the ranks.
+* the callback forms below (`value_sharded`, `prox_l1b2_sharded_`, ...): the host all-reduces through
+  `torch.distributed` (gloo in the CPU tests, NCCL on GPUs).  Kept as the fallback and for the CPU tests.
 """
 from __future__ import annotations
 
@@ -14,6 +24,52 @@ from typing import List, Optional, Sequence, Tuple
 import numpy as np
 import torch
 import torch.distributed as dist
+
+
+# ------------------------------------------------- collectives inside the library ---
+def comm_init(device=None, group=None) -> None:
+    """Attach an NCCL communicator to this rank's libshiftedprox context (spx_comm_init): rank 0 draws the id
+    (spx_comm_unique_id), `torch.distributed` broadcasts its 128 bytes, every rank joins."""
+    from . import _lib as L, context
+
+    if not (dist.is_available() and dist.is_initialized()):
+        raise RuntimeError("comm_init needs an initialised torch.distributed process group (to pass the NCCL id)")
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    ctx = context(dev)
+    idbuf = (C.c_ubyte * 128)()
+    if rank == 0:
+        L.call("spx_comm_unique_id", idbuf)
+    carrier = dev if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    t = torch.tensor(list(idbuf), dtype=torch.uint8, device=carrier)
+    dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    raw = bytes(t.cpu().tolist())
+    L.call("spx_comm_init", ctx, C.c_int32(world), C.c_int32(rank), C.c_char_p(raw))
+
+
+def comm_destroy(device=None) -> None:
+    from . import _lib as L, context
+
+    L.call("spx_comm_destroy", context(device if device is not None else torch.cuda.current_device()))
+
+
+def reduce_scalars(on: bool, device=None) -> None:
+    """spx_comm_reduce_scalars: with `on`, every scalar the library hands back is the whole-vector value (all-reduced
+    on the device); every rank must then make the same calls in the same order."""
+    from . import _lib as L, context
+
+    L.call("spx_comm_reduce_scalars", context(device if device is not None else torch.cuda.current_device()),
+           C.c_int32(1 if on else 0))
+
+
+def comm_info(device=None):
+    """(nranks, rank, collectives issued so far) of this rank's context."""
+    from . import _lib as L, context
+
+    a, b, c = C.c_int32(), C.c_int32(), C.c_int64()
+    L.call("spx_comm_info", context(device if device is not None else torch.cuda.current_device()), C.byref(a),
+           C.byref(b), C.byref(c))
+    return a.value, b.value, c.value
 
 
 # ------------------------------------------------------------------ partitioning ---
@@ -129,25 +185,37 @@ def _make_reduce(dev, group):
     mirror and a device buffer are kept per device, the values travel H2D -> NCCL -> D2H on the current stream."""
 
     def _reduce(_user, vals, count):
+        # Never let an exception cross the C boundary, and never leave the peers alone in the collective: whatever
+        # fails locally, this rank still joins the all-reduce (with a poisoned status word riding along), so every
+        # rank sees the failure and aborts together instead of one returning early and the others hanging.
+        status = 0.0
+        host = buf = None
         try:
-            key = (dev.index, max(count, 64))
+            key = (dev.index, max(count + 1, 64))
             bufs = _REDUCE_BUFS.get(key)
             if bufs is None:
-                host = torch.empty(max(count, 64), dtype=torch.float64, pin_memory=dev.type == "cuda")
-                bufs = _REDUCE_BUFS[key] = (host, torch.empty(max(count, 64), dtype=torch.float64, device=dev))
+                h = torch.empty(max(count + 1, 64), dtype=torch.float64, pin_memory=dev.type == "cuda")
+                bufs = _REDUCE_BUFS[key] = (h, torch.empty(max(count + 1, 64), dtype=torch.float64, device=dev))
             host, buf = bufs
-            hv = host.numpy()
-            for i in range(count):
-                hv[i] = vals[i]
-            buf[:count].copy_(host[:count], non_blocking=True)
-            dist.all_reduce(buf[:count], op=dist.ReduceOp.SUM, group=group)
-            host[:count].copy_(buf[:count], non_blocking=True)
+            src = np.ctypeslib.as_array(vals, shape=(count,))
+            host[:count].numpy()[:] = src  # bulk copy, no per-element Python loop
+        except Exception:
+            status = 1.0
+        try:
+            if host is None:
+                host = torch.zeros(count + 1, dtype=torch.float64)
+                buf = torch.zeros(count + 1, dtype=torch.float64, device=dev)
+            host[count] = status
+            buf[:count + 1].copy_(host[:count + 1], non_blocking=True)
+            dist.all_reduce(buf[:count + 1], op=dist.ReduceOp.SUM, group=group)
+            host[:count + 1].copy_(buf[:count + 1], non_blocking=True)
             if dev.type == "cuda":
                 torch.cuda.current_stream(dev).synchronize()
-            for i in range(count):
-                vals[i] = float(hv[i])
+            if float(host[count]) != 0.0:
+                return -1  # some rank failed: every rank returns the error
+            np.ctypeslib.as_array(vals, shape=(count,))[:] = host[:count].numpy()
             return 0
-        except Exception:  # never let an exception cross the C boundary
+        except Exception:
             return -1
 
     return _reduce

@@ -7,7 +7,11 @@
 Every rank holds a contiguous shard of the same synthetic vectors.  Checks that (1) the all-reduced ψ(y)
 equals the single-device value, (2) the sharded ShiftedNormL1B2 prox! (K partial sums all-reduced per pass,
 root search replicated) reproduces the single-device result bit for bit on every shard, (3) the top-r projection
-of one vector spread over the ranks (histogram all-reduce per radix digit) is identical to the single-device one."""
+of one vector spread over the ranks (histogram all-reduce per radix digit) is identical to the single-device one,
+(4) the same scalars through the collectives INSIDE libshiftedprox (spx_comm_init + spx_comm_reduce_scalars:
+ncclAllReduce on the device slots): ψ(y), fused ψ, an infeasible shard -> Inf on every rank, the IndBallL0 count,
+the fused solver step's three scalars, ShiftedNormL1B2 prox! with its per-pass sums, a single ℓ2 group spanning the
+sharded vector."""
 import ctypes as C
 import os
 import sys
@@ -80,6 +84,67 @@ def main():
         if rank == 0:
             print(f"[{dtype}] world={world} sharded top-r (r={r_top}, quantised ties) identical to single device: {top_ok}",
                   flush=True)
+        # (4) collectives inside the library
+        rtol = 1e-13 if dtype == torch.float64 else 1e-6
+        if dtype == torch.float64 and not getattr(main, "_comm", False):
+            sharded.comm_init(dev)
+            main._comm = True
+        sharded.reduce_scalars(True, dev)
+        c0 = sharded.comm_info(dev)[2]
+        ysh = torch.empty_like(q)
+        # ψ(y) stand-alone and fused
+        sp.prox_(yf, psi_f, full[2], 0.1)
+        sharded.reduce_scalars(False, dev)
+        v_full = psi_f(yf)
+        sharded.reduce_scalars(True, dev)
+        v_lib = psi_s(yf[lo:hi].clone())
+        _, v_fused = sp.prox_(ysh, psi_s, q, 0.1, want_value=True)
+        lib_ok = abs(v_lib - v_full) <= rtol * abs(v_full) and abs(v_fused - v_full) <= rtol * abs(v_full)
+        lib_ok &= bool(torch.equal(ysh, yf[lo:hi]))
+        # Box ψ: infeasible on the LAST rank only -> Inf everywhere
+        bx = sp.shifted(sp.shifted(sp.NormL0(1.1), xk, -3.0, 3.0), sj)
+        ybad = (yf[lo:hi] * 0).clone()
+        fin = bx(ybad)
+        if rank == world - 1:
+            ybad[-1] = 100.0
+        inf = bx(ybad)
+        lib_ok &= (fin < float("inf")) and (inf == float("inf"))
+        # IndBallL0 count over all shards: r = global count -> 0, r one short -> Inf
+        cnt = int(torch.count_nonzero((full[0] + full[1]) + yf).item())
+        ib = sp.shifted(sp.shifted(sp.IndBallL0(max(cnt, 1)), xk), sj)
+        ib1 = sp.shifted(sp.shifted(sp.IndBallL0(max(cnt - 1, 1)), xk), sj)
+        lib_ok &= ib(yf[lo:hi].clone()) == 0.0 and (cnt < 2 or ib1(yf[lo:hi].clone()) == float("inf"))
+        # fused solver step: the three scalars over the whole vector
+        sharded.reduce_scalars(False, dev)
+        once_f = sp.shifted(sp.NormL1(1.3), full[0])
+        sfull = torch.empty_like(full[2])
+        _, rf = sp.step_(sfull, once_f, full[2], 0.2)
+        sharded.reduce_scalars(True, dev)
+        once_s = sp.shifted(sp.NormL1(1.3), xk)
+        _, rs = sp.step_(ysh, once_s, q, 0.2)
+        lib_ok &= all(abs(a - b) <= rtol * max(1.0, abs(b)) for a, b in zip(rs, rf)) and bool(torch.equal(ysh, sfull[lo:hi]))
+        # L1B2: the plain prox! entry point, its per-pass sums all-reduced on the device
+        bs2 = sp.shifted(sp.shifted(sp.NormL1(1.0), xk, delta, sp.NormL2(1.0)), sj)
+        _, vs2 = sp.prox_(ysh, bs2, q, 0.1, want_value=True)
+        sharded.reduce_scalars(False, dev)
+        sp.prox_(yf, bf, full[2], 0.1)
+        diff2 = float((ysh - yf[lo:hi]).abs().max())
+        lib_ok &= diff2 <= tol * 4.0 and (abs(vs2 - vf) <= (1e-9 if dtype == torch.float64 else 1e-4) * abs(vf))
+        # one ℓ2 group spanning the whole (sharded) vector: ShiftedGroupNormL2 from NormL2
+        gf = sp.shifted(sp.shifted(sp.NormL2(0.7), full[0]), full[1])
+        sp.prox_(yf, gf, full[2], 0.3)
+        sharded.reduce_scalars(True, dev)
+        gs = sp.shifted(sp.shifted(sp.NormL2(0.7), xk), sj)
+        sp.prox_(ysh, gs, q, 0.3)
+        gdiff = float((ysh - yf[lo:hi]).abs().max())
+        lib_ok &= gdiff <= 8 * torch.finfo(dtype).eps * 8.0
+        ncoll = sharded.comm_info(dev)[2] - c0
+        sharded.reduce_scalars(False, dev)
+        ok &= lib_ok
+        if rank == 0:
+            print(f"[{dtype}] world={world} in-library NCCL: psi {v_lib:.12g} / fused {v_fused:.12g} vs {v_full:.12g}; "
+                  f"l1b2 max diff {diff2:.3e} passes {bs2.last_passes}; one-group max diff {gdiff:.3e}; "
+                  f"{ncoll} collectives; ok={lib_ok}", flush=True)
         if rank == 0:
             print(f"[{dtype}] world={world} psi rel err {rel:.2e}; l1b2 passes {bs.last_passes} (single {bf.last_passes}), "
                   f"max |y_sharded - y_single| {diff:.3e}, psi {vs:.12g} vs {vf:.12g}", flush=True)
@@ -88,6 +153,8 @@ def main():
     if rank == 0:
         print("SHARDED CHECK", "OK" if flag.item() == 1.0 else "FAILED", flush=True)
     dist.barrier()
+    if getattr(main, "_comm", False):
+        sharded.comm_destroy(dev)
     dist.destroy_process_group()
     sys.exit(0 if flag.item() == 1.0 else 1)
 
