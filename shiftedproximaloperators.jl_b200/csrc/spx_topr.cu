@@ -18,6 +18,8 @@
 // the end of this file (z stashed in y, one histogram pass per digit).
 #include <cooperative_groups.h>
 
+#include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -558,6 +560,308 @@ __global__ void __launch_bounds__(kTrThreads, 1)
   }
 }
 
+// ------------------------------------------- batches of problems: the stream form --
+// One CTA per problem, several CTAs per SM, no cluster and no state in registers between phases -- so while one
+// CTA of an SM selects, its neighbours stream, which the one-cluster-per-problem form above cannot do (its z pins
+// every register of the SM; profiles/r01_topr_lin_phase_timing.txt: 35 % of a problem is select time during which
+// the SM pulls nothing from HBM).
+//   pass 1  streams xk, sj, q once (3R): writes the DROPPED value of every entry, y_i = clamp(0 - (xk+sj)_i) (1W), and
+//           a 16-bit monotone image of |z_i| (the top 16 bits of its Float32 bit pattern: 8 exponent + 7 mantissa
+//           bits; NaN -> 0xFFFF) into a per-CTA scratch array that lives in L2 (2 B per element, rewritten for every
+//           problem of the CTA);
+//   pass 2a re-reads the 16-bit keys (L2), histograms them relative to the problem's largest key (one bin per
+//           distinct key value: the 2047 values below the maximum cover 16 binades) and locates the key value t16
+//           that holds the r-th largest entry;
+//   pass 2b re-reads the keys: an entry with key > t16 is kept whatever the order inside t16 -- its y is rewritten
+//           as clamp(z - xs) from the three inputs re-read at that index (~r scattered sectors); entries with
+//           key == t16 (a few hundred) are ranked exactly (full key descending, position ascending: the reference's
+//           tie order) and the first r - #above of them rewritten the same way.
+// HBM traffic = 4R + the scattered re-reads (~r sectors of 32 B per input) + whatever part of the key scratch L2
+// writes back.  Problems it cannot decide (NaN / Inf, all zeros, > 1024 candidates, the threshold more than 16
+// binades below the maximum) are flagged for the radix kernel above, as in the cluster form.  Not used when y
+// aliases an input (pass 1 overwrites y before pass 2 re-reads q at the kept positions).
+#ifndef SPX_TS_THREADS
+#define SPX_TS_THREADS 256
+#endif
+#ifndef SPX_TS_MINB
+#define SPX_TS_MINB 4
+#endif
+#ifndef SPX_TS_UNROLL
+#define SPX_TS_UNROLL 2
+#endif
+constexpr int kTsUnroll = SPX_TS_UNROLL;  // 128-bit packets per operand in flight per thread in pass 1
+constexpr int kTsCand = 1024;
+
+// L2 residency hints (createpolicy): the streamed operands are marked evict-first, the 16-bit key scratch -- written
+// in pass 1 and read twice right after -- evict-last, so the 4R stream does not push the keys out of L2
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void ld_hint(const double* p, Pack<double, 2>& o, uint64_t pol) {
+  asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;"
+               : "=d"(o.v[0]), "=d"(o.v[1])
+               : "l"(p), "l"(pol));
+}
+__device__ __forceinline__ void ld_hint(const float* p, Pack<float, 4>& o, uint64_t pol) {
+  asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=f"(o.v[0]), "=f"(o.v[1]), "=f"(o.v[2]), "=f"(o.v[3])
+               : "l"(p), "l"(pol));
+}
+__device__ __forceinline__ uint4 ld_keys(const uint4* p, uint64_t pol) {
+  uint4 v;
+  asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ void st_keys(unsigned* p, unsigned v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_keys(uint2* p, uint2 v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v2.u32 [%0], {%1, %2}, %3;" ::"l"(p), "r"(v.x), "r"(v.y), "l"(pol) : "memory");
+}
+
+template <class R> __device__ __forceinline__ unsigned key16_of(R z) {
+  const float f = fabsf((float)z);  // rounding is monotone: the image is non-decreasing in |z|
+  const unsigned k = (unsigned)__float_as_int(f) >> 16;
+  return (z != z) ? 0xffffu : k;
+}
+
+template <bool SMEMKEYS> __device__ __forceinline__ uint4 get_keys(const uint4* p, uint64_t pol) {
+  if (SMEMKEYS) return *p;
+  return ld_keys(p, pol);
+}
+
+template <int THREADS> struct TsShared {
+  unsigned hist[kTrBins];
+  int ws[40];
+  unsigned kmax_w[THREADS / 32];
+  int sel_bin;
+  long long sel_above, sel_count;
+  int cand_count;
+  int rewrites;
+  int cand_idx[kTsCand];
+  unsigned long long cand_key[kTsCand];
+};
+
+// THREADS x MINB resident threads per SM.  SMEMKEYS: the 16-bit keys of the problem live in (dynamic) shared memory
+// -- 2 n bytes, one 1024-thread CTA per SM for n = 65536 -- instead of the L2-resident global scratch (larger n).
+template <class R, bool BINF, int THREADS, int MINB, bool SMEMKEYS>
+__global__ void __launch_bounds__(THREADS, MINB)
+    topr_stream_kernel(R* y, const R* xk, const R* sj, const R* q, long long n, long long r, R delta, long long nprob,
+                       unsigned short* __restrict__ key_scratch, unsigned char* __restrict__ fallback) {
+  using KT = KeyTraits<R>;
+  constexpr int VEC = 16 / (int)sizeof(R);
+  constexpr int kTsThreads = THREADS;
+  constexpr int kTsBpt = kTrBins / THREADS;
+  __shared__ TsShared<THREADS> sh;
+  extern __shared__ __align__(16) unsigned char ts_dyn[];
+  const int t = threadIdx.x, lane = t & 31;
+  const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
+  unsigned short* keys = SMEMKEYS ? reinterpret_cast<unsigned short*>(ts_dyn) : key_scratch + (size_t)blockIdx.x * (size_t)n;
+  const int nvec = (int)(n / VEC);  // n is a multiple of 8, at most 131072: 32-bit offsets inside a problem
+  const int nk8 = (int)(n / 8);
+  auto drop = [&](R xs) -> R {
+    R v = R(0) - xs;  // a dropped entry: 0 - (xk + sj)   (shiftedIndBallL0.jl:69-70)
+    if (BINF) v = jl_min(jl_max(v, -delta), delta);
+    return v;
+  };
+  auto keep = [&](R xs, R z) -> R {
+    R v = z - xs;  // a kept entry: z - (xk + sj)   (shiftedIndBallL0.jl:70)
+    if (BINF) v = jl_min(jl_max(v, -delta), delta);
+    return v;
+  };
+  auto fix = [&](int i, const R* pxk, const R* psj, const R* pq, R* py) {  // rewrite entry i in its kept form
+    const R xs = pxk[i] + psj[i];
+    py[i] = keep(xs, xs + pq[i]);
+  };
+  auto unfix = [&](int i, const R* pxk, const R* psj, R* py) { py[i] = drop(pxk[i] + psj[i]); };
+  // Pass 1 already writes the KEPT form where the 16-bit key reaches `guess` -- the threshold key of the previous
+  // problem of this CTA, which for a batch of like problems is the threshold of this one or its neighbour -- so pass
+  // 2b only has to rewrite the entries the guess got wrong plus the unkept ones among the threshold-valued entries,
+  // instead of re-reading three operands for every kept entry.  A guess that proves bad (more than r rewrites) is
+  // dropped for the next problem.
+  unsigned guess = 0x10000u;  // nothing pre-kept
+  for (long long prob = blockIdx.x; prob < nprob; prob += gridDim.x) {
+    const R* pxk = xk + prob * n;
+    const R* psj = sj + prob * n;
+    const R* pq = q + prob * n;
+    R* py = y + prob * n;
+    // ---- pass 1 -----------------------------------------------------------------------------------------
+    unsigned kmax = 0;
+    for (int v0 = t; v0 < nvec; v0 += kTsUnroll * kTsThreads) {
+      Pack<R, VEC> a[kTsUnroll], b[kTsUnroll], c[kTsUnroll];
+#pragma unroll
+      for (int u = 0; u < kTsUnroll; ++u) {
+        const int v = v0 + u * kTsThreads;
+        if (v < nvec) {
+          ld_hint(pxk + v * VEC, a[u], pol_stream);
+          ld_hint(psj + v * VEC, b[u], pol_stream);
+          ld_hint(pq + v * VEC, c[u], pol_stream);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kTsUnroll; ++u) {
+        const int v = v0 + u * kTsThreads;
+        if (v < nvec) {
+          Pack<R, VEC> o;
+          unsigned k16[VEC];
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) {
+            const R xs = a[u].v[e] + b[u].v[e];
+            const R z = xs + c[u].v[e];  // (xk + sj) + q   shiftedIndBallL0.jl:66
+            k16[e] = key16_of(z);
+            o.v[e] = (k16[e] >= guess) ? keep(xs, z) : drop(xs);
+            kmax = k16[e] > kmax ? k16[e] : kmax;
+          }
+          st_stream(py + v * VEC, o);
+          if (VEC == 2) {
+            const unsigned w = k16[0] | (k16[1] << 16);
+            if (SMEMKEYS) reinterpret_cast<unsigned*>(keys)[v] = w;
+            else st_keys(reinterpret_cast<unsigned*>(keys) + v, w, pol_keep);
+          } else {
+            uint2 w;
+            w.x = k16[0] | (k16[1] << 16);
+            w.y = k16[2 % VEC] | (k16[3 % VEC] << 16);
+            if (SMEMKEYS) reinterpret_cast<uint2*>(keys)[v] = w;
+            else st_keys(reinterpret_cast<uint2*>(keys) + v, w, pol_keep);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned other = __shfl_xor_sync(0xffffffffu, kmax, o);
+      kmax = other > kmax ? other : kmax;
+    }
+    if (lane == 0) sh.kmax_w[t >> 5] = kmax;
+    for (int b = t; b < kTrBins; b += kTsThreads) sh.hist[b] = 0;
+    if (t == 0) {
+      sh.cand_count = 0;
+      sh.rewrites = 0;
+    }
+    __syncthreads();  // also orders pass 1's global writes (keys, y) before pass 2's reads / rewrites
+    kmax = 0;
+#pragma unroll
+    for (int w = 0; w < kTsThreads / 32; ++w) kmax = sh.kmax_w[w] > kmax ? sh.kmax_w[w] : kmax;
+    const unsigned base16 = kmax > (unsigned)(kTrBins - 1) ? kmax - (unsigned)(kTrBins - 1) : 0u;
+    // ---- pass 2a: one bin per key value below the maximum; keys <= base16 are not counted ------------------
+    for (int w0 = t - lane; w0 < nk8; w0 += 2 * kTsThreads) {  // warp-uniform trip count: the votes below need every lane
+      const int c0 = w0 + lane;
+      uint4 wv[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+        wv[u] = (c0 + u * kTsThreads < nk8) ? get_keys<SMEMKEYS>(reinterpret_cast<const uint4*>(keys) + c0 + u * kTsThreads, pol_keep)
+                                            : make_uint4(0u, 0u, 0u, 0u);  // key 0 is never counted
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const unsigned ww[4] = {wv[u].x, wv[u].y, wv[u].z, wv[u].w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const unsigned k = (ww[j >> 1] >> ((j & 1) * 16)) & 0xffffu;
+          const bool cnt = k > base16;
+          // a warp whose lanes all hit one bin (constant data, massive ties) adds once
+          const unsigned k0 = __shfl_sync(0xffffffffu, k, 0);
+          if (__all_sync(0xffffffffu, k == k0)) {
+            if (lane == 0 && cnt) atomicAdd(&sh.hist[k - base16], 32u);
+          } else if (cnt) {
+            atomicAdd(&sh.hist[k - base16], 1u);
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // ---- pick the key value holding the r-th largest entry ----------------------------------------------
+    bool hard;
+    unsigned t16 = 0;
+    long long need = 0;
+    {
+      int c[kTsBpt], mine = 0;
+#pragma unroll
+      for (int j = 0; j < kTsBpt; ++j) {
+        c[j] = (int)sh.hist[kTrBins - 1 - kTsBpt * t - j];
+        mine += c[j];
+      }
+      if (t == 0) sh.sel_bin = 0;
+      int total;
+      long long above = block_excl_scan<kTsThreads>(mine, sh.ws, &total);
+#pragma unroll
+      for (int j = 0; j < kTsBpt; ++j) {
+        const int bin = kTrBins - 1 - kTsBpt * t - j;
+        if (bin > 0 && above < r && r <= above + c[j]) {
+          sh.sel_bin = bin;
+          sh.sel_above = above;
+          sh.sel_count = c[j];
+        }
+        above += c[j];
+      }
+      __syncthreads();
+      const int sel = sh.sel_bin;
+      // bin 0 (everything 16 binades below the maximum, zeros, the all-equal-to-zero problem), a NaN / Inf
+      // maximum, or a crowded threshold value: left to the radix kernel
+      hard = (sel == 0) || (kmax >= 0x7f80u) || (sh.sel_count > (long long)kTsCand);
+      t16 = base16 + (unsigned)sel;
+      need = r - sh.sel_above;  // rank inside the threshold value, 1-based
+    }
+    if (t == 0) fallback[prob] = hard ? 1 : 0;
+    if (!hard) {
+      // ---- pass 2b: entries pass 1 wrote in the wrong form rewritten, threshold-valued entries listed -----------
+      int nrewrite = 0;
+      for (int c8 = t; c8 < nk8; c8 += kTsThreads) {
+        const uint4 w = get_keys<SMEMKEYS>(reinterpret_cast<const uint4*>(keys) + c8, pol_stream);
+        const unsigned ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const unsigned k = (ww[j >> 1] >> ((j & 1) * 16)) & 0xffffu;
+          const int i = c8 * 8 + j;
+          if (k == t16) {
+            const int pos = atomicAdd(&sh.cand_count, 1);
+            if (pos < kTsCand) sh.cand_idx[pos] = i;
+          } else if ((k > t16) != (k >= guess)) {  // pass 1 wrote the other form
+            if (k > t16) fix(i, pxk, psj, pq, py);
+            else unfix(i, pxk, psj, py);
+            ++nrewrite;
+          }
+        }
+      }
+      __syncthreads();
+      const int C = sh.cand_count < kTsCand ? sh.cand_count : kTsCand;  // == sel_count <= kTsCand
+      for (int ci = t; ci < C; ci += kTsThreads) {
+        const int i = sh.cand_idx[ci];
+        const R z = (pxk[i] + psj[i]) + pq[i];
+        sh.cand_key[ci] = (unsigned long long)KT::key(z);
+      }
+      __syncthreads();
+      // direct ranking: key descending, position ascending; the first `need` are kept
+      for (int ci = t; ci < C; ci += kTsThreads) {
+        const unsigned long long mk = sh.cand_key[ci];
+        const int mi = sh.cand_idx[ci];
+        int rank = 1;
+        for (int j = 0; j < C; ++j) {
+          const unsigned long long kj = sh.cand_key[j];
+          rank += (kj > mk) || (kj == mk && sh.cand_idx[j] < mi);
+        }
+        const bool kept = (long long)rank <= need;
+        if (kept != (t16 >= guess)) {
+          if (kept) fix(mi, pxk, psj, pq, py);
+          else unfix(mi, pxk, psj, py);
+        }
+      }
+      if (nrewrite) atomicAdd(&sh.rewrites, nrewrite);
+    }
+    __syncthreads();  // shared state (and the key scratch) is reused by the next problem
+    guess = (!hard && (long long)sh.rewrites <= r) ? t16 : 0x10000u;
+    __syncthreads();
+  }
+}
+
 // ------------------------------------------------- global multi-pass path ---
 // For one long vector: z is stashed in y (3R + 1W), every further digit costs
 // one read of y, the last pass reads y, xk, sj and writes y.
@@ -885,6 +1189,51 @@ static int32_t topr_cluster_launch(spx_ctx* ctx, int64_t nprob, int64_t n, R* y,
   return SPX_OK;
 }
 
+template <class R, bool BINF>
+static int32_t topr_stream_launch(spx_ctx* ctx, int64_t nprob, int64_t n, R* y, const R* xk, const R* sj, const R* q,
+                                  int64_t r, R delta) {
+  const size_t flags_bytes = ((size_t)nprob + 255) & ~(size_t)255;
+  const size_t key_bytes = (size_t)n * sizeof(unsigned short);
+  // keys in shared memory while 2 n bytes fit next to the static state of a CTA: one 1024-thread CTA per SM above
+  // 72 KiB of keys, two 512-thread CTAs down to 36 KiB, four 256-thread CTAs below
+  const bool smem_keys = key_bytes <= 200 * 1024 && std::getenv("SPX_TOPR_L2KEYS") == nullptr;
+  int32_t st = SPX_OK;
+  unsigned char* flags = nullptr;
+  auto go = [&](auto kern, int threads, size_t dyn, bool scratch_keys) -> int32_t {
+    if (dyn > 0) SPX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    int per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, dyn) != cudaSuccess || per_sm < 1) per_sm = 1;
+    const int64_t grid = std::min<int64_t>(nprob, (int64_t)ctx->sm_count * per_sm);
+    int32_t s2 = ensure_scratch(ctx, 4096 + flags_bytes + (scratch_keys ? (size_t)grid * key_bytes : 0));
+    if (s2 != SPX_OK) return s2;
+    flags = (unsigned char*)ctx->d_scratch + 4096;  // the first 4 KiB belong to the reductions
+    unsigned short* keys = (unsigned short*)((char*)ctx->d_scratch + 4096 + flags_bytes);
+    kern<<<(unsigned)grid, threads, dyn, ctx->stream>>>(y, xk, sj, q, (long long)n, (long long)r, delta, (long long)nprob,
+                                                        keys, flags);
+    ctx->launches++;
+    SPX_CUDA(cudaGetLastError());
+    return SPX_OK;
+  };
+  if (!smem_keys) st = go(topr_stream_kernel<R, BINF, 512, 2, false>, 512, 0, true);
+  else if (key_bytes > 72 * 1024) st = go(topr_stream_kernel<R, BINF, 1024, 1, true>, 1024, key_bytes, false);
+  else if (key_bytes > 36 * 1024) st = go(topr_stream_kernel<R, BINF, 512, 2, true>, 512, key_bytes, false);
+  else st = go(topr_stream_kernel<R, BINF, 256, 4, true>, 256, key_bytes, false);
+  if (st != SPX_OK) return st;
+  // radix select on the problems it flagged (NaN / Inf / all-zero / crowded threshold value)
+  int csize = 1;
+  while ((long long)csize * kTrChunk < n) csize <<= 1;
+  const size_t smem = ((sizeof(TrShared) + 15) / 16) * 16 + sizeof(R) * (size_t)kTrChunk;
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  auto rk = topr_cluster_kernel<R, BINF, true>;
+  st = cluster_grid(ctx, rk, csize, smem, nprob, &cfg, attr);
+  if (st != SPX_OK) return st;
+  SPX_CUDA(cudaLaunchKernelEx(&cfg, rk, y, xk, sj, q, (long long)n, (long long)r, delta, (long long)nprob,
+                              (const unsigned char*)flags));
+  ctx->launches++;
+  return SPX_OK;
+}
+
 template <class R>
 static int32_t prox_indballl0(spx_ctx* ctx, int64_t nprob, int64_t n, R* y, const R* xk, const R* sj, const R* q,
                               int64_t r, int32_t binf, double delta) {
@@ -902,6 +1251,17 @@ static int32_t prox_indballl0(spx_ctx* ctx, int64_t nprob, int64_t n, R* y, cons
   }
   const uintptr_t bits = (uintptr_t)y | (uintptr_t)xk | (uintptr_t)sj | (uintptr_t)q;
   const bool vec = (bits & 15u) == 0 && (n * (int64_t)sizeof(R)) % 16 == 0;
+  // batches: the stream form (one CTA per problem, several CTAs per SM)
+  {
+    const char *y0 = (const char*)y, *y1 = y0 + (size_t)nprob * n * sizeof(R);
+    auto overlaps = [&](const R* p) { return (const char*)p < y1 && (const char*)p + (size_t)nprob * n * sizeof(R) > y0; };
+    const bool alias = overlaps(xk) || overlaps(sj) || overlaps(q);
+    if (vec && !alias && n % 8 == 0 && n >= 4096 && r > 0 && r < n && nprob >= 2 * (int64_t)ctx->sm_count &&
+        std::getenv("SPX_TOPR_CLUSTER") == nullptr) {
+      return binf ? topr_stream_launch<R, true>(ctx, nprob, n, y, xk, sj, q, r, (R)delta)
+                  : topr_stream_launch<R, false>(ctx, nprob, n, y, xk, sj, q, r, (R)delta);
+    }
+  }
   if (binf) {
     return vec ? topr_cluster_launch<R, true, true>(ctx, nprob, n, y, xk, sj, q, r, (R)delta)
                : topr_cluster_launch<R, true, false>(ctx, nprob, n, y, xk, sj, q, r, (R)delta);

@@ -901,3 +901,48 @@ def test_group_l2binf_uniform_candidates_that_are_not_uniform(dt):
     yq = T(q).clone()
     sp.prox_(yq, psi, yq, sigma)
     check_groupl2binf(N(yq), xk, sj, q, offs, lam_g, sigma, delta, label=f"uniform aliased {dt.__name__}")
+
+
+# ------------------------------------------- batched top-r: the stream form (one CTA per problem) ---
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("pn,r", [(4096, 100), (16_384, 1), (32_768, 700), (65_536, 1024), (65_536, 65_535), (131_072, 5000)])
+@pytest.mark.parametrize("binf", [False, True])
+def test_indballl0_batch_stream_form(dt, pn, r, binf):
+    """Batches of >= 2 x 148 problems take topr_stream_kernel (16-bit keys in shared memory up to n = 65536, in the
+    L2-resident scratch above): bit-exact against the oracle, including a tie-stress problem (magnitudes quantised to
+    1/64), a constant problem, an all-zero problem and problems holding NaN / Inf (flagged for the radix kernel)."""
+    nprob = 300
+    n = nprob * pn
+    xk, sj, q = inputs(n, dt)
+    special = {3: "ties", 7: "const", 11: "zero", 13: "nan", 17: "inf", nprob - 1: "ties"}
+    for p, kind in special.items():
+        s = slice(p * pn, (p + 1) * pn)
+        if kind == "ties":
+            xk[s] = 0; sj[s] = 0
+            q[s] = (np.round(q[s] * 64) / 64).astype(dt)
+        elif kind == "const":
+            xk[s] = 0; sj[s] = 0; q[s] = dt(1.25)
+        elif kind == "zero":
+            xk[s] = 0; sj[s] = 0; q[s] = 0
+        elif kind == "nan":
+            q[p * pn + 5] = np.nan; q[p * pn + pn - 2] = np.nan
+        elif kind == "inf":
+            q[p * pn + 9] = np.inf; q[p * pn + 77] = -np.inf
+    h = sp.IndBallL0(r)
+    psi = sp.shifted(h, T(xk), 1.0, sp.NormLinf(1.0), nprob=nprob) if binf else sp.shifted(h, T(xk), nprob=nprob)
+    psi = sp.shifted(psi, T(sj))
+    y = torch.empty(n, dtype=T(q).dtype, device=DEV)
+    sp.prox_(y, psi, T(q), 1.0)
+    got = N(y)
+    check = sorted(set(special) | {0, 1, 2, nprob // 2, nprob - 2}) if pn > 20_000 else range(nprob)
+    for p in check:
+        s = slice(p * pn, (p + 1) * pn)
+        ref = orc.prox_indballl0(xk[s], sj[s], q[s], r, delta=1.0 if binf else None)
+        assert np.array_equal(got[s], ref, equal_nan=True), (p, special.get(p), np.flatnonzero(got[s] != ref)[:8])
+    # every problem keeps exactly r entries (NaN problems excepted: NaN != NaN in the support test below)
+    xs = (xk + sj).reshape(nprob, pn)
+    kept = (got.reshape(nprob, pn) != np.clip(dt(0) - xs, -1.0, 1.0)) if binf else (got.reshape(nprob, pn) != dt(0) - xs)
+    plain = [p for p in range(nprob) if p not in special]
+    assert np.all(kept[plain].sum(1) <= r)
+    if not binf:
+        assert np.all(kept[plain].sum(1) == r)

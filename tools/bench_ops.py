@@ -174,7 +174,7 @@ def main():
             timeit("prox_groupl2binf_g64_biglambda", lambda psi=psil: sp.prox_(y, psi, q, 0.3), 4 * R,
                    note="lambda_g x 200")
     # top-r batch: problems of 65536, r = 1024
-    if re.search(args.only, "prox_indballl0"):
+    if any(re.search(args.only, nm) for nm in ("prox_indballl0_batch", "prox_indballl0binf_batch", "prox_indballl0_single")):
         pn = 65536
         nprob = n // pn
         for binf in (False, True):
