@@ -157,6 +157,11 @@ int32_t spx_fill_uniform_f32(spx_ctx* ctx, float* out, int64_t n, int64_t i0, ui
  * mismatches_out[0]: branch-free sqrt vs sqrt();  [1]: reciprocal + two Markstein corrections vs a/d;
  * [2]: uniform-divisor quotient vs a/s.  All three must be 0. */
 int32_t spx_selftest_math(spx_ctx* ctx, int64_t n, uint64_t seed, int64_t* mismatches_out);
+/* Device self-test of the digit pick of the single-vector top-r path (spx_prox_indballl0_* with one long vector and
+ * its sharded form): hist_host holds 2048 counts, most significant digit first by bin index, possibly above 2^31;
+ * returns the bin that holds the need-th largest element and the number of elements in the bins above it. */
+int32_t spx_selftest_topr_pick(spx_ctx* ctx, const uint64_t* hist_host, int64_t need, int32_t* bin_out,
+                               int64_t* above_out);
 /* order-independent 64-bit checksum of a buffer's bits (Σ mix(word_i, i) mod 2^64),
  * identical to oracle.checksum(); used for full-size parity */
 int32_t spx_checksum(spx_ctx* ctx, const void* p, int64_t nwords64, uint64_t* out);
@@ -277,7 +282,9 @@ typedef struct spx_box_job_f32 {
                                    double delta);                                                \
   /* one vector spread over `world` GPUs in rank order (this rank holds n_local contiguous elements of */ \
   /* the n_global): the 2048-bin histogram of every radix digit goes through `reduce` (sum over ranks), */ \
-  /* then one vector of `world` tie counts; lowest global index wins ties, as on one GPU */             \
+  /* then one vector of `world` tie counts; lowest global index wins ties, as on one GPU.  reduce == NULL: */ \
+  /* the context's communicator (spx_comm_init, `world` ranks) all-reduces histograms and tie counts on */    \
+  /* the device, with no host staging */                                                                   \
   int32_t spx_prox_indballl0_sharded_##SUF(spx_ctx* ctx, int64_t n_local, int64_t n_global, R* y,       \
                                            const R* xk, const R* sj, const R* q, int64_t r,            \
                                            int32_t binf, double delta, int32_t rank, int32_t world,    \

@@ -34,6 +34,9 @@ struct NcclApi {
   ncclResult_t (*GetVersion)(int*) = nullptr;
 };
 
+static_assert((int)ncclInt64 == kNcclInt64 && (int)ncclUint64 == kNcclUint64 && (int)ncclFloat64 == kNcclFloat64 &&
+                  (int)ncclSum == kNcclSum && (int)ncclMax == kNcclMax,
+              "spx_common.cuh NCCL constants");
 static NcclApi g_nccl;
 static std::once_flag g_nccl_once;
 

@@ -263,6 +263,8 @@ bool comm_active(const spx_ctx* ctx);
 int32_t comm_neutral_result(spx_ctx* ctx, int nslot);
 int32_t comm_allreduce_result(spx_ctx* ctx, int nslot);
 int32_t comm_allreduce_raw(spx_ctx* ctx, void* buf, size_t count, int nccl_dtype, int nccl_op);
+// ncclDataType_t / ncclRedOp_t values (checked against nccl.h in spx_comm.cu), for callers that do not include nccl.h
+constexpr int kNcclInt64 = 4, kNcclUint64 = 5, kNcclFloat64 = 8, kNcclSum = 0, kNcclMax = 2;
 // enqueue only: fold `nblocks` partials at `partials` into *result on `stream`
 int32_t enqueue_fold(spx_ctx* ctx, cudaStream_t stream, const Partial* partials, int nblocks, Partial* result);
 

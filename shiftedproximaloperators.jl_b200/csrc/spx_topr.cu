@@ -108,6 +108,34 @@ template <int THREADS> __device__ __forceinline__ int block_excl_scan(int v, int
   return ws[w] + inc - v;
 }
 
+// the same scan on 64-bit counts (the histograms of a vector of >= 2^31 elements, or of one summed over 8 GPUs)
+template <int THREADS> __device__ __forceinline__ long long block_excl_scan64(long long v, long long* ws, long long* total) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  long long inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    long long t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  __syncthreads();  // ws reuse
+  if (lane == 31) ws[w] = inc;
+  __syncthreads();
+  if (w == 0) {
+    long long s = lane < (THREADS / 32) ? ws[lane] : 0;
+    long long sinc = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      long long t = __shfl_up_sync(0xffffffffu, sinc, o);
+      if (lane >= o) sinc += t;
+    }
+    ws[lane] = sinc - s;  // exclusive warp offsets
+    if (lane == 31) ws[32] = sinc;
+  }
+  __syncthreads();
+  *total = ws[32];
+  return ws[w] + inc - v;
+}
+
 struct TrShared {
   unsigned hist[kTrBins];
   unsigned tot[kTrBins];
@@ -919,7 +947,7 @@ __global__ void __launch_bounds__(256) topr_g_hist(const R* y, long long n, int 
 template <class R>
 __global__ void __launch_bounds__(kPickThreads) topr_g_pick(int pass, GlobalSel* st) {
   using KT = KeyTraits<R>;
-  __shared__ int ws[40];
+  __shared__ long long ws[40];
   __shared__ int sel_bin;
   __shared__ long long sel_above, sel_count;
   if (st->done) return;
@@ -927,14 +955,10 @@ __global__ void __launch_bounds__(kPickThreads) topr_g_pick(int pass, GlobalSel*
   const int width = digit_bits(KT::BITS, pass);
   const int b0 = kTrBins - 1 - 2 * t, b1 = b0 - 1;
   const long long c0 = (long long)st->hist[b0], c1 = (long long)st->hist[b1];
-  // counts can exceed int for huge n: scan in two 31-bit halves is overkill; clamp-free 64-bit scan
-  // via two int scans of the low / high parts
-  int total_lo, total_hi;
-  const long long s = c0 + c1;
-  const int lo = (int)(s & 0x3fffffff), hi = (int)(s >> 30);
-  const long long above_lo = block_excl_scan<kPickThreads>(lo, ws, &total_lo);
-  const long long above_hi = block_excl_scan<kPickThreads>(hi, ws, &total_hi);
-  const long long above = above_lo + (above_hi << 30);
+  // 64-bit scan: a bin of the first digit can hold every element of the vector (n_global >= 2^31 for a Float32
+  // vector on one B200, or for the histogram summed over the GPUs of a box)
+  long long total;
+  const long long above = block_excl_scan64<kPickThreads>(c0 + c1, ws, &total);
   const long long need = st->need;
   if (above < need && need <= above + c0) {
     sel_bin = b0; sel_above = above; sel_count = c0;
@@ -987,6 +1011,18 @@ __global__ void topr_g_scan(long long* block_eq, int nblocks, GlobalSel* st) {
       run += c;
     }
     st->eq_total = run;
+  }
+}
+
+// phase 0: slots[rr] = (rr == rank) ? this shard's threshold-equal count : 0;  phase 1 (after the sum over ranks):
+// eq_base = the counts of the lower-ranked shards
+__global__ void topr_g_rank_slot(long long* slots, int world, int rank, GlobalSel* st, int phase) {
+  if (phase == 0) {
+    for (int rr = threadIdx.x; rr < world; rr += blockDim.x) slots[rr] = rr == rank ? st->eq_total : 0;
+  } else if (threadIdx.x == 0) {
+    long long base = 0;
+    for (int rr = 0; rr < rank; ++rr) base += slots[rr];
+    st->eq_base = base;
   }
 }
 
@@ -1058,7 +1094,7 @@ static int32_t topr_global(spx_ctx* ctx, int64_t n, R* y, const R* xk, const R* 
   using KT = KeyTraits<R>;
   if (n_global < 0) n_global = n;
   const int nblk = ctx->sm_count * 8;
-  int32_t stt = ensure_scratch(ctx, sizeof(GlobalSel) + sizeof(long long) * (size_t)(nblk + 1));
+  int32_t stt = ensure_scratch(ctx, sizeof(GlobalSel) + sizeof(long long) * (size_t)(nblk + 1 + 64));
   if (stt != SPX_OK) return stt;
   GlobalSel* st = (GlobalSel*)ctx->d_scratch;
   long long* block_eq = (long long*)((char*)ctx->d_scratch + sizeof(GlobalSel));
@@ -1071,7 +1107,9 @@ static int32_t topr_global(spx_ctx* ctx, int64_t n, R* y, const R* xk, const R* 
   // sum the histogram over the shards (counts are exact in Float64 up to 2^53)
   std::vector<unsigned long long> hh;
   std::vector<double> hd;
+  const bool lib_comm = !reduce && world > 1;  // the communicator of the context: all-reduce on the device
   auto reduce_hist = [&]() -> int32_t {
+    if (lib_comm) return comm_allreduce_raw(ctx, st->hist, kTrBins, kNcclUint64, kNcclSum);
     if (!reduce) return SPX_OK;
     hh.resize(kTrBins);
     hd.resize(kTrBins);
@@ -1108,7 +1146,15 @@ static int32_t topr_global(spx_ctx* ctx, int64_t n, R* y, const R* xk, const R* 
     topr_g_eqcount<R><<<nblk, 256, 0, ctx->stream>>>(y, n, per_block, st, block_eq);
     topr_g_scan<<<1, 32, 0, ctx->stream>>>(block_eq, nblk, st);
     ctx->launches += 2;
-    if (reduce && world > 1) {
+    if (lib_comm) {
+      // exclusive prefix over ranks of the threshold-equal counts, on the device: one slot per rank, summed
+      long long* slots = block_eq + nblk + 1;
+      topr_g_rank_slot<<<1, 64, 0, ctx->stream>>>(slots, world, rank, st, 0);
+      int32_t st2 = comm_allreduce_raw(ctx, slots, (size_t)world, kNcclInt64, kNcclSum);
+      if (st2 != SPX_OK) return st2;
+      topr_g_rank_slot<<<1, 64, 0, ctx->stream>>>(slots, world, rank, st, 1);
+      ctx->launches += 2;
+    } else if (reduce && world > 1) {
       // exclusive prefix over ranks of the threshold-equal counts: all-reduce a vector with one slot per rank
       long long eq_total = 0;
       SPX_CUDA(cudaMemcpyAsync(&eq_total, &st->eq_total, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1284,6 +1330,30 @@ extern "C" int32_t spx_debug_topr_timing(unsigned long long* out8, int reset) {
   return 0;
 }
 #endif
+// Device self-test of the digit pick of the global path on a caller-supplied first-digit histogram (counts may
+// exceed 2^31): returns the bin holding the `need`-th largest element and the number of elements above that bin.
+extern "C" int32_t spx_selftest_topr_pick(spx_ctx* ctx, const uint64_t* hist_host, int64_t need, int32_t* bin_out,
+                                          int64_t* above_out) {
+  SPX_REQUIRE(ctx && hist_host && bin_out && above_out, "null argument");
+  DeviceGuard g(ctx->device);
+  int32_t st0 = ensure_scratch(ctx, sizeof(GlobalSel) + 4096);
+  if (st0 != SPX_OK) return st0;
+  GlobalSel* st = (GlobalSel*)ctx->d_scratch;
+  static GlobalSel init;
+  memset(&init, 0, sizeof(init));
+  for (int b = 0; b < kTrBins; ++b) init.hist[b] = hist_host[b];
+  init.need = need;
+  init.shift = KeyTraits<double>::BITS;
+  SPX_CUDA(cudaMemcpyAsync(st, &init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+  topr_g_pick<double><<<1, kPickThreads, 0, ctx->stream>>>(0, st);
+  ctx->launches++;
+  SPX_CUDA(cudaGetLastError());
+  SPX_CUDA(cudaMemcpyAsync(&init, st, sizeof(init), cudaMemcpyDeviceToHost, ctx->stream));
+  SPX_CUDA(cudaStreamSynchronize(ctx->stream));
+  *bin_out = (int32_t)init.prefix;
+  *above_out = need - init.need;
+  return SPX_OK;
+}
 extern "C" int32_t spx_prox_indballl0_f64(spx_ctx* ctx, int64_t nprob, int64_t n, double* y, const double* xk,
                                           const double* sj, const double* q, int64_t r, int32_t binf, double delta) {
   return prox_indballl0<double>(ctx, nprob, n, y, xk, sj, q, r, binf, delta);
@@ -1295,7 +1365,8 @@ extern "C" int32_t spx_prox_indballl0_sharded_f64(spx_ctx* ctx, int64_t n_local,
   SPX_REQUIRE(ctx != nullptr, "null context");
   SPX_REQUIRE(n_local >= 0 && n_global >= n_local && world >= 1 && rank >= 0 && rank < world, "bad shard description");
   SPX_REQUIRE(n_local == 0 || (y && xk && sj && q), "null device vector");
-  SPX_REQUIRE(world == 1 || reduce != nullptr, "a sharded vector needs the all-reduce callback");
+  SPX_REQUIRE(world == 1 || reduce != nullptr || (ctx->comm != nullptr && ctx->comm_nranks == world),
+              "a sharded vector needs the all-reduce callback or a communicator (spx_comm_init) of `world` ranks");
   DeviceGuard g(ctx->device);
   return topr_global<double>(ctx, n_local, y, xk, sj, q, r, binf != 0, delta, n_global, rank, world, reduce, user);
 }
@@ -1306,7 +1377,8 @@ extern "C" int32_t spx_prox_indballl0_sharded_f32(spx_ctx* ctx, int64_t n_local,
   SPX_REQUIRE(ctx != nullptr, "null context");
   SPX_REQUIRE(n_local >= 0 && n_global >= n_local && world >= 1 && rank >= 0 && rank < world, "bad shard description");
   SPX_REQUIRE(n_local == 0 || (y && xk && sj && q), "null device vector");
-  SPX_REQUIRE(world == 1 || reduce != nullptr, "a sharded vector needs the all-reduce callback");
+  SPX_REQUIRE(world == 1 || reduce != nullptr || (ctx->comm != nullptr && ctx->comm_nranks == world),
+              "a sharded vector needs the all-reduce callback or a communicator (spx_comm_init) of `world` ranks");
   DeviceGuard g(ctx->device);
   return topr_global<float>(ctx, n_local, y, xk, sj, q, r, binf != 0, (float)delta, n_global, rank, world, reduce,
                             user);

@@ -250,10 +250,16 @@ def prox_indballl0_sharded_(y_local, psi, q_local, n_global: int, group=None):
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     world = dist.get_world_size(group) if dist.is_initialized() else 1
 
-    cb = L.ALLREDUCE_FN(_make_reduce(dev, group))
     binf = isinstance(psi, ShiftedIndBallL0BInf)
+    # a communicator on the context (comm_init): histograms and tie counts are all-reduced on the device (NULL callback)
+    in_library = world > 1 and comm_info(dev)[0] == world
+    if in_library:
+        cb = C.cast(None, L.ALLREDUCE_FN)
+    elif world > 1:
+        cb = L.ALLREDUCE_FN(_make_reduce(dev, group))
+    else:
+        cb = L.ALLREDUCE_FN(lambda u, v, c: 0)
     psi._call("prox_indballl0_sharded", C.c_int64(psi.n), C.c_int64(n_global), _p(y_local), _p(psi.xk), _p(psi.sj),
               _p(q_local), C.c_int64(psi.h.r), C.c_int32(1 if binf else 0),
-              C.c_double(psi.Delta if binf else 0.0), C.c_int32(rank), C.c_int32(world),
-              cb if world > 1 else L.ALLREDUCE_FN(lambda u, v, c: 0), None)
+              C.c_double(psi.Delta if binf else 0.0), C.c_int32(rank), C.c_int32(world), cb, None)
     return y_local

@@ -946,3 +946,26 @@ def test_indballl0_batch_stream_form(dt, pn, r, binf):
     assert np.all(kept[plain].sum(1) <= r)
     if not binf:
         assert np.all(kept[plain].sum(1) == r)
+
+
+def test_topr_digit_pick_with_counts_above_2p31():
+    """The digit pick of the single-vector path scans 64-bit counts (a first-digit bin can hold every element of a
+    vector of >= 2^31 elements, or of the histogram summed over the GPUs of a box)."""
+    import ctypes as C
+    from shiftedprox import _lib as L
+
+    rng = np.random.default_rng(5)
+    hist = np.zeros(2048, np.uint64)
+    hist[2047] = 3_000_000_000  # > 2^31 in the top bin
+    hist[2040] = 5_000_000_000
+    hist[1000:1010] = rng.integers(1, 1 << 33, size=10).astype(np.uint64)
+    hist[3] = 7
+    cum = np.cumsum(hist[::-1].astype(object))  # counts from the top bin down
+    for need in (1, 2_999_999_999, 3_000_000_000, 3_000_000_001, 8_000_000_000, int(cum[-1]) - 3, int(cum[-1])):
+        k = int(np.searchsorted(np.array([int(c) for c in cum], dtype=object), need, side="left"))
+        want_bin = 2047 - k
+        want_above = int(cum[k - 1]) if k > 0 else 0
+        b, a = C.c_int32(), C.c_int64()
+        L.call("spx_selftest_topr_pick", sp.context(DEV), hist.ctypes.data_as(C.c_void_p), C.c_int64(need), C.byref(b),
+               C.byref(a))
+        assert (b.value, a.value) == (want_bin, want_above), (need, b.value, a.value, want_bin, want_above)

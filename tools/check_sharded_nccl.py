@@ -138,6 +138,11 @@ def main():
         sp.prox_(ysh, gs, q, 0.3)
         gdiff = float((ysh - yf[lo:hi]).abs().max())
         lib_ok &= gdiff <= 8 * torch.finfo(dtype).eps * 8.0
+        # single-vector top-r: histograms and tie counts all-reduced by the library's communicator (no callback)
+        sp.prox_(yf, pf, qq, 1.0)
+        yt2 = torch.empty_like(q)
+        sharded.prox_indballl0_sharded_(yt2, ps, qq[lo:hi].clone(), n)
+        lib_ok &= bool(torch.equal(yt2, yf[lo:hi]))
         ncoll = sharded.comm_info(dev)[2] - c0
         sharded.reduce_scalars(False, dev)
         ok &= lib_ok
