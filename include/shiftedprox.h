@@ -358,6 +358,28 @@ typedef struct spx_box_job_f32 {
 SPX_DECL_SEPARABLE(f64, double)
 SPX_DECL_SEPARABLE(f32, float)
 
+/* ---- thresholding stage of the spectral operators, GIVEN an SVD ----------------------------
+ * ShiftedRank / ShiftedNuclearnorm / ShiftedCappedl1 prox! (shiftedRank.jl:68-84, shiftedNuclearnorm.jl:68-81,
+ * shiftedCappedl1.jl:68-86):  sol = q + xk + sj;  U, S, Vt = svd(reshape(sol));  S' = threshold(S);  U[:, i] *= S'_i;
+ * A = U * Vt;  y = reshape(A) - (xk + sj).  The SVD (LAPACK in the reference) and the GEMM (`mul!`) stay library
+ * calls on the caller's side (cuSOLVER / cuBLAS); these three entry points are the stages around them.
+ *   kind 0 Rank:        column i zeroed where S_i <= sqrt(2 lambda sigma), scaled by S_i elsewhere (S untouched)
+ *   kind 1 Nuclearnorm: S_i = max(0, S_i - lambda sigma), column scaled by it
+ *   kind 2 Cappedl1:    S_i = the better of max(theta, S_i) and min(theta, max(0, S_i - lambda sigma)) (:72-77)
+ * u: m x k column-major, leading dimension ldu; s: k singular values (overwritten for kinds 1, 2 like ψ.h.F.S). */
+#define SPX_SPECTRAL_RANK 0
+#define SPX_SPECTRAL_NUCLEAR 1
+#define SPX_SPECTRAL_CAPPEDL1 2
+#define SPX_DECL_SPECTRAL(SUF, R)                                                                               \
+  /* a_out = (q + xk) + sj   (`ψ.sol .= q .+ ψ.xk .+ ψ.sj`, shiftedRank.jl:69) */                               \
+  int32_t spx_spectral_sol_##SUF(spx_ctx* ctx, int64_t n, R* a_out, const R* xk, const R* sj, const R* q);     \
+  int32_t spx_spectral_threshold_##SUF(spx_ctx* ctx, int32_t kind, int64_t m, int64_t k, R* u, int64_t ldu,    \
+                                       R* s, double lambda, double sigma, double theta);                       \
+  /* y = a - (xk + sj)   (shiftedRank.jl:82) */                                                                 \
+  int32_t spx_spectral_finish_##SUF(spx_ctx* ctx, int64_t n, R* y, const R* a, const R* xk, const R* sj);
+SPX_DECL_SPECTRAL(f64, double)
+SPX_DECL_SPECTRAL(f32, float)
+
 /* scalar helpers, exported for the glue's unit tests:
  * prox_zero  ShiftedProximalOperators.jl:203, iprox_zero :217-236 */
 double spx_prox_zero_f64(double q, double l, double u);

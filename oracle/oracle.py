@@ -304,3 +304,42 @@ def uniform(n, stream, dtype=np.float64, scale=1.0, shift=0.0, i0=0, seed=SEED):
     _call(f"orc_fill_uniform_{s}", None, _p(out), i64(n), i64(i0), C.c_uint64(seed), C.c_uint64(stream),
           ft(scale), ft(shift))
     return out
+
+
+# ------------------------------------------ spectral thresholding stage ---
+def spectral_threshold(kind, U, S, lam, sigma, theta=0.0):
+    """The stage between the SVD and the `mul!` of ShiftedRank / ShiftedNuclearnorm / ShiftedCappedl1 prox!, in the
+    element type of S (numpy restatement; the SVD itself is LAPACK in the reference and out of scope):
+      "rank"     shiftedRank.jl:72-80         c = sqrt(2λσ); S_i <= c -> U[:, i] = 0, else U[:, i] *= S_i (S untouched)
+      "nuclear"  shiftedNuclearnorm.jl:72-77  S = max.(0, S .- λσ); U[:, i] *= S_i
+      "cappedl1" shiftedCappedl1.jl:71-82     x1 = max(θ, S_i); x2 = min(θ, max(0, S_i - λσ));
+                                              S_i = ((x1-S_i)^2/2 + λσθ < (x2-S_i)^2/2 + λσ x2) ? x1 : x2; U[:, i] *= S_i
+    Returns (U', S')."""
+    dt = S.dtype.type
+    U = np.array(U, dtype=dt, copy=True)
+    S = np.array(S, dtype=dt, copy=True)
+    lam, sigma, theta = dt(lam), dt(sigma), dt(theta)
+    if kind == "rank":
+        c = np.sqrt(dt(2) * lam * sigma)
+        for i in range(S.size):
+            if S[i] <= c:
+                U[:, i] = 0
+            else:
+                U[:, i] = U[:, i] * S[i]
+    elif kind == "nuclear":
+        S = np.maximum(dt(0), S - lam * sigma).astype(dt)
+        for i in range(S.size):
+            U[:, i] = U[:, i] * S[i]
+    elif kind == "cappedl1":
+        for i in range(S.size):
+            x1 = max(theta, S[i])
+            x2 = min(theta, max(dt(0), S[i] - lam * sigma))
+            d1, d2 = dt(x1 - S[i]), dt(x2 - S[i])
+            if dt(d1 * d1) / dt(2) + lam * sigma * theta < dt(d2 * d2) / dt(2) + lam * sigma * x2:
+                S[i] = x1
+            else:
+                S[i] = x2
+            U[:, i] = U[:, i] * S[i]
+    else:
+        raise ValueError(kind)
+    return U, S

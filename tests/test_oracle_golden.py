@@ -288,3 +288,24 @@ def test_float32_lhalf_promotions():
             coef = np.float32(2) * np.float32(np.sign(z[i])) / np.float32(3) * np.float32(abs(z[i]))
             exp = np.float32(float(coef) * (1 + np.cos(2 * np.pi / 3 - 2 * phi / 3))) - x[i]
         assert abs(float(y[i]) - float(exp)) <= 2 * np.spacing(np.float32(abs(exp)))
+
+
+def test_spectral_stage_matches_the_reference_identities():
+    """runtests.jl:945-946,963-964 (Rank: the thresholded singular values are NormL0's prox of S),
+    :1163-1164,1181-1182 (Nuclearnorm: NormL1's prox of S), :1064-1066 (Cappedl1, θ = 1, λ = 10 on a diagonal with
+    entries in [0, 1.75): NormL0's prox as well).  The oracle's stage scales column i of U by exactly that value."""
+    rng = np.random.default_rng(0)
+    for lam, gamma in ((10.0, 10.0), (1.0, 5.0)):
+        S = np.sort(rng.random(11) * (20.0 if lam == 10.0 else 8.0))[::-1].copy()
+        U = np.eye(11)
+        hard = np.where(np.abs(S) > np.sqrt(2 * lam * gamma), S, 0.0)  # prox of λ‖·‖₀ with step γ
+        soft = np.sign(S) * np.maximum(np.abs(S) - lam * gamma, 0.0)  # prox of λ‖·‖₁
+        Ur, Sr = orc.spectral_threshold("rank", U, S, lam, gamma)
+        assert np.array_equal(np.diag(Ur), hard) and np.array_equal(Sr, S)
+        Un, Sn = orc.spectral_threshold("nuclear", U, S, lam, gamma)
+        assert np.array_equal(np.diag(Un), soft) and np.array_equal(Sn, soft)
+    st1 = rng.random(10)
+    S = st1 + st1 ** 2 + st1 / 2  # the diagonal of runtests.jl:1056-1066, all below sqrt(2·10·10)
+    Uc, Sc = orc.spectral_threshold("cappedl1", np.eye(10), S, 10.0, 10.0, theta=1.0)
+    assert np.array_equal(Sc, np.where(np.abs(S) > np.sqrt(2 * 10.0 * 10.0), S, 0.0))
+    assert np.array_equal(np.diag(Uc), Sc)
