@@ -162,6 +162,11 @@ int32_t spx_selftest_math(spx_ctx* ctx, int64_t n, uint64_t seed, int64_t* misma
  * returns the bin that holds the need-th largest element and the number of elements in the bins above it. */
 int32_t spx_selftest_topr_pick(spx_ctx* ctx, const uint64_t* hist_host, int64_t need, int32_t* bin_out,
                                int64_t* above_out);
+/* GroupNormL2's constructor checks (groupNormL2.jl:20-23) for the device layout: offs (device int64, ngroups + 1 entries)
+ * must start at 0, never decrease and end at n; SPX_E_INVALID otherwise.  Call once when ψ is built: the prox!/ψ(y)
+ * entry points trust the offsets.  Index sets that are not contiguous ranges in order (the reference accepts any
+ * `idx`) cannot be expressed as CSR offsets: the host layer rejects them at construction. */
+int32_t spx_group_validate_offsets(spx_ctx* ctx, int64_t n, int64_t ngroups, const int64_t* offs);
 /* order-independent 64-bit checksum of a buffer's bits (Σ mix(word_i, i) mod 2^64),
  * identical to oracle.checksum(); used for full-size parity */
 int32_t spx_checksum(spx_ctx* ctx, const void* p, int64_t nwords64, uint64_t* out);

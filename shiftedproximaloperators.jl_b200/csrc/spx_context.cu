@@ -314,6 +314,16 @@ int32_t spx_ctx_set_stream(spx_ctx* c, void* stream) {
     cudaStreamDestroy(c->stream);
     c->owns_stream = false;
   }
+  // The reduction scratch (d_partials, d_result, h_result, d_scratch) is shared by every call of the context: work still
+  // queued on the old stream must finish before anything enqueued on the new one touches it.
+  if ((cudaStream_t)stream != c->stream) {
+    DeviceGuard g(c->device);
+    cudaEvent_t ev;
+    SPX_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    SPX_CUDA(cudaEventRecord(ev, c->stream));
+    SPX_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, ev, 0));
+    SPX_CUDA(cudaEventDestroy(ev));
+  }
   c->stream = (cudaStream_t)stream;
   return SPX_OK;
 }

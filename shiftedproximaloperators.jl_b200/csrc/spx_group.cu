@@ -1585,6 +1585,38 @@ extern "C" int32_t spx_debug_group_stats(unsigned long long* out2, int reset) {
 }
 #endif
 
+// GroupNormL2's constructor checks (groupNormL2.jl:20-23) extended to the device layout: the CSR offsets must start at
+// 0, never decrease and end at n -- anything else would make the group kernels read and write out of bounds.
+__global__ void __launch_bounds__(256) group_validate_kernel(const long long* __restrict__ offs, long long ngroups,
+                                                             long long n, unsigned* bad) {
+  bool b = false;
+  for (long long g = (long long)blockIdx.x * 256 + threadIdx.x; g < ngroups; g += (long long)gridDim.x * 256)
+    b = b || (offs[g] > offs[g + 1]) || (offs[g] < 0);
+  if (blockIdx.x == 0 && threadIdx.x == 0) b = b || (offs[0] != 0) || (offs[ngroups] != n);
+  if (__syncthreads_or(b) && threadIdx.x == 0) *bad = 1u;
+}
+extern "C" int32_t spx_group_validate_offsets(spx_ctx* ctx, int64_t n, int64_t ngroups, const int64_t* offs) {
+  SPX_REQUIRE(ctx != nullptr, "null context");
+  SPX_REQUIRE(n >= 0 && ngroups >= 0, "negative size");
+  SPX_REQUIRE(offs != nullptr, "null offsets");
+  DeviceGuard g(ctx->device);
+  int32_t st = ensure_scratch(ctx, 4096);
+  if (st != SPX_OK) return st;
+  unsigned* flag = (unsigned*)ctx->d_scratch;
+  SPX_CUDA(cudaMemsetAsync(flag, 0, sizeof(unsigned), ctx->stream));
+  const int grid = (int)std::min<int64_t>((ngroups + 256) / 256, (int64_t)ctx->sm_count * 8);
+  group_validate_kernel<<<grid, 256, 0, ctx->stream>>>((const long long*)offs, ngroups, n, flag);
+  ctx->launches++;
+  unsigned h = 0;
+  SPX_CUDA(cudaMemcpyAsync(&h, flag, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+  SPX_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (h != 0) {
+    set_error("group offsets must start at 0, be non-decreasing and end at n = %lld", (long long)n);
+    return SPX_E_INVALID;
+  }
+  return SPX_OK;
+}
+
 #define SPX_DEFINE_GROUP(SUF, R)                                                                                 \
   extern "C" int32_t spx_prox_groupl2_##SUF(spx_ctx* ctx, int64_t n, R* y, const R* xk, const R* sj, const R* q, \
                                             int64_t ngroups, const int64_t* offs, const R* lambda_g,             \

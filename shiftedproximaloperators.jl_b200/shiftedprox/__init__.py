@@ -562,6 +562,12 @@ class _GroupBase(ShiftedProximableFunction):
         self.ngroups = self._offs.numel() - 1
         if self._lam_g.numel() != self.ngroups:
             raise ValueError("number of weights and groups should be the same")
+        if h.offsets is not None:  # caller-supplied device offsets: checked once here, trusted by the kernels afterwards
+            try:
+                L.call("spx_group_validate_offsets", context(dev), C.c_int64(xk.numel()), C.c_int64(self.ngroups),
+                       _p(self._offs))
+            except SpxError as e:
+                raise ValueError(str(e)) from None
         return h
 
     @property

@@ -89,3 +89,19 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".jl")):
                 text = open(os.path.join(dirpath, f), encoding="utf-8").read()
                 assert "liboracle" not in text and "from oracle" not in text and "import oracle" not in text, f
+
+
+def test_group_index_sets_must_be_contiguous_ranges():
+    """The reference's GroupNormL2 accepts any index collection per group (groupNormL2.jl:15-31); the device layout is
+    CSR offsets, so the host layer rejects anything that is not a partition of the vector into contiguous ranges in
+    order -- at construction, loudly (documented in DESIGN.md §7 and include/shiftedprox.h)."""
+    import pytest
+    import shiftedprox as sp
+
+    sp.GroupNormL2([1.0, 2.0], [range(0, 3), range(3, 6)])  # fine
+    with pytest.raises(ValueError, match="contiguous ranges"):
+        sp.GroupNormL2([1.0, 2.0], [range(0, 3), range(4, 6)])  # gap
+    with pytest.raises(ValueError, match="contiguous ranges"):
+        sp.GroupNormL2([1.0, 2.0], [range(3, 6), range(0, 3)])  # out of order
+    with pytest.raises(ValueError, match="same"):
+        sp.GroupNormL2([1.0], [range(0, 3), range(3, 6)])

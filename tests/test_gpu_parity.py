@@ -969,3 +969,15 @@ def test_topr_digit_pick_with_counts_above_2p31():
         L.call("spx_selftest_topr_pick", sp.context(DEV), hist.ctypes.data_as(C.c_void_p), C.c_int64(need), C.byref(b),
                C.byref(a))
         assert (b.value, a.value) == (want_bin, want_above), (need, b.value, a.value, want_bin, want_above)
+
+
+def test_group_offsets_are_validated_at_construction():
+    """Device CSR offsets handed to GroupNormL2(offsets=...) are checked once when ψ is built (start at 0, monotone, end at n):
+    the kernels trust them afterwards."""
+    n = 1000
+    x = T(np.zeros(n))
+    good = T(np.array([0, 10, 10, 500, n], np.int64))
+    sp.shifted(sp.GroupNormL2(T(np.ones(4)), None, offsets=good), x)
+    for bad in ([1, 10, 500, n], [0, 600, 500, n], [0, 10, 500, n + 5], [0, 10, 500, n - 1]):
+        with pytest.raises(ValueError, match="offsets"):
+            sp.shifted(sp.GroupNormL2(T(np.ones(3)), None, offsets=T(np.array(bad, np.int64))), x)
