@@ -308,15 +308,17 @@ int32_t spx_ctx_destroy(spx_ctx* c) {
 
 int32_t spx_ctx_set_stream(spx_ctx* c, void* stream) {
   SPX_REQUIRE(c != nullptr, "null context");
+  bool drained = false;
   if (c->owns_stream) {
     DeviceGuard g(c->device);
     cudaStreamSynchronize(c->stream);
     cudaStreamDestroy(c->stream);
     c->owns_stream = false;
+    drained = true;  // nothing left on the old stream (which no longer exists)
   }
   // The reduction scratch (d_partials, d_result, h_result, d_scratch) is shared by every call of the context: work still
   // queued on the old stream must finish before anything enqueued on the new one touches it.
-  if ((cudaStream_t)stream != c->stream) {
+  if (!drained && (cudaStream_t)stream != c->stream) {
     DeviceGuard g(c->device);
     cudaEvent_t ev;
     SPX_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
