@@ -326,112 +326,141 @@ static int32_t prox_l1b2(spx_ctx* ctx, int64_t n, R* y, const R* xk, const R* sj
     return SPX_OK;
   };
 
-  std::vector<R> f, df, pts(1, delta);
-  int32_t st = eval(pts, false, f, df);  // ‖ProjB(-xk)‖  (:56-58); also the residual and slope at η = Δ
+  // ---- the search -----------------------------------------------------------------------------------------------
+  // The residual f(η) = η - χ(ProjB(-xk η/Δ)) is C¹ and increasing; every pass returns f and f' at up to four trial
+  // values.  Pass 0 is a ladder Δ·{1, 2, 4, 16}: f(Δ) decides whether the ball is active (:58), the ladder brackets
+  // the root.  Every further pass evaluates a cluster around the root x̂ of the cubic Hermite interpolant of f on the
+  // current bracket, x̂ - e, x̂, x̂ + e and one point 3e out on the wider side, e = 2^-6 of the bracket for the first
+  // cluster and 2^-16 afterwards (what the interpolant's error leaves: for large n, A(η) and B(η) of
+  // ||·||² = (η/Δ)² A + B are smooth up to the granularity of single entries changing side).  The search ends on an
+  // evaluated point with |f| <= 4 ulp(η), on an exact zero, or on two adjacent floats around the sign change (Roots'
+  // end state); when the bracket is already narrower than the interpolant is accurate to an ulp, the FINISH pass takes
+  // x̂ unevaluated and doubles as its check -- it returns Σ(sj + y)² = (||w|| Δ/η)², i.e. the residual at x̂ -- which
+  // saves one pass over the vector; a failed check (never observed) re-enters the search.
+  struct Pt { R x, f, d; };
+  std::vector<Pt> known;
+  std::vector<R> f, df, pts;
+  for (double m : {1.0, 2.0, 4.0, 16.0}) {
+    const R x = delta * (R)m;
+    if (std::isfinite(x) && (pts.empty() || x > pts.back())) pts.push_back(x);
+  }
+  int32_t st = eval(pts, true, f, df);  // η = Δ: scale 1, i.e. ||ProjB(-xk)|| itself (:56-58)
   if (st != SPX_OK) return st;
   // f[0] = Δ - χ(y); the reference tests Δ <= χ(y)  (:58) -- the sign of a difference is exact
   if (!(f[0] <= R(0))) return finish(false, R(1), R(1));
-  R a = delta, fa = f[0], da = df[0], b = a, fb = fa, db = da;
-  R eta = a;
-  auto ulps_between = [](R lo, R hi) -> long long {  // representable numbers strictly inside (lo, hi), 0 < lo < hi
-    if (sizeof(R) == 8) {
-      long long x, y;
-      double l = (double)lo, h = (double)hi;
-      memcpy(&x, &l, 8);
-      memcpy(&y, &h, 8);
-      return y - x - 1;
+  for (size_t k = 0; k < pts.size(); ++k) known.push_back({pts[k], f[k], df[k]});
+  auto ulp_of = [](R x) -> R { return std::nextafter(x, std::numeric_limits<R>::infinity()) - x; };
+  auto hermite_root = [](R a, R fa, R da, R b, R fb, R db) -> R {  // root of the cubic Hermite interpolant in (a, b)
+    const double h = (double)b - (double)a;
+    auto p = [&](double x) {
+      const double t = (x - (double)a) / h, t2 = t * t, t3 = t2 * t;
+      return (2 * t3 - 3 * t2 + 1) * (double)fa + (t3 - 2 * t2 + t) * h * (double)da + (-2 * t3 + 3 * t2) * (double)fb +
+             (t3 - t2) * h * (double)db;
+    };
+    double lo = (double)a, hi = (double)b;
+    for (int it = 0; it < 200; ++it) {
+      const double mid = 0.5 * (lo + hi);
+      if (!(lo < mid && mid < hi)) break;
+      if ((p(mid) < 0.0) == ((double)fa < 0.0)) lo = mid;
+      else hi = mid;
     }
-    int x, y;
-    float l = (float)lo, h = (float)hi;
-    memcpy(&x, &l, 4);
-    memcpy(&y, &h, 4);
-    return (long long)y - x - 1;
+    return (R)(0.5 * (lo + hi));
   };
-  // scan evaluated points (ascending, strictly inside the bracket): the residual is increasing, so the
-  // bracket becomes the first sign change
-  auto absorb = [&](const std::vector<R>& p, bool& have_b, bool& exact) {
-    for (size_t k = 0; k < p.size(); ++k) {
-      if (f[k] == R(0)) { eta = p[k]; exact = true; return; }
-      if (f[k] < R(0)) { a = p[k]; fa = f[k]; da = df[k]; }
-      else { b = p[k]; fb = f[k]; db = df[k]; have_b = true; return; }
+  R eta = delta;
+  int clusters = 0;
+  bool unverified_ok = can_stash;  // a failed check re-reads q, which must not have been overwritten by y
+  R b0 = std::max(R(2) * pts.back(), pts.back() + R(1));
+  for (;;) {
+    // bracket = the largest evaluated point with f < 0 and the smallest with f > 0 (f is increasing)
+    const Pt *pa = nullptr, *pb = nullptr, *pz = nullptr, *best = &known[0];
+    for (const Pt& k : known) {
+      if (k.f == R(0)) pz = &k;
+      if (k.f < R(0) && (!pa || k.x > pa->x)) pa = &k;
+      if (k.f > R(0) && (!pb || k.x < pb->x)) pb = &k;
+      if (std::fabs(k.f) < std::fabs(best->f)) best = &k;
     }
-  };
-  if (fa != R(0)) {
-    bool have_b = false, exact = false;
-    // bracket: a Newton step from a (the residual is convex there in practice, so it lands just past the
-    // root) next to the reference's own guesses max(2a, a+1) 2^k
-    R b0 = std::max(R(2) * a, a + R(1));
-    while (!have_b && !exact) {
+    if (pz) { eta = pz->x; break; }
+    if (!pa || passes > 200) {
+      set_error("spx_prox_l1b2: no sign change of the trust-region residual");
+      return SPX_E_NOROOT;
+    }
+    if (!pb) {  // the ladder did not reach the root: the reference's own guesses max(2a, a+1) 4^k, and a Newton point
       pts.clear();
-      const R xn = (da > R(0)) ? a - fa / da : std::numeric_limits<R>::infinity();
-      if (std::isfinite(xn) && xn > a) {
+      const R xn = (pa->d > R(0)) ? pa->x - pa->f / pa->d : std::numeric_limits<R>::infinity();
+      if (std::isfinite(xn) && xn > pa->x) {
         pts.push_back(xn);
-        pts.push_back(xn + (xn - a) / R(16));
-        pts.push_back(xn + (xn - a));
+        pts.push_back(xn + (xn - pa->x));
       }
-      for (int k = 0; k < 4; ++k) pts.push_back(b0 * (R)std::ldexp(1.0, 2 * k));
+      for (int k = 0; k < 2; ++k) pts.push_back(b0 * (R)std::ldexp(1.0, 2 * k));
+      b0 = b0 * R(16);
       std::sort(pts.begin(), pts.end());
       pts.erase(std::unique(pts.begin(), pts.end()), pts.end());
-      while (!pts.empty() && !std::isfinite(pts.back())) pts.pop_back();
-      if (pts.empty()) {
+      while (!pts.empty() && !(std::isfinite(pts.back()) && pts.back() > pa->x)) pts.pop_back();
+      std::vector<R> in;
+      for (R x : pts)
+        if (x > pa->x) in.push_back(x);
+      if (in.empty()) {
         set_error("spx_prox_l1b2: no sign change of the trust-region residual");
         return SPX_E_NOROOT;
       }
-      st = eval(pts, true, f, df);
-      if (st != SPX_OK) return st;
-      absorb(pts, have_b, exact);
-      if (!have_b && !exact) {
-        b0 = R(2) * a;
-        if (!std::isfinite(b0) || passes > 200) {
-          set_error("spx_prox_l1b2: no sign change of the trust-region residual");
-          return SPX_E_NOROOT;
-        }
-      }
-    }
-    if (!exact) eta = b;
-    exact = exact || (fb == R(0));
-    bool slow = false;
-    while (!exact) {
-      const R mid = a + (b - a) / R(2);
-      if (!(a < mid && mid < b)) break;
-      const R w = b - a;
-      const long long inside = ulps_between(a, b);
-      pts.clear();
-      if (inside <= 8) {  // last pass: every float left in the bracket
-        R x = a;
-        for (long long k = 0; k < inside; ++k) {
-          x = std::nextafter(x, b);
-          pts.push_back(x);
-        }
-      } else if (slow) {  // poor shrink: section uniformly
-        for (int k = 1; k <= 8; ++k) pts.push_back(a + w * ((R)k / (R)9));
-      } else {
-        // secant point and the Newton points of both ends, each with a neighbour one estimated error
-        // further out, so that the next bracket is as tight as the estimates agree
-        const R xs = a - fa * (w / (fb - fa));
-        const R xa = (da > R(0)) ? a - fa / da : mid;
-        const R xb = (db > R(0)) ? b - fb / db : mid;
-        const R best = (std::fabs(fa) <= std::fabs(fb)) ? xa : xb;
-        R err = std::max(std::fabs(best - xs), std::fabs(xa - xb));
-        err = std::max(err, R(4) * (std::nextafter(best, b) - best));
-        // four trial points keep the pass HBM-bound (eight are FP64-issue bound)
-        const R c[4] = {xs, best, best - err, best + err};
-        for (R x : c) pts.push_back(x);
-      }
-      std::sort(pts.begin(), pts.end());
-      std::vector<R> in;
-      for (R x : pts)
-        if (x > a && x < b && (in.empty() || x > in.back())) in.push_back(x);
-      if (in.empty()) in.push_back(mid);
-      if ((int)in.size() > 8) in.resize(8);
       st = eval(in, true, f, df);
       if (st != SPX_OK) return st;
-      bool hb = true;
-      absorb(in, hb, exact);
-      slow = !((b - a) <= w / R(8));
-      if (passes > 200) break;
+      for (size_t k = 0; k < in.size(); ++k) known.push_back({in[k], f[k], df[k]});
+      continue;
     }
-    if (!exact) eta = (std::fabs(fa) <= std::fabs(fb)) ? a : b;
+    const R a = pa->x, b = pb->x;
+    if (std::fabs(best->f) <= R(4) * ulp_of(best->x)) { eta = best->x; break; }
+    const R mid = a + (b - a) / R(2);
+    if (!(a < mid && mid < b)) {  // adjacent floats around the sign change
+      eta = (std::fabs(pa->f) <= std::fabs(pb->f)) ? a : b;
+      break;
+    }
+    R xh = hermite_root(a, pa->f, pa->d, b, pb->f, pb->d);
+    if (!(xh > a && xh < b)) xh = mid;
+    const R width = b - a;
+    // bracket narrow enough for the interpolant to be good to an ulp: x̂ goes to the finish pass, which checks it
+    const R narrow = (sizeof(R) == 8 ? R(1e-6) : R(2e-4)) * a;
+    if (unverified_ok && clusters >= 1 && width <= narrow) {
+      double s = 0.0, s2 = 0.0;
+      const R scale = xh / delta, post = delta / xh;
+      st = finish_pass<R>(ctx, n, y, xk, sj, q, ls, true, scale, post, &s, &s2, stashed);
+      if (st != SPX_OK) return st;
+      ++passes;
+      stashed = false;  // y now holds the result, not sj + q
+      if (reduce) {
+        double v[2] = {s, s2};
+        st = reduce(user, v, 2);
+        if (st != SPX_OK) return st;
+        s = v[0];
+        s2 = v[1];
+      }
+      // ||w|| = ||sj + y|| η/Δ;  f(x̂) = x̂ - χ ||w||
+      const R nw = (R)(std::sqrt(s2) * ((double)xh / (double)delta));
+      const R fx = xh - chil * nw;
+      if (std::fabs(fx) <= R(8) * ulp_of(xh)) {
+        if (passes_out) *passes_out = passes;
+        if (psi_out)
+          *psi_out = in_ball_l2<R>((R)std::sqrt(s2), delta) ? (double)(lam * (R)s) : std::numeric_limits<double>::infinity();
+        return SPX_OK;
+      }
+      unverified_ok = false;  // re-enter the search with what the check measured (slope unknown: reuse the nearer end's)
+      known.push_back({xh, fx, (xh - a < b - xh) ? pa->d : pb->d});
+      continue;
+    }
+    const int kbits = clusters == 0 ? 6 : 16;
+    R e = std::max(R(4) * ulp_of(xh), width * (R)std::ldexp(1.0, -kbits));
+    const R far = (b - xh > xh - a) ? xh + R(3) * e : xh - R(3) * e;
+    const R cand[4] = {xh - e, xh, xh + e, far};
+    pts.assign(cand, cand + 4);
+    std::sort(pts.begin(), pts.end());
+    std::vector<R> in;
+    for (R x : pts)
+      if (x > a && x < b && (in.empty() || x > in.back())) in.push_back(x);
+    if (in.empty()) in.push_back(mid);
+    st = eval(in, true, f, df);
+    if (st != SPX_OK) return st;
+    for (size_t k = 0; k < in.size(); ++k) known.push_back({in[k], f[k], df[k]});
+    ++clusters;
   }
   return finish(true, eta / delta, delta / eta);
 }
