@@ -11,6 +11,7 @@
 // and the deeply batched loads a lone warp needs to hide latency do not share one register budget.  Sums of squares are accumulated in Float64 whatever R is; the butterfly order is fixed, so
 // results are deterministic.
 #include <algorithm>
+#include <cstdlib>
 
 #include "spx_elementwise.cuh"
 #include "spx_ops.cuh"
@@ -671,7 +672,7 @@ __global__ void __launch_bounds__(kGroupThreads, PART == 0 ? SPX_GB_MINB : 2)
     group_l2binf_kernel(R* y, const R* xk, const R* sj, const R* q, long long ngroups,
                         const long long* __restrict__ offs, const R* __restrict__ lambda_g, R sigma, R delta,
                         UDiv<R> by_sigma, unsigned long long* task_counter, unsigned* long_flag,
-                        const unsigned* __restrict__ uniform_flag) {
+                        const unsigned* __restrict__ uniform_flag, const unsigned char* __restrict__ done) {
   if (uniform_flag != nullptr && *uniform_flag != 0u) return;  // the uniform-layout kernels own this call
   if (PART == 1 && long_flag != nullptr && *long_flag == 0u) return;
   const int lane = threadIdx.x & 31;
@@ -699,6 +700,10 @@ __global__ void __launch_bounds__(kGroupThreads, PART == 0 ? SPX_GB_MINB : 2)
         continue;
       }
       if (k < 0) {  // long group: the whole warp, sol stashed in y
+        if (done != nullptr && done[g0 + pos]) {  // solved by group_l2binf_big_kernel
+          pos += 1;
+          continue;
+        }
         const long long b = __shfl_sync(0xffffffffu, th.lo, pos), e = __shfl_sync(0xffffffffu, th.hi, pos);
         const R lam = __shfl_sync(0xffffffffu, lam_lane, pos);
         for (long long i0 = b + lane; i0 < e; i0 += 128) {  // :80, loads batched (y may alias q)
@@ -1184,6 +1189,231 @@ __global__ void __launch_bounds__(kGroupThreads, FAST ? SPX_GU_MINB : 2)
   }
 }
 
+// ---- one CTA per group of 1025..4096 elements (ShiftedGroupNormL2Binf) ----------------------------------------------
+// The warp path above keeps a long group in the output vector and re-reads it from L2 for every evaluation of froot:
+// with groups of thousands of elements nearly all of a ragged vector goes through one warp per group.  Here the group
+// sits in the registers of a 256-thread CTA (8 or 16 elements per thread: sol and xk), every evaluation is a pass over
+// registers plus one block reduction (a single __syncthreads: the reduction slots alternate), and the search is the
+// one of the uniform path in R arithmetic: froot(lmin) skipped when its sign is certain, Newton on
+// h(n) = (n - σλ) froot(n)/n from lmax down to a step of 2^-40 n, then the final pass as the acceptance test
+// (froot(n) = n - ||v|| within max(4, min(32, 4/κ)) ulps).  Groups that fail a guard or the test are left -- unmarked
+// in `done` -- to the bracketing search of the warp path, which runs afterwards.
+constexpr int kBinfBigThreads = 256;  // two CTAs per SM, 16 (or 8) elements per thread; 512 threads x 8 measured slower
+struct BigRed {
+  double v[2][kBinfBigThreads / 32][4];
+};
+// sums a[0..N) over the CTA; every thread gets the totals.  One barrier per call (slots alternate by `parity`).
+template <int N> __device__ __forceinline__ void block_sums(double (&a)[N], BigRed& red, int& parity) {
+#pragma unroll
+  for (int k = 0; k < N; ++k) a[k] = warp_sum(a[k]);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) red.v[parity][w][k] = a[k];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    double t = 0.0;
+#pragma unroll
+    for (int ww = 0; ww < kBinfBigThreads / 32; ++ww) t += red.v[parity][ww][k];
+    a[k] = t;
+  }
+  parity ^= 1;
+}
+#ifndef SPX_BINF_BIG_MIN
+#define SPX_BINF_BIG_MIN 1024
+#endif
+__device__ __forceinline__ bool is_binf_big(long long m) { return m > SPX_BINF_BIG_MIN && m <= kBigMax; }
+
+// one group, E elements per thread (E * 256 >= m).  Returns true when y_g has been written.
+template <class R, int E>
+__device__ __forceinline__ bool binf_big_group(R* y, const R* xk, const R* sj, const R* q, long long b, long long e,
+                                               R lam, R sigma, R delta, const UDiv<R>& by_sigma, BigRed& red,
+                                               int& parity) {
+  const int t = threadIdx.x;
+  const R epsR = Eps<R>::value;
+  const R sl = lam * sigma;
+  R sol[E], xkr[E];
+#pragma unroll
+  for (int k = 0; k < E; ++k) {
+    const long long i = b + (long long)k * kBinfBigThreads + t;
+    sol[k] = R(0);
+    xkr[k] = R(0);
+    if (i < e) {
+      const R xi = ldv(xk + i), si = ldv(sj + i), qi = ldv(q + i);
+      sol[k] = (qi + xi) + si;  // :80
+      xkr[k] = xi;
+    }
+  }
+  // ---- the three norms of :97-100 (and max |xk|) at τa = σ c(lmin + 1)
+  const R lmin = sl * (R(1) + epsR);
+  const R ansatz = lmin + R(1);
+  const R tau_a = sigma * (ansatz / (sigma * (ansatz - sl)));
+  double nm[3] = {0.0, 0.0, 0.0};
+  R xmax = R(0);
+  {
+    const R sdc = tau_a * delta;
+#pragma unroll
+    for (int k = 0; k < E; ++k) {
+      const R tt = sol[k] - tau_a * xkr[k];
+      const R a = jl_abs(tt) - sdc;
+      const double z = a > R(0) ? (double)a : 0.0;
+      nm[0] = __fma_rn(z, z, nm[0]);
+      nm[1] = __fma_rn((double)sol[k], (double)sol[k], nm[1]);
+      nm[2] = __fma_rn((double)xkr[k], (double)xkr[k], nm[2]);
+      xmax = jl_abs(xkr[k]) > xmax ? jl_abs(xkr[k]) : xmax;
+    }
+    block_sums<3>(nm, red, parity);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const R other = __shfl_xor_sync(0xffffffffu, xmax, o);
+      xmax = other > xmax ? other : xmax;
+    }
+    // block-wide max of |xk| through the reduction slots (one more barrier)
+    const int lane = t & 31, w = t >> 5;
+    if (lane == 0) red.v[parity][w][0] = (double)xmax;
+    __syncthreads();
+    double m = 0.0;
+#pragma unroll
+    for (int ww = 0; ww < kBinfBigThreads / 32; ++ww) m = red.v[parity][ww][0] > m ? red.v[parity][ww][0] : m;
+    xmax = (R)m;
+    parity ^= 1;
+  }
+  const R nsol = (R)sqrt_fast(nm[1]);
+  const R lmax = nsol + sigma * ((R)sqrt_fast(nm[0]) / sigma + R(1) * lam * (R)sqrt_fast(nm[2]));
+  // guards: finite, well-scaled, a proper bracket (everything else: the bracketing search)
+  bool ok = (nm[1] > 1e-280 && nm[1] < 1e280) && (nm[2] < 1e280) && (nm[0] < 1e280) && (sl > R(0)) &&
+            (lmax > lmin * (R)1.001) && (lmax == lmax);
+  auto eval = [&](R tau, double& ssA, double& ssB) {
+    double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+    const R sdc = tau * delta;
+#pragma unroll
+    for (int k = 0; k < E; k += 2) {
+      binf_term<R, double>(sol[k], xkr[k], tau, sdc, a0, b0);
+      binf_term<R, double>(sol[k + 1], xkr[k + 1], tau, sdc, a1, b1);
+    }
+    double ab[2] = {a0 + a1, b0 + b1};
+    block_sums<2>(ab, red, parity);
+    ssA = ab[0];
+    ssB = ab[1];
+  };
+  // froot(lmin) < 0 for certain when some |xk_i| is clearly above Δ (see binf_fast_search)
+  const R tau_l = (R(1) + epsR) / epsR;
+  const R excess = xmax - delta;
+  const bool fl_neg = (excess > (R)1e-4 * (xmax + delta)) && (excess * tau_l > (R)1e4 * (lmin + nsol));
+  R fl = R(-1);
+  if (ok && !fl_neg) {  // CTA-uniform
+    double ssA, ssB;
+    eval(tau_l, ssA, ssB);
+    const R nw = (R)sqrt_fast(ssA + ssB);
+    fl = lmin - nw;
+    ok = ok && (jl_abs(fl) > (R)1e-6 * jl_max(lmin, nw));
+  }
+  // Newton on h(n) = (n - σλ) froot(n)/n from lmax
+  R x = lmax, a_ = lmin, b_ = lmax;
+  bool zero_out = false, conv = !ok;
+#pragma unroll 1
+  for (int it = 0; it < 16 && !conv; ++it) {
+    const R gap = x - sl;
+    const R tau = div_fast(x, gap);
+    double ssA, ssB;
+    eval(tau, ssA, ssB);
+    const R nw = (R)sqrt_fast(ssA + ssB);
+    const R fx = x - nw;
+    const R dfx = R(1) + div_fast((R)ssA * sl, x * nw * gap);  // froot' = 1 + (ssA/τ) σλ / (||w|| gap²)
+    if (it == 0) {
+      ok = ok && (jl_abs(fx) > (R)1e-6 * x);
+      zero_out = (fl > R(0)) == (fx > R(0));  // fl*fm > 0  (:102)
+      if (!ok || zero_out) break;
+    }
+    const R den = fx + gap * (dfx - div_fast(fx, x));
+    const R stp = div_fast(gap * fx, den);
+    R xn = x - stp;
+    a_ = (fx < R(0)) ? x : a_;
+    b_ = (fx < R(0)) ? b_ : x;
+    if (!(xn >= a_ && xn <= b_)) xn = a_ + (b_ - a_) / R(2);
+    conv = (jl_abs(stp) <= (R)(sizeof(R) == 8 ? 1.5e-8 : 2e-4) * x) || (fx == R(0));  // the NEXT iterate is then good
+    x = xn;                                                                            // to the square of that
+  }
+  ok = ok && (zero_out || (conv && x == x && x > lmin && sl < R(64) * (x - sl)));
+  if (!ok) return false;  // CTA-uniform: every thread holds the same scalars
+  // ---- y_g = l2prox(sol - σ softthres(sol/σ - c xk, Δ c), σλ) - (xk + sj)   (:109-116), and the acceptance test
+  const R nroot = x;
+  const R step = div_fast(nroot, sigma * (nroot - sl));
+  const R dstep2 = delta * step;
+  double vs[1] = {0.0};
+#pragma unroll
+  for (int k = 0; k < E; ++k) {  // w overwrites sol
+    sol[k] = sol[k] - sigma * softthres_sel(quot_uniform(sol[k], by_sigma) - step * xkr[k], dstep2);
+    vs[0] = __fma_rn((double)sol[k], (double)sol[k], vs[0]);
+  }
+  block_sums<1>(vs, red, parity);
+  const R nv = (R)sqrt_fast(vs[0]);
+  if (!zero_out) {
+    const R res = nroot - nv;
+    const R gap = nroot - sl;
+    const R ulps = jl_max(R(4), jl_min(R(32), R(4) * gap * (R)(1.0 / (double)sl)));
+    if (!(jl_abs(res) <= ulps * epsR * nroot)) return false;  // not accepted: the bracketing search takes the group
+  }
+  const R alpha = zero_out ? R(0) : jl_max(R(0), R(1) - div_fast(sl, nv));
+#pragma unroll
+  for (int k = 0; k < E; ++k) {
+    const long long i = b + (long long)k * kBinfBigThreads + t;
+    if (i < e) {
+      const R o = zero_out ? R(0) : alpha * sol[k];
+      stv(y + i, o - (xkr[k] + sj[i]));
+    }
+  }
+  return true;
+}
+
+template <class R>
+__global__ void __launch_bounds__(kBinfBigThreads, 2)
+    group_l2binf_big_kernel(R* y, const R* xk, const R* sj, const R* q, long long ngroups,
+                            const long long* __restrict__ offs, const R* __restrict__ lambda_g, R sigma, R delta,
+                            UDiv<R> by_sigma, const unsigned* __restrict__ uniform_flag, unsigned char* __restrict__ done) {
+  if (uniform_flag != nullptr && *uniform_flag != 0u) return;
+  __shared__ int list[kBinfBigThreads];
+  __shared__ int wcount[kBinfBigThreads / 32];
+  __shared__ BigRed red;
+  const int t = threadIdx.x;
+  int parity = 0;
+  for (long long g0 = (long long)blockIdx.x * kBinfBigThreads; g0 < ngroups; g0 += (long long)gridDim.x * kBinfBigThreads) {
+    // index-ordered list of this chunk's groups of 1025..4096 elements
+    int nbig;
+    {
+      const int lane = t & 31, w = t >> 5;
+      const long long g = g0 + t;
+      const bool big = g < ngroups && is_binf_big(offs[g + 1] - offs[g]);
+      const unsigned bal = __ballot_sync(0xffffffffu, big);
+      __syncthreads();  // list / wcount reuse
+      if (lane == 0) wcount[w] = __popc(bal);
+      __syncthreads();
+      int base = 0;
+      nbig = 0;
+#pragma unroll
+      for (int ww = 0; ww < kBinfBigThreads / 32; ++ww) {
+        if (ww < w) base += wcount[ww];
+        nbig += wcount[ww];
+      }
+      if (big) list[base + __popc(bal & ((1u << lane) - 1u))] = t;
+      __syncthreads();
+    }
+    for (int j = 0; j < nbig; ++j) {
+      const long long g = g0 + list[j];
+      const long long b = offs[g], e = offs[g + 1];
+      const R lam = lambda_g[g];
+      bool wrote;
+      if (e - b <= 8 * kBinfBigThreads)
+        wrote = binf_big_group<R, 8>(y, xk, sj, q, b, e, lam, sigma, delta, by_sigma, red, parity);
+      else
+        wrote = binf_big_group<R, 16>(y, xk, sj, q, b, e, lam, sigma, delta, by_sigma, red, parity);
+      if (wrote && t == 0) done[g] = 1;
+    }
+  }
+}
+
 // flag = 1 iff offs[g] == g m for every g <= ngroups (grid-stride; the flag starts at 1)
 __global__ void __launch_bounds__(256) group_uniform_check_kernel(const long long* __restrict__ offs, long long ngroups,
                                                                   long long m, unsigned* flag) {
@@ -1530,9 +1760,13 @@ static int32_t prox_group(spx_ctx* ctx, bool binf, int64_t n, R* y, const R* xk,
     // {0, m, 2m, ...} is checked on the device; the flag gates the uniform kernels and the generic ones.
     const int64_t m = ngroups > 0 && n % ngroups == 0 ? n / ngroups : 0;
     const bool aligned = (((uintptr_t)y | (uintptr_t)xk | (uintptr_t)sj | (uintptr_t)q) & 15u) == 0;
-    const bool uni = aligned && (m == 16 || m == 32 || m == 64 || m == 128 || m == 256) && n < (int64_t(1) << 39);
+    // the fast searches take sol/σ through the branch-free quotient: σ far inside the normal range only
+    const bool sigma_ok = std::isfinite(sigma) && std::fabs(sigma) > 1e-30 && std::fabs(sigma) < 1e30 &&
+                          std::isfinite(delta) && std::fabs(delta) < 1e30;
+    const bool uni = sigma_ok && aligned && (m == 16 || m == 32 || m == 64 || m == 128 || m == 256) && n < (int64_t(1) << 39);
     const int64_t nrounds = uni ? (n + kRoundElems - 1) / kRoundElems : 0;
-    int32_t st0 = ensure_scratch(ctx, 4096 + (size_t)nrounds * sizeof(unsigned));
+    const size_t done_off = 4096 + (((size_t)nrounds * sizeof(unsigned) + 255) & ~(size_t)255);
+    int32_t st0 = ensure_scratch(ctx, done_off + (size_t)ngroups + 256);
     if (st0 != SPX_OK) return st0;
     unsigned long long* counter = (unsigned long long*)ctx->d_scratch;  // long groups: dynamic task hand-out
     unsigned* long_flag = (unsigned*)((char*)ctx->d_scratch + 8);
@@ -1550,10 +1784,31 @@ static int32_t prox_group(spx_ctx* ctx, bool binf, int64_t n, R* y, const R* xk,
     }
     group_l2binf_kernel<R, 0><<<grid0, kGroupThreads, 0, ctx->stream>>>(
         y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, (R)sigma, (R)delta, by_sigma, nullptr, long_flag,
-        uni ? uniform_flag : nullptr);
+        uni ? uniform_flag : nullptr, nullptr);
+    // groups of 257..4096 elements: one CTA per group, the group in registers; whatever it cannot accept stays
+    // unmarked in `done` for the warp path below.  Not when y aliases an input: the warp path stashes sol in y.
+    unsigned char* done = nullptr;
+    {
+      const char *y0 = (const char*)y, *y1 = y0 + (size_t)n * sizeof(R);
+      auto overlaps = [&](const R* p) { return (const char*)p < y1 && (const char*)p + (size_t)n * sizeof(R) > y0; };
+      if (sigma_ok && !(overlaps(xk) || overlaps(sj) || overlaps(q)) && std::getenv("SPX_BINF_NOBIG") == nullptr) {
+        done = (unsigned char*)ctx->d_scratch + done_off;
+        SPX_CUDA(cudaMemsetAsync(done, 0, (size_t)ngroups, ctx->stream));
+        int per_sm = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)group_l2binf_big_kernel<R>, kBinfBigThreads,
+                                                          0) != cudaSuccess || per_sm < 1)
+          per_sm = 1;
+        const int gridb = (int)std::max<int64_t>(
+            1, std::min<int64_t>((ngroups + kBinfBigThreads - 1) / kBinfBigThreads, (int64_t)ctx->sm_count * per_sm));
+        group_l2binf_big_kernel<R><<<gridb, kBinfBigThreads, 0, ctx->stream>>>(
+            y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, (R)sigma, (R)delta, by_sigma,
+            uni ? uniform_flag : nullptr, done);
+        ctx->launches++;
+      }
+    }
     group_l2binf_kernel<R, 1><<<grid1, kGroupThreads, 0, ctx->stream>>>(
         y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, (R)sigma, (R)delta, by_sigma, counter, long_flag,
-        uni ? uniform_flag : nullptr);
+        uni ? uniform_flag : nullptr, done);
     ctx->launches += 2;
     SPX_CUDA(cudaGetLastError());
   }
