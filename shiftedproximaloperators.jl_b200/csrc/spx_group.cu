@@ -358,6 +358,47 @@ __device__ __forceinline__ int list_big_groups(const long long* __restrict__ off
   return total;
 }
 
+// one group of the CTA-per-group class, E elements per thread (E * 256 >= m); returns the group's ψ term
+template <class R, bool PSI, bool SHIFTED, int E>
+__device__ __forceinline__ double l2_big_group(R* y, const R* xk, const R* sj, const R* q, long long b, long long e, R lam,
+                                               R sigma, double* red) {
+  const int t = threadIdx.x;
+  R sol[E], xs[E];
+  double ss = 0.0;
+#pragma unroll
+  for (int k = 0; k < E; ++k) {
+    const long long i = b + (long long)k * kGroupThreads + t;
+    sol[k] = R(0);
+    xs[k] = R(0);
+    if (i < e) {
+      const R xi = SHIFTED ? ldv(xk + i) : R(0), si = SHIFTED ? ldv(sj + i) : R(0), qi = ldv(q + i);
+      sol[k] = (qi + xi) + si;  // shiftedGroupNormL2.jl:65
+      xs[k] = xi + si;
+      ss += (double)sol[k] * (double)sol[k];
+    }
+  }
+  ss = block_sum(ss, red);
+  const R snorm = (R)sqrt(ss);
+  const R alpha = jl_max(R(1) - sigma * lam / snorm, R(0));
+  double vv = 0.0;
+#pragma unroll
+  for (int k = 0; k < E; ++k) {
+    const long long i = b + (long long)k * kGroupThreads + t;
+    if (i < e) {
+      const R o = (snorm == R(0) ? R(0) : alpha * sol[k]) - xs[k];  // :70-77
+      stv(y + i, o);
+      if (PSI) {
+        const double v = (double)(xs[k] + o);
+        vv += v * v;
+      }
+    }
+  }
+  if (!PSI) return 0.0;
+  vv = block_sum(vv, red);
+  // shifted: λ_g ‖(xk + sj + y)_g‖; unshifted: λ_g ‖x_g‖ of the input (groupNormL2.jl:49-54)
+  return (double)(lam * (SHIFTED ? (R)sqrt(vv) : snorm));
+}
+
 template <class R, bool PSI, bool SHIFTED>
 __global__ void __launch_bounds__(kGroupThreads)
     group_l2_big_kernel(R* y, const R* xk, const R* sj, const R* q, long long ngroups,
@@ -374,41 +415,12 @@ __global__ void __launch_bounds__(kGroupThreads)
       const long long g = g0 + list[j];
       const long long b = offs[g], e = offs[g + 1];
       const R lam = lambda_g[g];
-      R sol[kBigE], xs[kBigE];
-      double ss = 0.0;
-#pragma unroll
-      for (int k = 0; k < kBigE; ++k) {
-        const long long i = b + (long long)k * kGroupThreads + t;
-        sol[k] = R(0);
-        xs[k] = R(0);
-        if (i < e) {
-          const R xi = SHIFTED ? ldv(xk + i) : R(0), si = SHIFTED ? ldv(sj + i) : R(0), qi = ldv(q + i);
-          sol[k] = (qi + xi) + si;  // shiftedGroupNormL2.jl:65
-          xs[k] = xi + si;
-          ss += (double)sol[k] * (double)sol[k];
-        }
-      }
-      ss = block_sum(ss, red);
-      const R snorm = (R)sqrt(ss);
-      const R alpha = jl_max(R(1) - sigma * lam / snorm, R(0));
-      double vv = 0.0;
-#pragma unroll
-      for (int k = 0; k < kBigE; ++k) {
-        const long long i = b + (long long)k * kGroupThreads + t;
-        if (i < e) {
-          const R o = (snorm == R(0) ? R(0) : alpha * sol[k]) - xs[k];  // :70-77
-          stv(y + i, o);
-          if (PSI) {
-            const double v = (double)(xs[k] + o);
-            vv += v * v;
-          }
-        }
-      }
-      if (PSI) {
-        vv = block_sum(vv, red);
-        // shifted: λ_g ‖(xk + sj + y)_g‖; unshifted: λ_g ‖x_g‖ of the input (groupNormL2.jl:49-54)
-        if (t == 0) psi += (double)(lam * (SHIFTED ? (R)sqrt(vv) : snorm));
-      }
+      double term;
+      if (e - b <= (kBigE / 2) * kGroupThreads)
+        term = l2_big_group<R, PSI, SHIFTED, kBigE / 2>(y, xk, sj, q, b, e, lam, sigma, red);
+      else
+        term = l2_big_group<R, PSI, SHIFTED, kBigE>(y, xk, sj, q, b, e, lam, sigma, red);
+      if (PSI && t == 0) psi += term;
     }
   }
   if (PSI && t == 0) {
@@ -1688,16 +1700,34 @@ static int32_t launch_group_l2(spx_ctx* ctx, int64_t n, R* y, const R* xk, const
     *psi_out = (double)(R)ctx->h_result[0].s;
     return SPX_OK;
   }
-  const int grid0 = group_grid(ctx, ngroups, (const void*)group_l2_kernel<R, false, 0, SHIFTED>);
-  const int grid1 = group_grid(ctx, ngroups, (const void*)group_l2_kernel<R, false, 1, SHIFTED>);
-  group_l2_kernel<R, false, 0, SHIFTED><<<grid0, kGroupThreads, 0, ctx->stream>>>(
+  // The three size classes are independent: they run CONCURRENTLY on the context's side streams (fork / join by
+  // events on the caller's stream), with one short-lived CTA per chunk of work instead of a persistent grid, so the
+  // block scheduler interleaves the three kernels as resources free up.  Alone, none of them fills HBM on a ragged
+  // layout (the long-group classes wait on their reductions, the short-group class on its per-group arithmetic).
+  for (int i = 0; i < 2; ++i)
+    if (!ctx->pipe_streams[i]) SPX_CUDA(cudaStreamCreateWithFlags(&ctx->pipe_streams[i], cudaStreamNonBlocking));
+  for (int i = 13; i < 16; ++i)
+    if (!ctx->pipe_events[i]) SPX_CUDA(cudaEventCreateWithFlags(&ctx->pipe_events[i], cudaEventDisableTiming));
+  const long long ntasks = (ngroups + kTask - 1) / kTask;
+  const long long warps_per_cta = kGroupThreads / 32;
+  const int grid0 = (int)std::max<long long>(1, std::min<long long>((ntasks + warps_per_cta - 1) / warps_per_cta, 1 << 20));
+  const int grid2s = (int)std::max<long long>(1, std::min<long long>((ngroups + kGroupThreads - 1) / kGroupThreads, 1 << 20));
+  (void)grid2;
+  SPX_CUDA(cudaEventRecord(ctx->pipe_events[13], ctx->stream));
+  SPX_CUDA(cudaStreamWaitEvent(ctx->pipe_streams[0], ctx->pipe_events[13], 0));
+  SPX_CUDA(cudaStreamWaitEvent(ctx->pipe_streams[1], ctx->pipe_events[13], 0));
+  group_l2_big_kernel<R, false, SHIFTED><<<grid2s, kGroupThreads, 0, ctx->stream>>>(
       y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, sigma, ctx->d_partials);
-  group_l2_kernel<R, false, 1, SHIFTED><<<grid1, kGroupThreads, 0, ctx->stream>>>(
+  group_l2_kernel<R, false, 1, SHIFTED><<<grid0, kGroupThreads, 0, ctx->pipe_streams[0]>>>(
       y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, sigma, ctx->d_partials);
-  group_l2_big_kernel<R, false, SHIFTED><<<grid2, kGroupThreads, 0, ctx->stream>>>(
+  group_l2_kernel<R, false, 0, SHIFTED><<<grid0, kGroupThreads, 0, ctx->pipe_streams[1]>>>(
       y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, sigma, ctx->d_partials);
   ctx->launches += 3;
   SPX_CUDA(cudaGetLastError());
+  SPX_CUDA(cudaEventRecord(ctx->pipe_events[14], ctx->pipe_streams[0]));
+  SPX_CUDA(cudaEventRecord(ctx->pipe_events[15], ctx->pipe_streams[1]));
+  SPX_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->pipe_events[14], 0));
+  SPX_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->pipe_events[15], 0));
   return SPX_OK;
 }
 
@@ -1782,9 +1812,17 @@ static int32_t prox_group(spx_ctx* ctx, bool binf, int64_t n, R* y, const R* xk,
                              uniform_flag, wl_count, wl_rounds);
       ctx->launches += 3;
     }
-    group_l2binf_kernel<R, 0><<<grid0, kGroupThreads, 0, ctx->stream>>>(
+    // the short groups (<= 256 elements) on a side stream, concurrently with the CTA-per-group class below; the warp
+    // path for what is left joins both (it reads long_flag and the done bitmap)
+    if (!ctx->pipe_streams[0]) SPX_CUDA(cudaStreamCreateWithFlags(&ctx->pipe_streams[0], cudaStreamNonBlocking));
+    for (int i = 13; i < 15; ++i)
+      if (!ctx->pipe_events[i]) SPX_CUDA(cudaEventCreateWithFlags(&ctx->pipe_events[i], cudaEventDisableTiming));
+    SPX_CUDA(cudaEventRecord(ctx->pipe_events[13], ctx->stream));
+    SPX_CUDA(cudaStreamWaitEvent(ctx->pipe_streams[0], ctx->pipe_events[13], 0));
+    group_l2binf_kernel<R, 0><<<grid0, kGroupThreads, 0, ctx->pipe_streams[0]>>>(
         y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, (R)sigma, (R)delta, by_sigma, nullptr, long_flag,
         uni ? uniform_flag : nullptr, nullptr);
+    SPX_CUDA(cudaEventRecord(ctx->pipe_events[14], ctx->pipe_streams[0]));
     // groups of 257..4096 elements: one CTA per group, the group in registers; whatever it cannot accept stays
     // unmarked in `done` for the warp path below.  Not when y aliases an input: the warp path stashes sol in y.
     unsigned char* done = nullptr;
@@ -1806,6 +1844,7 @@ static int32_t prox_group(spx_ctx* ctx, bool binf, int64_t n, R* y, const R* xk,
         ctx->launches++;
       }
     }
+    SPX_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->pipe_events[14], 0));
     group_l2binf_kernel<R, 1><<<grid1, kGroupThreads, 0, ctx->stream>>>(
         y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, (R)sigma, (R)delta, by_sigma, counter, long_flag,
         uni ? uniform_flag : nullptr, done);
