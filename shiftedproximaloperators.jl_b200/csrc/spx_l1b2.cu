@@ -6,15 +6,15 @@
 //
 // Every evaluation of the residual is a full streaming pass over xk, sj, q (3R per element; 2R once
 // mid = sj + q has been stashed in the output vector, which the search is free to use as scratch when it
-// aliases no input), so the pass count is what matters.  A pass evaluates up to 4 (last pass: 8) trial values
-// of η at once and returns, next to Σw², the sum Σ w dw/dη that gives the derivative of the residual (~12
-// instructions per trial: four trials keep the pass HBM-bound, eight are FP64-issue bound).  Roots' one-point-per-pass iteration becomes a safeguarded
-// Newton / secant search whose bracket closes superlinearly from both sides: the residual at η = Δ comes
-// from the very pass that decides whether the ball is active, a Newton step from there brackets the
-// root, each further pass evaluates the secant point and the Newton points of both ends, and the last
-// pass evaluates every float left inside the bracket.  End state as Roots' bisection: two adjacent floats
-// around the sign change.  When the vector is sharded over several GPUs the partial sums are all-reduced
-// by the caller's callback between passes; the scalar search itself is replicated on every rank.
+// aliases no input), so the pass count is what matters.  A pass evaluates up to 4 trial values of η at once and
+// returns, next to Σw², the sum Σ w dw/dη that gives the derivative of the residual (~12 instructions per trial:
+// four trials keep the pass HBM-bound, eight are FP64-issue bound).  Roots' one-point-per-pass iteration becomes:
+// a ladder pass Δ·{1, 2, 4, 16} (its first value decides whether the ball is active), then clusters of four trial
+// values around the root of the cubic Hermite interpolant of the residual on the bracket, and the finish pass as
+// the check of the last interpolated root (see prox_l1b2 below): 3 norm passes + finish on large vectors.  End
+// state: a point with |residual| <= 4 ulp, an exact zero, or -- as Roots' bisection -- two adjacent floats around
+// the sign change.  When the vector is sharded over several GPUs the partial sums of every pass are all-reduced, by
+// the context's communicator (spx_comm.cu) or by the caller's callback; the scalar search is replicated on every rank.
 #include <algorithm>
 #include <cstring>
 #include <vector>
