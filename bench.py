@@ -107,8 +107,25 @@ def cpu_baseline(budget_s: float):
     n2 = 1 << (n2.bit_length() - 1)
     t = cpu_sample(n2)
     total = sum(t.values())
+    # the "generous CPU bound" of SURVEY.md §8d: the same oracle port on every host core at once (chunks of the sample
+    # in a thread pool; ctypes releases the GIL) -- NOT the reference's behaviour (it is single-threaded), reported only
+    all_cores = None
+    try:
+        from concurrent.futures import ThreadPoolExecutor
+
+        cores = len(os.sched_getaffinity(0))
+        chunk = max(1 << 18, n2 // cores)
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(cores) as ex:
+            list(ex.map(lambda _: cpu_sample(chunk), range(cores)))
+        wall = time.perf_counter() - t0
+        all_cores = {"value": 3 * chunk * cores / wall, "unit": "elements/s", "cores": cores,
+                     "note": "oracle port on every host core (input generation of each chunk inside the timed region); "
+                             "the reference itself is single-threaded"}
+    except Exception:
+        pass
     return {
-        "value": 3 * n2 / total, "unit": "elements/s", "cores": 1, "kind": "port",
+        "value": 3 * n2 / total, "unit": "elements/s", "cores": 1, "kind": "port", "all_cores": all_cores,
         "sample": f"C2 step (L0Box prox!, LhalfBox prox!, L0Box iprox!) on n=2^{n2.bit_length() - 1} Float64, "
                   f"oracle port g++ -O2 -ffp-contract=off, 1 thread (the reference is single-threaded Julia; "
                   f"`julia` is not in the image), host has {os.cpu_count()} logical cores",
