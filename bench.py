@@ -611,7 +611,27 @@ def run_e2e(args, sp, L, dev, dist, world, n, dev_inputs):
         dt = float(tt.item())
     h2d = 6 * n * 8  # xk, sj, q (= g), d, l, u
     d2h = 3 * n * 8  # one result per operation
-    return {"value": world * 3 * n * K / dt, "unit": "elements/s", "h2d_bytes_per_step": h2d,
+    # what ONE drop-in prox!(y::Vector, ψ, q, σ) on host vectors costs (spx_box_host_f64: ShiftedNormL0Box prox!, five
+    # input vectors up, one result down) -- the reference API has no multi-operation verb
+    def single_op():
+        hp.box_host(ctx, "l0", hy0, hxk, hsj, hq, hl, hu, LAMBDA, SIGMA, chunk=1 << 22)
+
+    single_op()
+    barrier()
+    t1 = time.perf_counter()
+    for _ in range(K):
+        single_op()
+    barrier()
+    dt1 = time.perf_counter() - t1
+    if dist is not None:
+        tt = torch.tensor([dt1], dtype=f64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt1 = float(tt.item())
+    single = {"api": "spx_box_host_f64: one ShiftedNormL0Box prox! on pinned host vectors", "ms_per_call": 1e3 * dt1 / K,
+              "elements_per_s": world * n * K / dt1, "h2d_bytes_per_call": 5 * n * 8, "d2h_bytes_per_call": n * 8,
+              "pcie_gbs_per_gpu": 6 * n * 8 * K / dt1 / 1e9}
+    return {"value": world * 3 * n * K / dt, "unit": "elements/s", "h2d_bytes_per_step": h2d, "single_op": single,
+            "pcie_gbs_per_gpu": (h2d + d2h) * K / dt / 1e9,
             "d2h_bytes_per_step": d2h, "steps": K, "ms_per_step": 1e3 * dt / K,
             "pcie_gbs": (h2d + d2h) * K / dt / 1e9,
             "api": "spx_box_multi_host_f64: the three operations of the step at one shifted point, pinned host vectors, "
