@@ -428,9 +428,18 @@ template <class R> struct BoxPsi {
 };
 
 // shiftedNormL1Box.jl:89-125
+// resident CTAs per SM asked of ptxas: the fused-ψ forms spill under the 64 registers of four CTAs (measured at
+// n = 2^28 Float64: L0Box+ψ 84.3 % -> 90.6 %, L1Box+ψ 88.2 % -> 92.1 %, L0Box 88.2 % -> 93.2 %, L1Box 92.5 % -> 94.8 % of
+// HBM peak with three; LhalfBox keeps four: 85.6 % vs 76.8 %)
+#ifndef SPX_PSI_MINB
+#define SPX_PSI_MINB 3
+#endif
+#ifndef SPX_BOX_MINB
+#define SPX_BOX_MINB 3
+#endif
 template <class R, bool PSI> struct ProxL1Box {
   using Real = R;
-  static constexpr int NIN = 5, UNROLL = 2, MINB = 4;
+  static constexpr int NIN = 5, UNROLL = 2, MINB = PSI ? SPX_PSI_MINB : SPX_BOX_MINB;
   static constexpr bool OUT = true, ACC = PSI;
   static constexpr bool SPLIT_NULL = true;  // l, u: both vectors or both scalars at compile time
   const R* in[NIN];  // xk, sj, q, l, u
@@ -555,7 +564,7 @@ template <class R, bool PSI> struct IproxL1Box {
 // shiftedNormL0Box.jl:89-131
 template <class R, bool PSI> struct ProxL0Box {
   using Real = R;
-  static constexpr int NIN = 5, UNROLL = 2, MINB = 4;
+  static constexpr int NIN = 5, UNROLL = 2, MINB = PSI ? SPX_PSI_MINB : SPX_BOX_MINB;
   static constexpr bool OUT = true, ACC = PSI;
   static constexpr bool SPLIT_NULL = true;  // l, u: both vectors or both scalars at compile time
   const R* in[NIN];  // xk, sj, q, l, u
@@ -728,7 +737,10 @@ template <class R, bool PSI> struct ProxLhalfBox {
 #ifndef SPX_LHB_STAGES
 #define SPX_LHB_STAGES 0
 #endif
-  static constexpr int NIN = 5, UNROLL = SPX_LHB_UNROLL, MINB = SPX_LHB_MINB, STAGES = SPX_LHB_STAGES;
+#ifndef SPX_LHB_PSI_MINB
+#define SPX_LHB_PSI_MINB 4
+#endif
+  static constexpr int NIN = 5, UNROLL = SPX_LHB_UNROLL, MINB = PSI ? SPX_LHB_PSI_MINB : SPX_LHB_MINB, STAGES = SPX_LHB_STAGES;
   static constexpr bool OUT = true, ACC = PSI;
   static constexpr bool SPLIT_NULL = true;  // l, u: both vectors or both scalars at compile time
   const R* in[NIN];  // xk, sj, q, l, u
