@@ -801,8 +801,8 @@ __global__ void __launch_bounds__(kGroupThreads, PART == 0 ? SPX_GB_MINB : 2)
 //   B  one evaluation in R with Float64 sums; A and B of the current piece give froot', froot'' in closed form:
 //      a Halley step lands on the root to ~1 ulp (cubic: 1e-6 -> 1e-18).
 //   C  the final pass IS an evaluation: v = sol - σ softthres(sol/σ - c xk, Δc) = -w (:109), so ||v|| gives
-//      froot(n) = n - ||v|| in the reference's own arithmetic.  |froot(n)| <= max(4, min(32, 4/κ)) ulp(n),
-//      κ = σλ/(n - σλ), accepts n (froot' >= 1: n is within that many ulps of the root, the distance bisection to
+//      froot(n) = n - ||v|| in the reference's own arithmetic.  |froot(n)| / froot'(n) <= max(2, min(16, 1/κ)) ulp(n),
+//      κ = σλ/(n - σλ), accepts n (n is within that many ulps of the root, the distance bisection to
 //      adjacent floats leaves between two summation orders).  Rounds that fail any check (NaN/Inf, magnitudes
 //      outside the Float32 range, no clear sign, ill-conditioned roots next to the pole, residual not met) are
 //      listed and redone by the bracketing search (binf_solve) in a second launch over the list.
@@ -1176,9 +1176,10 @@ __global__ void __launch_bounds__(kGroupThreads, FAST ? SPX_GU_MINB : 2)
       // froot(nroot) = nroot - ||v|| in the reference's arithmetic: the acceptance test of the fast search
       const R res = nroot - nv;
       const R gap = nroot - sl;
-      // max(4, min(32, 4/κ)) ulps, κ = σλ/gap:  4/κ = 4 gap/σλ
-      const R ulps = jl_max(R(4), jl_min(R(32), R(4) * gap * (R)(1.0 / (double)sl)));
-      const bool accepted = zero_out || !t.valid || (jl_abs(res) <= ulps * Eps<R>::value * nroot);
+      // n is within |res| / froot'(n) of the root (froot' >= 1, ~1 + κ next to the pole -- where the residual's own
+      // rounding noise grows with κ as well): accepted within max(2, min(16, 1/κ)) ulps of the ROOT, κ = σλ/gap
+      const R ulps = jl_max(R(2), jl_min(R(16), gap * (R)(1.0 / (double)sl)));
+      const bool accepted = zero_out || !t.valid || (jl_abs(res) <= ulps * Eps<R>::value * nroot * (R)fp);
       if (__any_sync(0xffffffffu, !accepted)) {
         if (lane == 0) wl_rounds[atomicAdd(wl_count, 1u)] = (unsigned)round;
         continue;
@@ -1208,7 +1209,7 @@ __global__ void __launch_bounds__(kGroupThreads, FAST ? SPX_GU_MINB : 2)
 // registers plus one block reduction (a single __syncthreads: the reduction slots alternate), and the search is the
 // one of the uniform path in R arithmetic: froot(lmin) skipped when its sign is certain, Newton on
 // h(n) = (n - σλ) froot(n)/n from lmax down to a step of 2^-40 n, then the final pass as the acceptance test
-// (froot(n) = n - ||v|| within max(4, min(32, 4/κ)) ulps).  Groups that fail a guard or the test are left -- unmarked
+// (|froot(n)| / froot'(n) within max(2, min(16, 1/κ)) ulps of n).  Groups that fail a guard or the test are left -- unmarked
 // in `done` -- to the bracketing search of the warp path, which runs afterwards.
 constexpr int kBinfBigThreads = 256;  // two CTAs per SM, 16 (or 8) elements per thread; 512 threads x 8 measured slower
 struct BigRed {
@@ -1323,7 +1324,7 @@ __device__ __forceinline__ bool binf_big_group(R* y, const R* xk, const R* sj, c
     ok = ok && (jl_abs(fl) > (R)1e-6 * jl_max(lmin, nw));
   }
   // Newton on h(n) = (n - σλ) froot(n)/n from lmax
-  R x = lmax, a_ = lmin, b_ = lmax;
+  R x = lmax, a_ = lmin, b_ = lmax, dfx_last = R(1);
   bool zero_out = false, conv = !ok;
 #pragma unroll 1
   for (int it = 0; it < 16 && !conv; ++it) {
@@ -1334,6 +1335,7 @@ __device__ __forceinline__ bool binf_big_group(R* y, const R* xk, const R* sj, c
     const R nw = (R)sqrt_fast(ssA + ssB);
     const R fx = x - nw;
     const R dfx = R(1) + div_fast((R)ssA * sl, x * nw * gap);  // froot' = 1 + (ssA/τ) σλ / (||w|| gap²)
+    dfx_last = dfx;
     if (it == 0) {
       ok = ok && (jl_abs(fx) > (R)1e-6 * x);
       zero_out = (fl > R(0)) == (fx > R(0));  // fl*fm > 0  (:102)
@@ -1365,8 +1367,9 @@ __device__ __forceinline__ bool binf_big_group(R* y, const R* xk, const R* sj, c
   if (!zero_out) {
     const R res = nroot - nv;
     const R gap = nroot - sl;
-    const R ulps = jl_max(R(4), jl_min(R(32), R(4) * gap * (R)(1.0 / (double)sl)));
-    if (!(jl_abs(res) <= ulps * epsR * nroot)) return false;  // not accepted: the bracketing search takes the group
+    // within max(2, min(16, 1/κ)) ulps of the root: |res| / froot' (see group_l2binf_uniform_kernel)
+    const R ulps = jl_max(R(2), jl_min(R(16), gap * (R)(1.0 / (double)sl)));
+    if (!(jl_abs(res) <= ulps * epsR * nroot * dfx_last)) return false;  // not accepted: the bracketing search takes it
   }
   const R alpha = zero_out ? R(0) : jl_max(R(0), R(1) - div_fast(sl, nv));
 #pragma unroll
