@@ -981,3 +981,60 @@ def test_group_offsets_are_validated_at_construction():
     for bad in ([1, 10, 500, n], [0, 600, 500, n], [0, 10, 500, n + 5], [0, 10, 500, n - 1]):
         with pytest.raises(ValueError, match="offsets"):
             sp.shifted(sp.GroupNormL2(T(np.ones(3)), None, offsets=T(np.array(bad, np.int64))), x)
+
+
+# ------------------------------------------------------------- out-of-bounds writes (canaries) ---
+@pytest.mark.parametrize("dt", DT)
+def test_round2_kernels_write_only_inside_y(dt):
+    """compute-sanitizer is not available on the GPU pool, so the kernels added in round 2 (uniform-layout and
+    CTA-per-group GroupNormL2Binf, concurrent GroupNormL2 size classes, stream-form top-r, L1B2 with its stash in y) are
+    run with y embedded in a larger buffer full of a sentinel: nothing outside y[0:n] may change."""
+    pad = 256
+    sentinel = dt(-12345.678)
+
+    def embedded(n):
+        buf = torch.full((n + 2 * pad,), float(sentinel), dtype=torch.float64 if dt == np.float64 else torch.float32, device=DEV)
+        return buf, buf[pad:pad + n]
+
+    def intact(buf, n):
+        return bool((buf[:pad] == float(sentinel)).all()) and bool((buf[pad + n:] == float(sentinel)).all())
+
+    # uniform layout, last round partial
+    for m in (16, 64, 256):
+        ng = 1203
+        n = ng * m
+        xk, sj, q = inputs(n, dt)
+        lam_g = (dt(0.5) + orc.uniform(ng, 12, dt)).astype(dt)
+        h = sp.GroupNormL2(T(lam_g), None, offsets=T(np.arange(0, n + 1, m)))
+        buf, y = embedded(n)
+        sp.prox_(y, sp.shifted(sp.shifted(h, T(xk), 0.5, sp.NormLinf(1.0)), T(sj)), T(q), 0.3)
+        assert intact(buf, n), ("uniform Binf", m)
+        buf, y = embedded(n)
+        sp.prox_(y, sp.shifted(sp.shifted(h, T(xk)), T(sj)), T(q), 0.3)
+        assert intact(buf, n), ("GroupL2", m)
+    # ragged with groups up to 4096 and beyond (CTA-per-group, warp paths, concurrent size classes)
+    offs = np.concatenate([[0], np.cumsum([1024, 1025, 7, 4096, 4097, 256, 257, 2049, 1, 3000, 5000, 64, 64])])
+    n = int(offs[-1])
+    xk, sj, q = inputs(n, dt)
+    lam_g = (dt(0.5) + orc.uniform(len(offs) - 1, 12, dt)).astype(dt)
+    h = sp.GroupNormL2(T(lam_g), None, offsets=T(offs))
+    for psi in (sp.shifted(sp.shifted(h, T(xk), 0.5, sp.NormLinf(1.0)), T(sj)), sp.shifted(sp.shifted(h, T(xk)), T(sj))):
+        buf, y = embedded(n)
+        sp.prox_(y, psi, T(q), 0.3)
+        assert intact(buf, n), type(psi).__name__
+    # stream-form top-r: three shared-memory tiers and the L2-scratch tier
+    for pn in (4096, 32_768, 65_536, 131_072):
+        nprob = 300
+        n = nprob * pn
+        xk, sj, q = inputs(n, dt)
+        buf, y = embedded(n)
+        psi = sp.shifted(sp.shifted(sp.IndBallL0(97), T(xk), 1.0, sp.NormLinf(1.0), nprob=nprob), T(sj))
+        sp.prox_(y, psi, T(q), 1.0)
+        assert intact(buf, n), ("top-r stream", pn)
+    # L1B2 (y is the stash of the search)
+    n = 300_001
+    xk, sj, q = inputs(n, dt)
+    buf, y = embedded(n)
+    psi = sp.shifted(sp.shifted(sp.NormL1(1.0), T(xk), 50.0, sp.NormL2(1.0)), T(sj))
+    sp.prox_(y, psi, T(q), 0.1)
+    assert intact(buf, n), "L1B2"
