@@ -118,6 +118,15 @@ int32_t spx_comm_destroy(spx_ctx* ctx);
  * make the same calls in the same order.  on == 0: per-shard values (the default). */
 int32_t spx_comm_reduce_scalars(spx_ctx* ctx, int32_t on);
 int32_t spx_comm_info(spx_ctx* ctx, int32_t* nranks_out, int32_t* rank_out, int64_t* collectives_out);
+/* Peer-memory exchange (optional, on top of or instead of the NCCL communicator): every rank exports the IPC handle of
+ * its exchange buffer, the host passes the nranks handles around (rank order), every rank maps them.  The scalar
+ * reductions (1..16 slots of {Σ, Σ₂, flag}) are then finished by the fold kernel itself: stores into every peer's
+ * buffer over NVLink, a spin on the own buffer, the sum in rank order -- no separate collective launch. */
+#define SPX_PEER_HANDLE_BYTES 64
+int32_t spx_comm_peer_export(spx_ctx* ctx, void* handle_out64);
+int32_t spx_comm_peer_attach(spx_ctx* ctx, int32_t nranks, int32_t rank, const void* handles /* nranks x 64 bytes */);
+int32_t spx_comm_peer_detach(spx_ctx* ctx);
+int32_t spx_comm_peer_active(spx_ctx* ctx); /* 1 when the scalar reductions go over the exchange buffers */
 /* building block: in-place all-reduce of `count` doubles in device memory, enqueued on the context's stream
  * (op 0 = sum, 1 = max); a context without communicator leaves the buffer as is */
 int32_t spx_comm_allreduce_f64(spx_ctx* ctx, double* dev_buf, int64_t count, int32_t op);

@@ -16,6 +16,7 @@
 #include <nccl.h>
 
 #include <cstdlib>
+#include <cstring>
 #include <mutex>
 
 #include "spx_common.cuh"
@@ -103,7 +104,9 @@ __global__ void neutral_partials_kernel(Partial* __restrict__ r, int nslot) {
   }
 }
 
-bool comm_active(const spx_ctx* ctx) { return ctx->comm != nullptr && ctx->reduce_scalars && ctx->comm_nranks > 1; }
+bool comm_active(const spx_ctx* ctx) {
+  return (ctx->comm != nullptr || ctx->d_peer_ptrs != nullptr) && ctx->reduce_scalars && ctx->comm_nranks > 1;
+}
 
 int32_t comm_neutral_result(spx_ctx* ctx, int nslot) {
   neutral_partials_kernel<<<1, kMaxScale, 0, ctx->stream>>>(ctx->d_result, nslot);
@@ -150,6 +153,130 @@ int32_t comm_allreduce_raw(spx_ctx* ctx, void* buf, size_t count, int dtype, int
   }
   SPX_NCCL(a->AllReduce(buf, buf, count, (ncclDataType_t)dtype, (ncclRedOp_t)op, (ncclComm_t)ctx->comm, ctx->stream));
   ctx->collectives += 1;
+  return SPX_OK;
+}
+
+// ------------------------------------------------------------------ peer-memory all-reduce ---
+// The reductions of the path are 1..16 slots of {Σ, Σ₂, flag}: latency, not bandwidth.  With every rank's exchange
+// buffer mapped into every process (CUDA IPC over NVLink / NVSwitch) the fold kernel finishes the all-reduce itself:
+//   block k folds slot k of this rank's partials; threads 0..nranks-1 store the folded slot -- data, a system-scope
+//   fence, then the sequence number -- into bank (seq & 1), row `rank`, of EVERY rank's buffer; the same threads then
+//   spin (acquire loads) until row w of the OWN buffer carries this sequence number; thread 0 sums the rows in rank
+//   order, so every rank computes the same bits; the flag is max-reduced.
+// Two banks suffice: a rank can only be one reduction ahead of a peer (it needs the peer's row to finish its own).
+// A rank that never arrives would hang the others exactly like an NCCL collective; the spin is bounded by the
+// global timer (SPX_PEER_TIMEOUT_S, default 120 s) and poisons the flag instead, which the host turns into an error.
+struct PeerSlot {
+  double s, s2;
+  long long bad;
+  unsigned long long seq;
+};
+constexpr int kPeerMaxRanks = 16;
+constexpr size_t kPeerBytes = sizeof(PeerSlot) * 2 * kPeerMaxRanks * kMaxScale;
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long v;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v));
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(256) fold_allreduce_peer_kernel(const Partial* __restrict__ partials, int nblocks,
+                                                                  Partial* __restrict__ result, void* const* peers,
+                                                                  int nranks, int rank, unsigned long long seq,
+                                                                  unsigned long long timeout_ns) {
+  const int k = blockIdx.x;  // slot
+  Partial acc;
+  acc.s = 0.0;
+  acc.s2 = 0.0;
+  acc.bad = -1;
+  const Partial* p = partials + (size_t)k * nblocks;
+  for (int i = threadIdx.x; i < nblocks; i += 256) {
+    Partial t = p[i];
+    acc.s += t.s;
+    acc.s2 += t.s2;
+    acc.bad = t.bad > acc.bad ? t.bad : acc.bad;
+  }
+  acc = block_fold<256>(acc);
+  __shared__ Partial mine;
+  __shared__ int timed_out;
+  if (threadIdx.x == 0) {
+    mine = acc;
+    timed_out = 0;
+  }
+  __syncthreads();
+  const int bank = (int)(seq & 1ull);
+  const int t = threadIdx.x;
+  if (t < nranks) {  // push: my folded slot into row `rank` of peer t's buffer
+    PeerSlot* dst = (PeerSlot*)peers[t] + ((size_t)bank * kPeerMaxRanks + rank) * kMaxScale + k;
+    dst->s = mine.s;
+    dst->s2 = mine.s2;
+    dst->bad = mine.bad;
+    __threadfence_system();
+    st_release_sys(&dst->seq, seq);
+    // pull: wait for row t of my own buffer
+    const PeerSlot* src = (const PeerSlot*)peers[rank] + ((size_t)bank * kPeerMaxRanks + t) * kMaxScale + k;
+    unsigned long long t0 = 0;
+    unsigned spins = 0;
+    while (ld_acquire_sys(&src->seq) != seq) {
+      if ((++spins & 1023u) == 0) {  // look at the clock every ~1000 polls
+        const unsigned long long now = globaltimer_ns();
+        if (t0 == 0) t0 = now;
+        if (now - t0 > timeout_ns) {
+          timed_out = 1;
+          break;
+        }
+      }
+      __nanosleep(32);
+    }
+  }
+  __syncthreads();
+  if (t == 0) {
+    Partial out;
+    out.s = 0.0;
+    out.s2 = 0.0;
+    out.bad = -1;
+    const PeerSlot* base = (const PeerSlot*)peers[rank] + (size_t)bank * kPeerMaxRanks * kMaxScale + k;
+    for (int w = 0; w < nranks; ++w) {  // rank order: the same sum on every rank
+      const volatile PeerSlot* v = base + (size_t)w * kMaxScale;  // written by a peer during this kernel: no L1
+      const double vs = v->s, vs2 = v->s2;
+      const long long vb = v->bad;
+      out.s += vs;
+      out.s2 += vs2;
+      out.bad = vb > out.bad ? vb : out.bad;
+    }
+    if (timed_out) out.bad = 1ll << 61;
+    result[k] = out;
+  }
+}
+
+static unsigned long long peer_timeout_ns() {  // SPX_PEER_TIMEOUT_S: how long a rank waits for its peers (default 120 s)
+  static const unsigned long long v = [] {
+    const char* e = getenv("SPX_PEER_TIMEOUT_S");
+    double sec = e ? atof(e) : 120.0;
+    if (!(sec > 0.0)) sec = 120.0;
+    return (unsigned long long)(sec * 1e9);
+  }();
+  return v;
+}
+
+bool comm_peer_ready(const spx_ctx* ctx) { return ctx->d_peer_ptrs != nullptr && ctx->peer_nranks == ctx->comm_nranks; }
+
+int32_t comm_fold_allreduce_peer(spx_ctx* ctx, int nblocks, int nslot) {
+  ctx->peer_seq += 1;
+  fold_allreduce_peer_kernel<<<nslot, 256, 0, ctx->stream>>>(ctx->d_partials, nblocks > 0 ? nblocks : 0, ctx->d_result,
+                                                             ctx->d_peer_ptrs, ctx->peer_nranks, ctx->comm_rank,
+                                                             ctx->peer_seq, peer_timeout_ns());
+  ctx->launches++;
+  ctx->collectives += 1;
+  SPX_CUDA(cudaGetLastError());
   return SPX_OK;
 }
 
@@ -211,7 +338,8 @@ int32_t spx_comm_destroy(spx_ctx* ctx) {
 
 int32_t spx_comm_reduce_scalars(spx_ctx* ctx, int32_t on) {
   SPX_REQUIRE(ctx != nullptr, "null context");
-  SPX_REQUIRE(on == 0 || ctx->comm != nullptr, "no communicator on this context (spx_comm_init)");
+  SPX_REQUIRE(on == 0 || ctx->comm != nullptr || ctx->d_peer_ptrs != nullptr,
+              "no communicator on this context (spx_comm_init / spx_comm_peer_attach)");
   ctx->reduce_scalars = on != 0;
   return SPX_OK;
 }
@@ -221,6 +349,68 @@ int32_t spx_comm_info(spx_ctx* ctx, int32_t* nranks, int32_t* rank, int64_t* col
   if (nranks) *nranks = ctx->comm ? ctx->comm_nranks : 1;
   if (rank) *rank = ctx->comm ? ctx->comm_rank : 0;
   if (collectives) *collectives = ctx->collectives;
+  return SPX_OK;
+}
+
+int32_t spx_comm_peer_export(spx_ctx* ctx, void* handle_out) {
+  SPX_REQUIRE(ctx != nullptr && handle_out != nullptr, "null argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == SPX_PEER_HANDLE_BYTES, "IPC handle size");
+  DeviceGuard g(ctx->device);
+  if (ctx->peer_own == nullptr) {
+    SPX_CUDA(cudaMalloc(&ctx->peer_own, kPeerBytes));
+    SPX_CUDA(cudaMemset(ctx->peer_own, 0, kPeerBytes));
+  }
+  cudaIpcMemHandle_t h;
+  SPX_CUDA(cudaIpcGetMemHandle(&h, ctx->peer_own));
+  memcpy(handle_out, &h, sizeof(h));
+  return SPX_OK;
+}
+
+int32_t spx_comm_peer_attach(spx_ctx* ctx, int32_t nranks, int32_t rank, const void* handles) {
+  SPX_REQUIRE(ctx != nullptr && handles != nullptr, "null argument");
+  SPX_REQUIRE(nranks >= 1 && nranks <= kPeerMaxRanks && rank >= 0 && rank < nranks, "bad rank / nranks");
+  SPX_REQUIRE(ctx->peer_own != nullptr, "call spx_comm_peer_export first");
+  SPX_REQUIRE(ctx->d_peer_ptrs == nullptr, "exchange buffers already attached");
+  DeviceGuard g(ctx->device);
+  void* ptrs[kPeerMaxRanks] = {};
+  for (int r = 0; r < nranks; ++r) {
+    if (r == rank) {
+      ptrs[r] = ctx->peer_own;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char*)handles + (size_t)r * sizeof(h), sizeof(h));
+    cudaError_t e = cudaIpcOpenMemHandle(&ptrs[r], h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      for (int q = 0; q < r; ++q)
+        if (q != rank && ptrs[q]) cudaIpcCloseMemHandle(ptrs[q]);
+      return cuda_fail(e, "cudaIpcOpenMemHandle (peer exchange buffer)");
+    }
+    ctx->peer_mapped[r] = ptrs[r];
+  }
+  SPX_CUDA(cudaMalloc((void**)&ctx->d_peer_ptrs, sizeof(void*) * kPeerMaxRanks));
+  SPX_CUDA(cudaMemcpy(ctx->d_peer_ptrs, ptrs, sizeof(void*) * kPeerMaxRanks, cudaMemcpyHostToDevice));
+  ctx->peer_nranks = nranks;
+  ctx->comm_rank = rank;
+  if (ctx->comm == nullptr) ctx->comm_nranks = nranks;  // the peer exchange alone carries the scalar reductions
+  ctx->peer_seq = 0;
+  return SPX_OK;
+}
+
+int32_t spx_comm_peer_active(spx_ctx* ctx) { return ctx != nullptr && comm_peer_ready(ctx) ? 1 : 0; }
+
+int32_t spx_comm_peer_detach(spx_ctx* ctx) {
+  SPX_REQUIRE(ctx != nullptr, "null context");
+  DeviceGuard g(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (int r = 0; r < kPeerMaxRanks; ++r)
+    if (ctx->peer_mapped[r]) {
+      cudaIpcCloseMemHandle(ctx->peer_mapped[r]);
+      ctx->peer_mapped[r] = nullptr;
+    }
+  if (ctx->d_peer_ptrs) cudaFree(ctx->d_peer_ptrs);
+  ctx->d_peer_ptrs = nullptr;
+  ctx->peer_nranks = 0;
   return SPX_OK;
 }
 

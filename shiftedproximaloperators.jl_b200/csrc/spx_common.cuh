@@ -73,6 +73,14 @@ struct spx_ctx {
   bool reduce_scalars = false;  // every folded reduction is all-reduced on the device before it reaches the host
   double* d_comm = nullptr;     // packed scalars of a multi-slot reduction
   long long collectives = 0;
+  // peer-memory exchange (spx_comm_peer_*): every rank's exchange buffer mapped into this process over NVLink;
+  // the fold kernel of a reduction then finishes the all-reduce itself (stores into the peers, spin on its own buffer)
+  void* peer_own = nullptr;        // this rank's exchange buffer (cudaMalloc, exported by IPC handle)
+  void** d_peer_ptrs = nullptr;    // device array [nranks]: every rank's exchange buffer as seen from here
+  void* peer_mapped[16] = {};      // host copies of the mapped pointers (closed on destroy)
+  int peer_nranks = 0;
+  unsigned long long peer_seq = 0;  // all-reduces done so far (the same number on every rank)
+  int* d_peer_fail = nullptr;
 };
 
 namespace spx {
@@ -265,6 +273,9 @@ int32_t comm_allreduce_result(spx_ctx* ctx, int nslot);
 int32_t comm_allreduce_raw(spx_ctx* ctx, void* buf, size_t count, int nccl_dtype, int nccl_op);
 // ncclDataType_t / ncclRedOp_t values (checked against nccl.h in spx_comm.cu), for callers that do not include nccl.h
 constexpr int kNcclInt64 = 4, kNcclUint64 = 5, kNcclFloat64 = 8, kNcclSum = 0, kNcclMax = 2;
+// spx_comm.cu: fold + all-reduce over peer memory in ONE kernel (when the exchange buffers are attached)
+bool comm_peer_ready(const spx_ctx* ctx);
+int32_t comm_fold_allreduce_peer(spx_ctx* ctx, int nblocks, int nslot);
 // enqueue only: fold `nblocks` partials at `partials` into *result on `stream`
 int32_t enqueue_fold(spx_ctx* ctx, cudaStream_t stream, const Partial* partials, int nblocks, Partial* result);
 

@@ -102,6 +102,20 @@ int32_t finalize_partials(spx_ctx* ctx, int nblocks, int nslot, bool) {
     }
     return SPX_OK;
   }
+  if (global && comm_peer_ready(ctx)) {
+    // one kernel: fold this rank's partials, store the folded slots into every peer's exchange buffer over NVLink,
+    // wait for the peers' slots in our own buffer, sum in rank order (identical bits on every rank)
+    int32_t st = comm_fold_allreduce_peer(ctx, nblocks, nslot);
+    if (st != SPX_OK) return st;
+    SPX_CUDA(cudaMemcpyAsync(ctx->h_result, ctx->d_result, sizeof(Partial) * nslot, cudaMemcpyDeviceToHost, ctx->stream));
+    SPX_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int k = 0; k < nslot; ++k)
+      if (ctx->h_result[k].bad == (1ll << 61)) {
+        set_error("peer all-reduce timed out: a rank did not reach the same reduction");
+        return SPX_E_INVALID;
+      }
+    return SPX_OK;
+  }
   if (nblocks > 0) {
     fold_kernel<<<nslot, 256, 0, ctx->stream>>>(ctx->d_partials, nblocks, ctx->d_result);
     ctx->launches++;
@@ -296,6 +310,8 @@ int32_t spx_ctx_destroy(spx_ctx* c) {
     if (c->pipe_events[i]) cudaEventDestroy(c->pipe_events[i]);
   if (c->pipe_buf) cudaFree(c->pipe_buf);
   if (c->d_scratch) cudaFree(c->d_scratch);
+  spx_comm_peer_detach(c);
+  if (c->peer_own) cudaFree(c->peer_own);
   spx_comm_destroy(c);
   if (c->d_comm) cudaFree(c->d_comm);
   cudaFree(c->d_partials);

@@ -27,9 +27,16 @@ import torch.distributed as dist
 
 
 # ------------------------------------------------- collectives inside the library ---
-def comm_init(device=None, group=None) -> None:
+def comm_init(device=None, group=None, peer=None) -> None:
     """Attach an NCCL communicator to this rank's libshiftedprox context (spx_comm_init): rank 0 draws the id
-    (spx_comm_unique_id), `torch.distributed` broadcasts its 128 bytes, every rank joins."""
+    (spx_comm_unique_id), `torch.distributed` broadcasts its 128 bytes, every rank joins.
+
+    `peer` (default: on unless SPX_PEER=0): also map every rank's exchange buffer into every process
+    (spx_comm_peer_export / _attach, CUDA IPC over NVLink), so that the scalar reductions are finished by the fold
+    kernel itself instead of a separate NCCL launch.  All ranks agree on the outcome: if one cannot map a peer
+    (no P2P path, IPC closed in the container) every rank detaches and the reductions stay on NCCL."""
+    import os
+
     from . import _lib as L, context
 
     if not (dist.is_available() and dist.is_initialized()):
@@ -45,6 +52,45 @@ def comm_init(device=None, group=None) -> None:
     dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
     raw = bytes(t.cpu().tolist())
     L.call("spx_comm_init", ctx, C.c_int32(world), C.c_int32(rank), C.c_char_p(raw))
+    if peer is None:
+        peer = os.environ.get("SPX_PEER", "1") != "0"
+    if peer and 1 < world <= 16:
+        _peer_attach(ctx, rank, world, carrier, group)
+
+
+def _peer_attach(ctx, rank, world, carrier, group) -> bool:
+    from . import _lib as L
+
+    hbuf = (C.c_ubyte * 64)()
+    ok = 1
+    try:
+        L.call("spx_comm_peer_export", ctx, hbuf)
+    except Exception:
+        ok = 0
+    mine = torch.tensor(list(hbuf), dtype=torch.uint8, device=carrier)
+    every = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(every, mine, group=group)
+    if ok:
+        raw = b"".join(bytes(e.cpu().tolist()) for e in every)
+        try:
+            L.call("spx_comm_peer_attach", ctx, C.c_int32(world), C.c_int32(rank), C.c_char_p(raw))
+        except Exception:
+            ok = 0
+    flag = torch.tensor([ok], dtype=torch.int32, device=carrier)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+    if int(flag.item()) == 0:
+        L.call("spx_comm_peer_detach", ctx)
+        return False
+    return True
+
+
+def comm_peer_active(device=None) -> bool:
+    """True when this rank's scalar reductions go over the peer-mapped exchange buffers (one fused kernel)."""
+    from . import _lib as L, context
+
+    lib = L.lib()
+    lib.spx_comm_peer_active.restype = C.c_int32
+    return bool(lib.spx_comm_peer_active(context(device if device is not None else torch.cuda.current_device())))
 
 
 def comm_destroy(device=None) -> None:
