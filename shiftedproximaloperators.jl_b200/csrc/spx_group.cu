@@ -25,10 +25,12 @@ constexpr int kTask = 32;  // consecutive groups per warp task
 // read per operand like the short groups (the warp path would stash and re-read them)
 constexpr long long kBigMin = 1024, kBigMax = 4096;
 constexpr int kBigE = (int)(kBigMax / kGroupThreads);
-__device__ __forceinline__ bool is_big(long long m) { return m > kBigMin && m <= kBigMax; }
+// CTA-per-group classes of ShiftedGroupNormL2: (kMidMin, kBigMin] with 128 threads, (kBigMin, kBigMax] with 256
+constexpr long long kMidMin = 256;
+__device__ __forceinline__ bool is_big(long long m) { return m > kMidMin && m <= kBigMax; }
 
 #ifdef SPX_GROUP_STATS
-__device__ unsigned long long g_stat_evals = 0, g_stat_groups = 0;
+__device__ unsigned long long g_stat_evals = 0, g_stat_groups = 0, g_stat_big[3] = {0, 0, 0};  // big: evals, groups, rejected
 #endif
 
 template <class R> __device__ __forceinline__ R ldv(const R* p) {
@@ -327,29 +329,128 @@ __global__ void __launch_bounds__(kGroupThreads)
 // Every CTA scans chunks of 256 groups (grid-stride), lists the big ones in index order and takes them one
 // after the other: 16 elements per thread in registers (all 48 loads of a thread in flight at once), one block
 // reduction for the norm, y written once.
-__device__ __forceinline__ double block_sum(double v, double* red) {
+template <int T = kGroupThreads> __device__ __forceinline__ double block_sum(double v, double* red) {
   v = warp_sum(v);
   __syncthreads();  // red reuse
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
   __syncthreads();
   double t = 0.0;
 #pragma unroll
-  for (int w = 0; w < kGroupThreads / 32; ++w) t += red[w];
+  for (int w = 0; w < T / 32; ++w) t += red[w];
   return t;
 }
-// index-ordered list of the big groups of one chunk; returns how many
-__device__ __forceinline__ int list_big_groups(const long long* __restrict__ offs, long long g0, long long ngroups,
-                                               int* list, int* wcount) {
+// L2 prefetch of elements [b, e) of up to three operand vectors by the whole CTA (T threads): a CTA-per-group kernel
+// issues this for its NEXT group right after the loads of the current one, so the next load phase finds its lines in L2
+// instead of paying HBM latency with nothing else in flight.
+template <class R, int T>
+__device__ __forceinline__ void prefetch_group_l2(const R* p0, const R* p1, const R* p2, long long b, long long e) {
+  const R* ps[3] = {p0, p1, p2};
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    if (ps[a] == nullptr) continue;
+    const uintptr_t lo = (uintptr_t)(ps[a] + b) & ~(uintptr_t)127, hi = (uintptr_t)(ps[a] + e);
+    for (uintptr_t l = lo + (uintptr_t)threadIdx.x * 128u; l < hi; l += (uintptr_t)T * 128u)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(l));
+  }
+}
+
+// one element (8 or 4 bytes) global -> shared, asynchronously: group starts are only element-aligned
+template <class R> __device__ __forceinline__ void cp_async_elem(uint32_t dst, const R* src) {
+  if (sizeof(R) == 8)
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+  else
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+// the CTA's copy of group [b, e) into the staging planes (thread t: elements b + t, b + T + t, ... into slots t, T + t,
+// ...: its own slots, which only it reads back, so cp.async.wait_group is the only synchronisation).  NP planes of PL
+// elements: q | xk | sj
+template <class R, int T, int EMAX, int PL, int NP>
+__device__ __forceinline__ void stage_group_async(R* stage, const R* q, const R* xk, const R* sj, long long b, long long e) {
+  const int t = threadIdx.x;
+  const uint32_t a0 = (uint32_t)__cvta_generic_to_shared(stage + t);
+#pragma unroll
+  for (int k = 0; k < EMAX; ++k) {
+    const long long i = b + (long long)k * T + t;
+    if (i < e) {
+      const uint32_t o = a0 + (uint32_t)(k * T * (int)sizeof(R));
+      cp_async_elem<R>(o, q + i);
+      if (NP > 1) {
+        cp_async_elem<R>(o + (uint32_t)(PL * (int)sizeof(R)), xk + i);
+        cp_async_elem<R>(o + (uint32_t)(2 * PL * (int)sizeof(R)), sj + i);
+      }
+    }
+  }
+  cp_async_commit();
+}
+
+// ---- TMA bulk copies (cp.async.bulk, one elected thread) for the CTA-per-group classes -------------------------------
+// A group is a contiguous run of each operand vector, so one thread moves it with three bulk copies that complete on an
+// mbarrier: no LSU instructions, no registers, any thread may read any element afterwards.  Bulk copies want 16-byte
+// aligned addresses and sizes while a group starts on an element boundary: the copy starts at the 16-byte granule that
+// holds the first element and ends with the granule that holds the last one (the few neighbouring bytes of the same
+// granules are read and ignored -- a granule that holds a valid byte lies in the same page); `skip` elements of
+// padding result at the front of each plane, per operand.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tSPX_MBAR_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra SPX_MBAR_DONE;\n\t"
+      "bra SPX_MBAR_WAIT;\n\tSPX_MBAR_DONE:\n\t}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// orders the CTA's earlier generic-proxy reads of the planes before the async-proxy writes of the next bulk copy
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <class R> __device__ __forceinline__ int bulk_skip(const R* p) {  // elements of front padding in the plane
+  return (int)(((uintptr_t)p & 15u) / sizeof(R));
+}
+// elements per staging plane of a class of groups of up to `maxm` elements (the padding of both ends included)
+template <class R> __host__ __device__ constexpr int bulk_plane(int maxm) { return maxm + 2 * (int)(16 / sizeof(R)); }
+// called by ONE thread: group [b, e) of NP operands into planes of PLS elements, completion on `bar`
+template <class R, int NP, int PLS>
+__device__ __forceinline__ void stage_group_bulk(R* stage, uint64_t* bar, const R* q, const R* xk, const R* sj, long long b,
+                                                 long long e) {
+  const R* ps[3] = {q, xk, sj};
+  uintptr_t lo[NP];
+  uint32_t bytes[NP], total = 0;
+#pragma unroll
+  for (int a = 0; a < NP; ++a) {
+    lo[a] = (uintptr_t)(ps[a] + b) & ~(uintptr_t)15;
+    bytes[a] = (uint32_t)((((uintptr_t)(ps[a] + e) + 15u) & ~(uintptr_t)15) - lo[a]);
+    total += bytes[a];
+  }
+  mbar_expect_tx(bar, total);
+#pragma unroll
+  for (int a = 0; a < NP; ++a) bulk_g2s(stage + a * PLS, (const void*)lo[a], bytes[a], bar);
+}
+
+// index-ordered list of one chunk's (T groups) members of the class LO < m <= HI; returns how many
+template <int T, int LO, int HI>
+__device__ __forceinline__ int list_class_groups(const long long* __restrict__ offs, long long g0, long long ngroups,
+                                                 int* list, int* wcount) {
   const int t = threadIdx.x, lane = t & 31, w = t >> 5;
   const long long g = g0 + t;
-  const bool big = g < ngroups && is_big(offs[g + 1] - offs[g]);
+  const long long m = g < ngroups ? offs[g + 1] - offs[g] : 0;
+  const bool big = m > LO && m <= HI;
   const unsigned bal = __ballot_sync(0xffffffffu, big);
   __syncthreads();  // list / wcount reuse
   if (lane == 0) wcount[w] = __popc(bal);
   __syncthreads();
   int base = 0, total = 0;
 #pragma unroll
-  for (int ww = 0; ww < kGroupThreads / 32; ++ww) {
+  for (int ww = 0; ww < T / 32; ++ww) {
     if (ww < w) base += wcount[ww];
     total += wcount[ww];
   }
@@ -358,32 +459,42 @@ __device__ __forceinline__ int list_big_groups(const long long* __restrict__ off
   return total;
 }
 
-// one group of the CTA-per-group class, E elements per thread (E * 256 >= m); returns the group's ψ term
-template <class R, bool PSI, bool SHIFTED, int E>
+// one group of a CTA-per-group class, E elements per thread (E T >= m); returns the group's ψ term.  The group has
+// been bulk-copied into staging buffer `stage`; once every thread holds its elements in registers (the barrier of the
+// first block sum) thread 0 refills the buffer with the group ST places further down the list, so that group's HBM
+// latency is spent under the work on the ST - 1 groups in between (ST = 1: under this group's scaling and stores).
+template <class R, bool PSI, bool SHIFTED, int E, int T, int PLS>
 __device__ __forceinline__ double l2_big_group(R* y, const R* xk, const R* sj, const R* q, long long b, long long e, R lam,
-                                               R sigma, double* red) {
+                                               R sigma, double* red, R* stage, uint64_t* bar, long long nb, long long ne) {
   const int t = threadIdx.x;
   R sol[E], xs[E];
   double ss = 0.0;
+  const R* pq = stage + bulk_skip(q + b) + t;
+  const R* px = stage + PLS + bulk_skip(xk + b) + t;
+  const R* pj = stage + 2 * PLS + bulk_skip(sj + b) + t;
 #pragma unroll
   for (int k = 0; k < E; ++k) {
-    const long long i = b + (long long)k * kGroupThreads + t;
+    const long long i = b + (long long)k * T + t;
     sol[k] = R(0);
     xs[k] = R(0);
     if (i < e) {
-      const R xi = SHIFTED ? ldv(xk + i) : R(0), si = SHIFTED ? ldv(sj + i) : R(0), qi = ldv(q + i);
+      const R xi = SHIFTED ? px[k * T] : R(0), si = SHIFTED ? pj[k * T] : R(0), qi = pq[k * T];
       sol[k] = (qi + xi) + si;  // shiftedGroupNormL2.jl:65
       xs[k] = xi + si;
       ss += (double)sol[k] * (double)sol[k];
     }
   }
-  ss = block_sum(ss, red);
+  ss = block_sum<T>(ss, red);
+  if (t == 0 && ne > nb) {
+    fence_proxy_async();
+    stage_group_bulk<R, SHIFTED ? 3 : 1, PLS>(stage, bar, q, xk, sj, nb, ne);
+  }
   const R snorm = (R)sqrt(ss);
   const R alpha = jl_max(R(1) - sigma * lam / snorm, R(0));
   double vv = 0.0;
 #pragma unroll
   for (int k = 0; k < E; ++k) {
-    const long long i = b + (long long)k * kGroupThreads + t;
+    const long long i = b + (long long)k * T + t;
     if (i < e) {
       const R o = (snorm == R(0) ? R(0) : alpha * sol[k]) - xs[k];  // :70-77
       stv(y + i, o);
@@ -394,32 +505,58 @@ __device__ __forceinline__ double l2_big_group(R* y, const R* xk, const R* sj, c
     }
   }
   if (!PSI) return 0.0;
-  vv = block_sum(vv, red);
+  vv = block_sum<T>(vv, red);
   // shifted: λ_g ‖(xk + sj + y)_g‖; unshifted: λ_g ‖x_g‖ of the input (groupNormL2.jl:49-54)
   return (double)(lam * (SHIFTED ? (R)sqrt(vv) : snorm));
 }
 
-template <class R, bool PSI, bool SHIFTED>
-__global__ void __launch_bounds__(kGroupThreads)
+// T threads per group of LO < m <= EB T elements (EA per thread up to EA T elements, EB above); ST staging buffers
+template <class R, bool PSI, bool SHIFTED, int T, int LO, int EA, int EB, int ST>
+__global__ void __launch_bounds__(T, (sizeof(R) == 4 ? 3 : 2) * 256 / T)
     group_l2_big_kernel(R* y, const R* xk, const R* sj, const R* q, long long ngroups,
                         const long long* __restrict__ offs, const R* __restrict__ lambda_g, R sigma,
                         Partial* __restrict__ partials) {
-  __shared__ int list[kGroupThreads];
-  __shared__ int wcount[kGroupThreads / 32];
-  __shared__ double red[kGroupThreads / 32];
+  constexpr int PLS = bulk_plane<R>(EB * T), NP = SHIFTED ? 3 : 1;
+  __shared__ int list[T];
+  __shared__ int wcount[T / 32];
+  __shared__ double red[T / 32];
+  __shared__ __align__(8) uint64_t bar[ST];
+  extern __shared__ __align__(128) unsigned char l2_stage_raw[];
+  R* const stage0 = reinterpret_cast<R*>(l2_stage_raw);  // ST buffers of q | xk | sj, PLS elements each
   const int t = threadIdx.x;
+  if (t == 0)
+    for (int s = 0; s < ST; ++s) mbar_init(&bar[s], 1);
+  __syncthreads();
+  uint32_t phases = 0;  // bit s: the parity buffer s completes next
   double psi = 0.0;
-  for (long long g0 = (long long)blockIdx.x * kGroupThreads; g0 < ngroups; g0 += (long long)gridDim.x * kGroupThreads) {
-    const int nbig = list_big_groups(offs, g0, ngroups, list, wcount);
+  for (long long g0 = (long long)blockIdx.x * T; g0 < ngroups; g0 += (long long)gridDim.x * T) {
+    const int nbig = list_class_groups<T, LO, EB * T>(offs, g0, ngroups, list, wcount);
+    if (t == 0) {
+      fence_proxy_async();
+      for (int s = 0; s < ST && s < nbig; ++s) {
+        const long long gf = g0 + list[s];
+        stage_group_bulk<R, NP, PLS>(stage0 + s * NP * PLS, &bar[s], q, xk, sj, offs[gf], offs[gf + 1]);
+      }
+    }
     for (int j = 0; j < nbig; ++j) {
+      const int sidx = j % ST;
       const long long g = g0 + list[j];
       const long long b = offs[g], e = offs[g + 1];
       const R lam = lambda_g[g];
+      long long nb = 0, ne = 0;
+      if (j + ST < nbig) {
+        const long long gn = g0 + list[j + ST];
+        nb = offs[gn];
+        ne = offs[gn + 1];
+      }
+      mbar_wait(&bar[sidx], (phases >> sidx) & 1u);
+      phases ^= 1u << sidx;
+      R* const stage = stage0 + sidx * NP * PLS;
       double term;
-      if (e - b <= (kBigE / 2) * kGroupThreads)
-        term = l2_big_group<R, PSI, SHIFTED, kBigE / 2>(y, xk, sj, q, b, e, lam, sigma, red);
+      if (e - b <= EA * T)
+        term = l2_big_group<R, PSI, SHIFTED, EA, T, PLS>(y, xk, sj, q, b, e, lam, sigma, red, stage, &bar[sidx], nb, ne);
       else
-        term = l2_big_group<R, PSI, SHIFTED, kBigE>(y, xk, sj, q, b, e, lam, sigma, red);
+        term = l2_big_group<R, PSI, SHIFTED, EB, T, PLS>(y, xk, sj, q, b, e, lam, sigma, red, stage, &bar[sidx], nb, ne);
       if (PSI && t == 0) psi += term;
     }
   }
@@ -1212,11 +1349,12 @@ __global__ void __launch_bounds__(kGroupThreads, FAST ? SPX_GU_MINB : 2)
 // (|froot(n)| / froot'(n) within max(2, min(16, 1/κ)) ulps of n).  Groups that fail a guard or the test are left -- unmarked
 // in `done` -- to the bracketing search of the warp path, which runs afterwards.
 constexpr int kBinfBigThreads = 256;  // two CTAs per SM, 16 (or 8) elements per thread; 512 threads x 8 measured slower
-struct BigRed {
-  double v[2][kBinfBigThreads / 32][4];
+constexpr int kBinfMidThreads = 128;  // groups of 257..1024 elements: four CTAs per SM, 8 (or 4) elements per thread
+template <int T> struct BigRed {
+  double v[2][T / 32][4];
 };
 // sums a[0..N) over the CTA; every thread gets the totals.  One barrier per call (slots alternate by `parity`).
-template <int N> __device__ __forceinline__ void block_sums(double (&a)[N], BigRed& red, int& parity) {
+template <int N, int T> __device__ __forceinline__ void block_sums(double (&a)[N], BigRed<T>& red, int& parity) {
 #pragma unroll
   for (int k = 0; k < N; ++k) a[k] = warp_sum(a[k]);
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -1229,32 +1367,50 @@ template <int N> __device__ __forceinline__ void block_sums(double (&a)[N], BigR
   for (int k = 0; k < N; ++k) {
     double t = 0.0;
 #pragma unroll
-    for (int ww = 0; ww < kBinfBigThreads / 32; ++ww) t += red.v[parity][ww][k];
+    for (int ww = 0; ww < T / 32; ++ww) t += red.v[parity][ww][k];
     a[k] = t;
   }
   parity ^= 1;
 }
-#ifndef SPX_BINF_BIG_MIN
-#define SPX_BINF_BIG_MIN 1024
-#endif
-__device__ __forceinline__ bool is_binf_big(long long m) { return m > SPX_BINF_BIG_MIN && m <= kBigMax; }
 
 // one group, E elements per thread (E * 256 >= m).  Returns true when y_g has been written.
-template <class R, int E>
+template <class R, int E, int T, int PL>
 __device__ __forceinline__ bool binf_big_group(R* y, const R* xk, const R* sj, const R* q, long long b, long long e,
-                                               R lam, R sigma, R delta, const UDiv<R>& by_sigma, BigRed& red,
-                                               int& parity) {
+                                               R lam, R sigma, R delta, const UDiv<R>& by_sigma, BigRed<T>& red,
+                                               int& parity, R* stage) {
   const int t = threadIdx.x;
   const R epsR = Eps<R>::value;
   const R sl = lam * sigma;
   R sol[E], xkr[E];
+  // every thread copies ITS elements of q, xk, sj into its slots of the staging planes (no registers tied up by loads
+  // in flight, all of them issued before the first use, nobody else reads the slots: cp.async.wait_group is the only
+  // synchronisation); sj stays there for the write phase
+  R* const st_q = stage + t;
+  R* const st_x = stage + PL + t;
+  R* const st_s = stage + 2 * PL + t;
+  {
+    const uint32_t aq = (uint32_t)__cvta_generic_to_shared(st_q), ax = (uint32_t)__cvta_generic_to_shared(st_x),
+                   as = (uint32_t)__cvta_generic_to_shared(st_s);
+#pragma unroll
+    for (int k = 0; k < E; ++k) {
+      const long long i = b + (long long)k * T + t;
+      if (i < e) {
+        const uint32_t o = (uint32_t)(k * T * (int)sizeof(R));
+        cp_async_elem<R>(aq + o, q + i);
+        cp_async_elem<R>(ax + o, xk + i);
+        cp_async_elem<R>(as + o, sj + i);
+      }
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+  }
 #pragma unroll
   for (int k = 0; k < E; ++k) {
-    const long long i = b + (long long)k * kBinfBigThreads + t;
+    const long long i = b + (long long)k * T + t;
     sol[k] = R(0);
     xkr[k] = R(0);
     if (i < e) {
-      const R xi = ldv(xk + i), si = ldv(sj + i), qi = ldv(q + i);
+      const R xi = st_x[k * T], si = st_s[k * T], qi = st_q[k * T];
       sol[k] = (qi + xi) + si;  // :80
       xkr[k] = xi;
     }
@@ -1277,7 +1433,7 @@ __device__ __forceinline__ bool binf_big_group(R* y, const R* xk, const R* sj, c
       nm[2] = __fma_rn((double)xkr[k], (double)xkr[k], nm[2]);
       xmax = jl_abs(xkr[k]) > xmax ? jl_abs(xkr[k]) : xmax;
     }
-    block_sums<3>(nm, red, parity);
+    block_sums<3, T>(nm, red, parity);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       const R other = __shfl_xor_sync(0xffffffffu, xmax, o);
@@ -1289,7 +1445,7 @@ __device__ __forceinline__ bool binf_big_group(R* y, const R* xk, const R* sj, c
     __syncthreads();
     double m = 0.0;
 #pragma unroll
-    for (int ww = 0; ww < kBinfBigThreads / 32; ++ww) m = red.v[parity][ww][0] > m ? red.v[parity][ww][0] : m;
+    for (int ww = 0; ww < T / 32; ++ww) m = red.v[parity][ww][0] > m ? red.v[parity][ww][0] : m;
     xmax = (R)m;
     parity ^= 1;
   }
@@ -1307,7 +1463,10 @@ __device__ __forceinline__ bool binf_big_group(R* y, const R* xk, const R* sj, c
       binf_term<R, double>(sol[k + 1], xkr[k + 1], tau, sdc, a1, b1);
     }
     double ab[2] = {a0 + a1, b0 + b1};
-    block_sums<2>(ab, red, parity);
+#ifdef SPX_GROUP_STATS
+    if (threadIdx.x == 0) atomicAdd(&g_stat_big[0], 1ull);
+#endif
+    block_sums<2, T>(ab, red, parity);
     ssA = ab[0];
     ssB = ab[1];
   };
@@ -1362,7 +1521,7 @@ __device__ __forceinline__ bool binf_big_group(R* y, const R* xk, const R* sj, c
     sol[k] = sol[k] - sigma * softthres_sel(quot_uniform(sol[k], by_sigma) - step * xkr[k], dstep2);
     vs[0] = __fma_rn((double)sol[k], (double)sol[k], vs[0]);
   }
-  block_sums<1>(vs, red, parity);
+  block_sums<1, T>(vs, red, parity);
   const R nv = (R)sqrt_fast(vs[0]);
   if (!zero_out) {
     const R res = nroot - nv;
@@ -1374,33 +1533,38 @@ __device__ __forceinline__ bool binf_big_group(R* y, const R* xk, const R* sj, c
   const R alpha = zero_out ? R(0) : jl_max(R(0), R(1) - div_fast(sl, nv));
 #pragma unroll
   for (int k = 0; k < E; ++k) {
-    const long long i = b + (long long)k * kBinfBigThreads + t;
+    const long long i = b + (long long)k * T + t;
     if (i < e) {
       const R o = zero_out ? R(0) : alpha * sol[k];
-      stv(y + i, o - (xkr[k] + sj[i]));
+      stv(y + i, o - (xkr[k] + st_s[k * T]));
     }
   }
   return true;
 }
 
-template <class R>
-__global__ void __launch_bounds__(kBinfBigThreads, 2)
+// T threads per group; groups of LO < m <= EA T elements with EA elements per thread, up to EB T with EB
+template <class R, int T, int LO, int EA, int EB>
+__global__ void __launch_bounds__(T, 512 / T)
     group_l2binf_big_kernel(R* y, const R* xk, const R* sj, const R* q, long long ngroups,
                             const long long* __restrict__ offs, const R* __restrict__ lambda_g, R sigma, R delta,
                             UDiv<R> by_sigma, const unsigned* __restrict__ uniform_flag, unsigned char* __restrict__ done) {
   if (uniform_flag != nullptr && *uniform_flag != 0u) return;
-  __shared__ int list[kBinfBigThreads];
-  __shared__ int wcount[kBinfBigThreads / 32];
-  __shared__ BigRed red;
+  constexpr int PL = EB * T;  // elements per staging plane
+  __shared__ int list[T];
+  __shared__ int wcount[T / 32];
+  __shared__ BigRed<T> red;
+  extern __shared__ __align__(16) unsigned char big_stage_raw[];
+  R* const stage = reinterpret_cast<R*>(big_stage_raw);  // three planes of PL elements: q | xk | sj
   const int t = threadIdx.x;
   int parity = 0;
-  for (long long g0 = (long long)blockIdx.x * kBinfBigThreads; g0 < ngroups; g0 += (long long)gridDim.x * kBinfBigThreads) {
-    // index-ordered list of this chunk's groups of 1025..4096 elements
+  for (long long g0 = (long long)blockIdx.x * T; g0 < ngroups; g0 += (long long)gridDim.x * T) {
+    // index-ordered list of this chunk's groups of LO+1 .. EB T elements
     int nbig;
     {
       const int lane = t & 31, w = t >> 5;
       const long long g = g0 + t;
-      const bool big = g < ngroups && is_binf_big(offs[g + 1] - offs[g]);
+      const long long mg = g < ngroups ? offs[g + 1] - offs[g] : 0;
+      const bool big = mg > LO && mg <= PL;
       const unsigned bal = __ballot_sync(0xffffffffu, big);
       __syncthreads();  // list / wcount reuse
       if (lane == 0) wcount[w] = __popc(bal);
@@ -1408,7 +1572,7 @@ __global__ void __launch_bounds__(kBinfBigThreads, 2)
       int base = 0;
       nbig = 0;
 #pragma unroll
-      for (int ww = 0; ww < kBinfBigThreads / 32; ++ww) {
+      for (int ww = 0; ww < T / 32; ++ww) {
         if (ww < w) base += wcount[ww];
         nbig += wcount[ww];
       }
@@ -1419,12 +1583,19 @@ __global__ void __launch_bounds__(kBinfBigThreads, 2)
       const long long g = g0 + list[j];
       const long long b = offs[g], e = offs[g + 1];
       const R lam = lambda_g[g];
+      if (j + 1 < nbig) {
+        const long long gn = g0 + list[j + 1];
+        prefetch_group_l2<R, T>(q, xk, sj, offs[gn], offs[gn + 1]);
+      }
       bool wrote;
-      if (e - b <= 8 * kBinfBigThreads)
-        wrote = binf_big_group<R, 8>(y, xk, sj, q, b, e, lam, sigma, delta, by_sigma, red, parity);
+      if (e - b <= EA * T)
+        wrote = binf_big_group<R, EA, T, PL>(y, xk, sj, q, b, e, lam, sigma, delta, by_sigma, red, parity, stage);
       else
-        wrote = binf_big_group<R, 16>(y, xk, sj, q, b, e, lam, sigma, delta, by_sigma, red, parity);
+        wrote = binf_big_group<R, EB, T, PL>(y, xk, sj, q, b, e, lam, sigma, delta, by_sigma, red, parity, stage);
       if (wrote && t == 0) done[g] = 1;
+#ifdef SPX_GROUP_STATS
+      if (t == 0) atomicAdd(&g_stat_big[wrote ? 1 : 2], 1ull);
+#endif
     }
   }
 }
@@ -1623,12 +1794,16 @@ static int group_grid(spx_ctx* ctx, int64_t ngroups, const void* kernel) {
   return (int)(want < cap ? want : cap);
 }
 
-// grid of the CTA-per-group kernels: one CTA per chunk of 256 groups, at most the resident CTAs
-static int big_grid(spx_ctx* ctx, int64_t ngroups, const void* kernel) {
+#ifndef SPX_L2_MID_STAGES
+#define SPX_L2_MID_STAGES 2
+#endif
+// grid of a CTA-per-group kernel: one CTA per chunk of `threads` groups, at most the resident CTAs
+static int big_grid(spx_ctx* ctx, int64_t ngroups, const void* kernel, int threads, size_t stage_bytes) {
   int per_sm = 1;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kGroupThreads, 0) != cudaSuccess || per_sm < 1)
+  cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, stage_bytes) != cudaSuccess || per_sm < 1)
     per_sm = 1;
-  long long want = (ngroups + kGroupThreads - 1) / kGroupThreads;
+  long long want = (ngroups + threads - 1) / threads;
   long long cap = (long long)ctx->sm_count * per_sm;
   if (cap > kMaxPartials / 4) cap = kMaxPartials / 4;
   if (want < 1) want = 1;
@@ -1686,27 +1861,39 @@ template <class R, bool SHIFTED>
 static int32_t launch_group_l2(spx_ctx* ctx, int64_t n, R* y, const R* xk, const R* sj, const R* q, int64_t ngroups,
                                const int64_t* offs, const R* lambda_g, R sigma, double* psi_out) {
   (void)n;
-  const int grid2 = big_grid(ctx, ngroups, (const void*)group_l2_big_kernel<R, false, SHIFTED>);
+  // The CTA-per-group classes stage q | xk | sj in shared memory with bulk copies: (1024, 4096] with 256 threads and one
+  // buffer (the copy of the next group runs under the stores of the current one; two CTAs per SM overlap the rest),
+  // (256, 1024] with 128 threads and a ring of two buffers (four CTAs per SM; a ring of four with two CTAs measured 3 % slower).
+  constexpr int kMidT = 128, kMidStages = SPX_L2_MID_STAGES, NP = SHIFTED ? 3 : 1;
+  const size_t big_bytes = NP * (size_t)bulk_plane<R>((int)kBigMax) * sizeof(R);
+  const size_t mid_bytes = kMidStages * NP * (size_t)bulk_plane<R>((int)kBigMin) * sizeof(R);
+  auto big_psi = group_l2_big_kernel<R, true, SHIFTED, kGroupThreads, (int)kBigMin, kBigE / 2, kBigE, 1>;
+  auto big_run = group_l2_big_kernel<R, false, SHIFTED, kGroupThreads, (int)kBigMin, kBigE / 2, kBigE, 1>;
+  auto mid_psi = group_l2_big_kernel<R, true, SHIFTED, kMidT, (int)kMidMin, 4, 8, kMidStages>;
+  auto mid_run = group_l2_big_kernel<R, false, SHIFTED, kMidT, (int)kMidMin, 4, 8, kMidStages>;
   if (psi_out) {
     const int grid0 = group_grid(ctx, ngroups, (const void*)group_l2_kernel<R, true, 0, SHIFTED>);
     const int grid1 = group_grid(ctx, ngroups, (const void*)group_l2_kernel<R, true, 1, SHIFTED>);
+    const int grid2 = big_grid(ctx, ngroups, (const void*)big_psi, kGroupThreads, big_bytes);
+    const int grid3 = big_grid(ctx, ngroups, (const void*)mid_psi, kMidT, mid_bytes);
     group_l2_kernel<R, true, 0, SHIFTED><<<grid0, kGroupThreads, 0, ctx->stream>>>(
         y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, sigma, ctx->d_partials);
     group_l2_kernel<R, true, 1, SHIFTED><<<grid1, kGroupThreads, 0, ctx->stream>>>(
         y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, sigma, ctx->d_partials + grid0);
-    group_l2_big_kernel<R, true, SHIFTED><<<grid2, kGroupThreads, 0, ctx->stream>>>(
-        y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, sigma, ctx->d_partials + grid0 + grid1);
-    ctx->launches += 3;
+    big_psi<<<grid2, kGroupThreads, big_bytes, ctx->stream>>>(y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, sigma,
+                                                             ctx->d_partials + grid0 + grid1);
+    mid_psi<<<grid3, kMidT, mid_bytes, ctx->stream>>>(y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, sigma,
+                                                     ctx->d_partials + grid0 + grid1 + grid2);
+    ctx->launches += 4;
     SPX_CUDA(cudaGetLastError());
-    int32_t st = finalize_partials(ctx, grid0 + grid1 + grid2, 1, false);
+    int32_t st = finalize_partials(ctx, grid0 + grid1 + grid2 + grid3, 1, false);
     if (st != SPX_OK) return st;
     *psi_out = (double)(R)ctx->h_result[0].s;
     return SPX_OK;
   }
-  // The three size classes are independent: they run CONCURRENTLY on the context's side streams (fork / join by
-  // events on the caller's stream), with one short-lived CTA per chunk of work instead of a persistent grid, so the
-  // block scheduler interleaves the three kernels as resources free up.  Alone, none of them fills HBM on a ragged
-  // layout (the long-group classes wait on their reductions, the short-group class on its per-group arithmetic).
+  // The size classes are independent: they run CONCURRENTLY on the context's side streams (fork / join by events on
+  // the caller's stream), with one short-lived CTA per chunk of work instead of a persistent grid, so the block
+  // scheduler interleaves the kernels as resources free up (the short-group class waits on its per-group arithmetic).
   for (int i = 0; i < 2; ++i)
     if (!ctx->pipe_streams[i]) SPX_CUDA(cudaStreamCreateWithFlags(&ctx->pipe_streams[i], cudaStreamNonBlocking));
   for (int i = 13; i < 16; ++i)
@@ -1715,17 +1902,22 @@ static int32_t launch_group_l2(spx_ctx* ctx, int64_t n, R* y, const R* xk, const
   const long long warps_per_cta = kGroupThreads / 32;
   const int grid0 = (int)std::max<long long>(1, std::min<long long>((ntasks + warps_per_cta - 1) / warps_per_cta, 1 << 20));
   const int grid2s = (int)std::max<long long>(1, std::min<long long>((ngroups + kGroupThreads - 1) / kGroupThreads, 1 << 20));
-  (void)grid2;
+  const int grid3s = (int)std::max<long long>(1, std::min<long long>((ngroups + kMidT - 1) / kMidT, 1 << 20));
+  SPX_CUDA(cudaFuncSetAttribute((const void*)big_run, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big_bytes));
+  SPX_CUDA(cudaFuncSetAttribute((const void*)mid_run, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mid_bytes));
   SPX_CUDA(cudaEventRecord(ctx->pipe_events[13], ctx->stream));
   SPX_CUDA(cudaStreamWaitEvent(ctx->pipe_streams[0], ctx->pipe_events[13], 0));
   SPX_CUDA(cudaStreamWaitEvent(ctx->pipe_streams[1], ctx->pipe_events[13], 0));
-  group_l2_big_kernel<R, false, SHIFTED><<<grid2s, kGroupThreads, 0, ctx->stream>>>(
-      y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, sigma, ctx->d_partials);
-  group_l2_kernel<R, false, 1, SHIFTED><<<grid0, kGroupThreads, 0, ctx->pipe_streams[0]>>>(
-      y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, sigma, ctx->d_partials);
+  big_run<<<grid2s, kGroupThreads, big_bytes, ctx->stream>>>(y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, sigma,
+                                                            ctx->d_partials);
+  mid_run<<<grid3s, kMidT, mid_bytes, ctx->pipe_streams[0]>>>(y, xk, sj, q, ngroups, (const long long*)offs, lambda_g,
+                                                             sigma, ctx->d_partials);
   group_l2_kernel<R, false, 0, SHIFTED><<<grid0, kGroupThreads, 0, ctx->pipe_streams[1]>>>(
       y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, sigma, ctx->d_partials);
-  ctx->launches += 3;
+  // groups above 4096 elements: the warp path (its CTAs exit at once when there are none)
+  group_l2_kernel<R, false, 1, SHIFTED><<<grid0, kGroupThreads, 0, ctx->pipe_streams[1]>>>(
+      y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, sigma, ctx->d_partials);
+  ctx->launches += 4;
   SPX_CUDA(cudaGetLastError());
   SPX_CUDA(cudaEventRecord(ctx->pipe_events[14], ctx->pipe_streams[0]));
   SPX_CUDA(cudaEventRecord(ctx->pipe_events[15], ctx->pipe_streams[1]));
@@ -1835,16 +2027,28 @@ static int32_t prox_group(spx_ctx* ctx, bool binf, int64_t n, R* y, const R* xk,
       if (sigma_ok && !(overlaps(xk) || overlaps(sj) || overlaps(q)) && std::getenv("SPX_BINF_NOBIG") == nullptr) {
         done = (unsigned char*)ctx->d_scratch + done_off;
         SPX_CUDA(cudaMemsetAsync(done, 0, (size_t)ngroups, ctx->stream));
-        int per_sm = 1;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)group_l2binf_big_kernel<R>, kBinfBigThreads,
-                                                          0) != cudaSuccess || per_sm < 1)
-          per_sm = 1;
-        const int gridb = (int)std::max<int64_t>(
-            1, std::min<int64_t>((ngroups + kBinfBigThreads - 1) / kBinfBigThreads, (int64_t)ctx->sm_count * per_sm));
-        group_l2binf_big_kernel<R><<<gridb, kBinfBigThreads, 0, ctx->stream>>>(
-            y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, (R)sigma, (R)delta, by_sigma,
-            uni ? uniform_flag : nullptr, done);
-        ctx->launches++;
+        // (1024, 4096]: 256 threads, 8 / 16 elements per thread; (256, 1024]: 128 threads, 4 / 8 per thread
+        auto launch_class = [&](auto kern, int threads, size_t stage_bytes) -> int32_t {
+          int per_sm = 1;
+          SPX_CUDA(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes));
+          if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)kern, threads, stage_bytes) != cudaSuccess ||
+              per_sm < 1)
+            per_sm = 1;
+          const int grid = (int)std::max<int64_t>(
+              1, std::min<int64_t>((ngroups + threads - 1) / threads, (int64_t)ctx->sm_count * per_sm));
+          kern<<<grid, threads, stage_bytes, ctx->stream>>>(y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, (R)sigma,
+                                                           (R)delta, by_sigma, uni ? uniform_flag : nullptr, done);
+          ctx->launches++;
+          return SPX_OK;
+        };
+        int32_t stc = launch_class(group_l2binf_big_kernel<R, kBinfBigThreads, 1024, 8, 16>, kBinfBigThreads,
+                                   3 * (size_t)16 * kBinfBigThreads * sizeof(R));
+        if (stc != SPX_OK) return stc;
+        if (std::getenv("SPX_BINF_NOMID") == nullptr) {
+          stc = launch_class(group_l2binf_big_kernel<R, kBinfMidThreads, 256, 4, 8>, kBinfMidThreads,
+                             3 * (size_t)8 * kBinfMidThreads * sizeof(R));
+          if (stc != SPX_OK) return stc;
+        }
       }
     }
     SPX_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->pipe_events[14], 0));
@@ -1873,10 +2077,13 @@ using namespace spx;
 extern "C" int32_t spx_debug_group_stats(unsigned long long* out2, int reset) {
   cudaMemcpyFromSymbol(out2, g_stat_evals, 8);
   cudaMemcpyFromSymbol(out2 + 1, g_stat_groups, 8);
+  cudaMemcpyFromSymbol(out2 + 2, g_stat_big, 24);  // callers pass room for five counters
   if (reset) {
     unsigned long long z = 0;
     cudaMemcpyToSymbol(g_stat_evals, &z, 8);
     cudaMemcpyToSymbol(g_stat_groups, &z, 8);
+    unsigned long long z3[3] = {0, 0, 0};
+    cudaMemcpyToSymbol(g_stat_big, z3, 24);
   }
   return 0;
 }

@@ -35,9 +35,11 @@ for name in ("g64", "ragged"):
     ng = offs.numel() - 1
     lam = (torch.rand(ng, generator=g, dtype=torch.float64) + 0.5).to(dev)
     psi = sp.shifted(sp.shifted(sp.GroupNormL2(lam, None, offsets=offs), xk, 0.5, sp.NormLinf(1.0)), sj)
-    out = (C.c_ulonglong * 2)()
+    out = (C.c_ulonglong * 5)()
     L.lib().spx_debug_group_stats(out, 1)
     sp.prox_(y, psi, q, 0.3)
     torch.cuda.synchronize()
     L.lib().spx_debug_group_stats(out, 1)
     print(f"{name}: groups {out[1]} (of {ng}), froot evaluations (warp-level) {out[0]}, per group-round {out[0] / max(1, out[1]):.2f}")
+    print(f"   CTA-per-group kernel: {out[3]} accepted, {out[4]} left to the bracketing search, "
+          f"{out[2] / max(1, out[3] + out[4]):.2f} froot evaluations per group (plus the norms pass and the final pass)")
