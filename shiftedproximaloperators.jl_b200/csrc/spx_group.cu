@@ -888,8 +888,20 @@ __global__ void __launch_bounds__(kGroupThreads, PART == 0 ? SPX_GB_MINB : 2)
         pos += 1;
         continue;
       }
+      if (done != nullptr) {  // groups the fast kernel has written: skip the round when none is left
+        const int gi = pos + (lane >> k);
+        const bool todo = gi < th.cnt && !done[g0 + gi];
+        if (!__any_sync(0xffffffffu, todo)) {
+          pos += 32 >> k;
+          continue;
+        }
+      }
       Tile<R, false> t;
       t.load(th, k, pos, lane, xk, sj, q);
+      if (done != nullptr && t.valid && done[g0 + t.group_in_task(pos, k, lane)]) {
+        t.valid = false;  // already written: take part in the round's votes, store nothing
+        t.e = t.b;
+      }
       const R lam = __shfl_sync(0xffffffffu, lam_lane, t.group_in_task(pos, k, lane) & 31);
       TileView<R> gv{t, by_sigma};
       R step;
@@ -1335,6 +1347,91 @@ __global__ void __launch_bounds__(kGroupThreads, FAST ? SPX_GU_MINB : 2)
         }
         st_stream(y + t.base + c * (L * VEC), po);
       }
+    }
+  }
+}
+
+// ---- ragged groups of <= 256 elements: the fast search on the warp rounds of the CSR planner ------------------------
+// Same rounds as group_l2binf_kernel<R, 0> (32 >> k groups of 1 << k lanes, 8 zero-padded elements per lane), same
+// search and acceptance test as the uniform-layout kernel, but per GROUP: an accepted group is written and marked in
+// `done`, anything else is left to the bracketing search that runs afterwards.
+template <class R, int L>
+__device__ __forceinline__ bool binf_tile_search(const Tile<R, true>& t, R lam, R sigma, R delta, R& nroot, double& fp,
+                                                 bool& zero_out) {
+  if constexpr (sizeof(R) == 8) {
+    LoCopy<double> lo;
+    lo.set(t.sol, t.xkr);
+    return binf_fast_search<double, L>(lo.so, lo.xg, t.sol, t.xkr, t.valid, lam, sigma, delta, nroot, fp, zero_out);
+  } else {
+    return binf_fast_search<float, L>(t.sol, t.xkr, t.sol, t.xkr, t.valid, lam, sigma, delta, nroot, fp, zero_out);
+  }
+}
+
+template <class R>
+__global__ void __launch_bounds__(kGroupThreads, sizeof(R) == 8 ? 2 : 3)
+    group_l2binf_small_fast_kernel(R* y, const R* xk, const R* sj, const R* q, long long ngroups,
+                                   const long long* __restrict__ offs, const R* __restrict__ lambda_g, R sigma, R delta,
+                                   UDiv<R> by_sigma, const unsigned* __restrict__ uniform_flag,
+                                   unsigned char* __restrict__ done) {
+  if (uniform_flag != nullptr && *uniform_flag != 0u) return;
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * kGroupThreads + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * kGroupThreads) >> 5;
+  const long long ntasks = (ngroups + kTask - 1) / kTask;
+  for (long long task = warp; task < ntasks; task += nwarps) {
+    const long long g0 = task * kTask;
+    const TaskHead th = load_task(offs, g0, ngroups, lane);
+    if (th.le[5] == 0u) continue;  // no group of <= 256 elements in this task
+    const R lam_lane = lane < th.cnt ? lambda_g[g0 + lane] : R(0);
+    int pos = 0;
+    while (pos < th.cnt) {
+      const int k = plan_round(th.le, pos);
+      if (k < 0) {
+        pos += 1;
+        continue;
+      }
+      Tile<R, true> t;
+      t.load(th, k, pos, lane, xk, sj, q);
+      const int gi = t.group_in_task(pos, k, lane);
+      const R lam = __shfl_sync(0xffffffffu, lam_lane, gi & 31);
+      const R sl = lam * sigma;
+      R nroot = R(0);
+      double fp = 1.0;
+      bool zero_out = false, ok = false;
+      switch (k) {
+        case 0: ok = binf_tile_search<R, 1>(t, lam, sigma, delta, nroot, fp, zero_out); break;
+        case 1: ok = binf_tile_search<R, 2>(t, lam, sigma, delta, nroot, fp, zero_out); break;
+        case 2: ok = binf_tile_search<R, 4>(t, lam, sigma, delta, nroot, fp, zero_out); break;
+        case 3: ok = binf_tile_search<R, 8>(t, lam, sigma, delta, nroot, fp, zero_out); break;
+        case 4: ok = binf_tile_search<R, 16>(t, lam, sigma, delta, nroot, fp, zero_out); break;
+        default: ok = binf_tile_search<R, 32>(t, lam, sigma, delta, nroot, fp, zero_out); break;
+      }
+      // y_g = l2prox(sol - σ softthres(sol/σ - step xk, Δ step), σλ) - (xk + sj)   (:109-116) and the acceptance test
+      const R step = div_fast(nroot, sigma * (nroot - sl));  // c(n)  (:85)
+      const R dstep2 = delta * step;
+      R w[kEPL];
+      double ss = 0.0;
+#pragma unroll
+      for (int j = 0; j < kEPL; ++j) {
+        w[j] = t.sol[j] - sigma * softthres_sel(quot_uniform(t.sol[j], by_sigma) - step * t.xkr[j], dstep2);
+        ss = __fma_rn((double)w[j], (double)w[j], ss);
+      }
+      ss = sub_sum(ss, t.L);
+      const R nv = (R)sqrt_fast(ss);
+      const R res = nroot - nv;
+      const R gap = nroot - sl;
+      const R ulps = jl_max(R(2), jl_min(R(16), gap * (R)(1.0 / (double)sl)));
+      const bool accepted = ok && (zero_out || (jl_abs(res) <= ulps * Eps<R>::value * nroot * (R)fp));
+      if (t.valid && accepted) {
+        const R alpha = zero_out ? R(0) : jl_max(R(0), R(1) - div_fast(sl, nv));
+#pragma unroll
+        for (int j = 0; j < kEPL; ++j) {
+          const long long i = t.b + (long long)j * t.L + t.sub;
+          if (i < t.e) stv(y + i, (zero_out ? R(0) : alpha * w[j]) - t.xs[j]);
+        }
+        if (t.sub == 0) done[g0 + gi] = 1;
+      }
+      pos += 32 >> k;
     }
   }
 }
@@ -2007,19 +2104,10 @@ static int32_t prox_group(spx_ctx* ctx, bool binf, int64_t n, R* y, const R* xk,
                              uniform_flag, wl_count, wl_rounds);
       ctx->launches += 3;
     }
-    // the short groups (<= 256 elements) on a side stream, concurrently with the CTA-per-group class below; the warp
-    // path for what is left joins both (it reads long_flag and the done bitmap)
-    if (!ctx->pipe_streams[0]) SPX_CUDA(cudaStreamCreateWithFlags(&ctx->pipe_streams[0], cudaStreamNonBlocking));
-    for (int i = 13; i < 15; ++i)
-      if (!ctx->pipe_events[i]) SPX_CUDA(cudaEventCreateWithFlags(&ctx->pipe_events[i], cudaEventDisableTiming));
-    SPX_CUDA(cudaEventRecord(ctx->pipe_events[13], ctx->stream));
-    SPX_CUDA(cudaStreamWaitEvent(ctx->pipe_streams[0], ctx->pipe_events[13], 0));
-    group_l2binf_kernel<R, 0><<<grid0, kGroupThreads, 0, ctx->pipe_streams[0]>>>(
-        y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, (R)sigma, (R)delta, by_sigma, nullptr, long_flag,
-        uni ? uniform_flag : nullptr, nullptr);
-    SPX_CUDA(cudaEventRecord(ctx->pipe_events[14], ctx->pipe_streams[0]));
-    // groups of 257..4096 elements: one CTA per group, the group in registers; whatever it cannot accept stays
-    // unmarked in `done` for the warp path below.  Not when y aliases an input: the warp path stashes sol in y.
+    // Fast kernels first, each marking the groups it has written in `done`: groups of <= 256 elements on the planner's
+    // warp rounds, (1024, 4096] with 256 threads per group, (256, 1024] with 128.  The bracketing search (the two warp
+    // kernels) then takes whatever is left.  Not when y aliases an input (the warp path stashes sol in y, so a group a
+    // fast kernel declines must still find its inputs) or σ, Δ are outside the range of the branch-free quotient.
     unsigned char* done = nullptr;
     {
       const char *y0 = (const char*)y, *y1 = y0 + (size_t)n * sizeof(R);
@@ -2027,7 +2115,13 @@ static int32_t prox_group(spx_ctx* ctx, bool binf, int64_t n, R* y, const R* xk,
       if (sigma_ok && !(overlaps(xk) || overlaps(sj) || overlaps(q)) && std::getenv("SPX_BINF_NOBIG") == nullptr) {
         done = (unsigned char*)ctx->d_scratch + done_off;
         SPX_CUDA(cudaMemsetAsync(done, 0, (size_t)ngroups, ctx->stream));
-        // (1024, 4096]: 256 threads, 8 / 16 elements per thread; (256, 1024]: 128 threads, 4 / 8 per thread
+        if (std::getenv("SPX_BINF_NOSMALL") == nullptr) {
+          const int grids = group_grid(ctx, ngroups, (const void*)group_l2binf_small_fast_kernel<R>);
+          group_l2binf_small_fast_kernel<R><<<grids, kGroupThreads, 0, ctx->stream>>>(
+              y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, (R)sigma, (R)delta, by_sigma,
+              uni ? uniform_flag : nullptr, done);
+          ctx->launches++;
+        }
         auto launch_class = [&](auto kern, int threads, size_t stage_bytes) -> int32_t {
           int per_sm = 1;
           SPX_CUDA(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes));
@@ -2051,7 +2145,9 @@ static int32_t prox_group(spx_ctx* ctx, bool binf, int64_t n, R* y, const R* xk,
         }
       }
     }
-    SPX_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->pipe_events[14], 0));
+    group_l2binf_kernel<R, 0><<<grid0, kGroupThreads, 0, ctx->stream>>>(
+        y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, (R)sigma, (R)delta, by_sigma, nullptr, long_flag,
+        uni ? uniform_flag : nullptr, done);
     group_l2binf_kernel<R, 1><<<grid1, kGroupThreads, 0, ctx->stream>>>(
         y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, (R)sigma, (R)delta, by_sigma, counter, long_flag,
         uni ? uniform_flag : nullptr, done);
