@@ -1714,7 +1714,7 @@ template <class R, int PART>
 __global__ void __launch_bounds__(kGroupThreads)
     group_value_kernel(const R* __restrict__ xk, const R* __restrict__ sj, const R* __restrict__ y, long long ngroups,
                        const long long* __restrict__ offs, const R* __restrict__ lambda_g, bool binf, double rad,
-                       Partial* __restrict__ partials) {
+                       bool skip_classes, Partial* __restrict__ partials) {
   const int lane = threadIdx.x & 31;
   const long long warp = ((long long)blockIdx.x * kGroupThreads + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * kGroupThreads) >> 5;
@@ -1745,8 +1745,8 @@ __global__ void __launch_bounds__(kGroupThreads)
     while (pos < th.cnt) {
       const int k = plan_round(th.le, pos);
       if (k < 0) {  // long group: the whole warp
-        if (PART == 1) {
-          const long long b = __shfl_sync(0xffffffffu, th.lo, pos), e = __shfl_sync(0xffffffffu, th.hi, pos);
+        const long long b = __shfl_sync(0xffffffffu, th.lo, pos), e = __shfl_sync(0xffffffffu, th.hi, pos);
+        if (PART == 1 && !(skip_classes && is_big(e - b))) {
           double ss = 0.0;
 #pragma unroll 4
           for (long long i = b + lane; i < e; i += 32) ss += term(xk[i], sj[i], y[i]);
@@ -1778,6 +1778,81 @@ __global__ void __launch_bounds__(kGroupThreads)
     }
   }
   p = block_fold<kGroupThreads>(p);
+  if (threadIdx.x == 0) partials[blockIdx.x] = p;
+}
+
+// ψ(y) of the CTA-per-group classes (see group_l2_big_kernel): xk | sj | y of a group arrive by bulk copies, ST groups
+// in flight ahead of the one being summed
+template <class R, int T, int LO, int EA, int EB, int ST>
+__global__ void __launch_bounds__(T, 512 / T)
+    group_value_big_kernel(const R* __restrict__ xk, const R* __restrict__ sj, const R* __restrict__ y, long long ngroups,
+                           const long long* __restrict__ offs, const R* __restrict__ lambda_g, bool binf, double rad,
+                           Partial* __restrict__ partials) {
+  constexpr int PLS = bulk_plane<R>(EB * T);
+  __shared__ int list[T];
+  __shared__ int wcount[T / 32];
+  __shared__ double red[T / 32];
+  __shared__ __align__(8) uint64_t bar[ST];
+  extern __shared__ __align__(128) unsigned char val_stage_raw[];
+  R* const stage0 = reinterpret_cast<R*>(val_stage_raw);
+  const int t = threadIdx.x;
+  if (t == 0)
+    for (int s = 0; s < ST; ++s) mbar_init(&bar[s], 1);
+  __syncthreads();
+  uint32_t phases = 0;
+  Partial p;
+  p.s = 0.0;
+  p.s2 = 0.0;
+  p.bad = -1;
+  for (long long g0 = (long long)blockIdx.x * T; g0 < ngroups; g0 += (long long)gridDim.x * T) {
+    const int nbig = list_class_groups<T, LO, EB * T>(offs, g0, ngroups, list, wcount);
+    if (t == 0) {
+      fence_proxy_async();
+      for (int s = 0; s < ST && s < nbig; ++s) {
+        const long long gf = g0 + list[s];
+        stage_group_bulk<R, 3, PLS>(stage0 + s * 3 * PLS, &bar[s], xk, sj, y, offs[gf], offs[gf + 1]);
+      }
+    }
+    for (int j = 0; j < nbig; ++j) {
+      const int sidx = j % ST;
+      const long long g = g0 + list[j];
+      const long long b = offs[g], e = offs[g + 1];
+      mbar_wait(&bar[sidx], (phases >> sidx) & 1u);
+      phases ^= 1u << sidx;
+      const R* stage = stage0 + sidx * 3 * PLS;
+      const R* px = stage + bulk_skip(xk + b) + t;
+      const R* ps = stage + PLS + bulk_skip(sj + b) + t;
+      const R* py = stage + 2 * PLS + bulk_skip(y + b) + t;
+      double ss = 0.0;
+      const int ne = (e - b <= EA * T) ? EA : EB;
+#pragma unroll
+      for (int k = 0; k < EB; ++k) {
+        const long long i = b + (long long)k * T + t;
+        if (k < ne && i < e) {
+          const R xi = px[k * T], si = ps[k * T], yi = py[k * T];
+          R v;
+          if (binf) {  // w = sj + y against the ball, v = w + xk  (shiftedGroupNormL2Binf.jl:34-39)
+            const R w = si + yi;
+            if ((double)w < -rad || (double)w > rad) p.bad = 1;
+            v = w + xi;
+          } else {
+            v = (xi + si) + yi;  // ShiftedProximalOperators.jl:51-54
+          }
+          ss += (double)v * (double)v;
+        }
+      }
+      ss = block_sum<T>(ss, red);
+      if (t == 0) {
+        if (j + ST < nbig) {
+          const long long gn = g0 + list[j + ST];
+          fence_proxy_async();
+          stage_group_bulk<R, 3, PLS>(stage0 + sidx * 3 * PLS, &bar[sidx], xk, sj, y, offs[gn], offs[gn + 1]);
+        }
+        p.s += (double)(lambda_g[g] * (R)sqrt(ss));  // λ_g ‖v_g‖  groupNormL2.jl:36
+      }
+    }
+  }
+  p = block_fold<T>(p);
   if (threadIdx.x == 0) partials[blockIdx.x] = p;
 }
 
@@ -1934,15 +2009,28 @@ int32_t value_group_binf(spx_ctx* ctx, int64_t n, const R* xk, const R* sj, cons
                                     : (double)(R)(double)(lam * (R)std::sqrt(ctx->h_result[0].s2));
     return SPX_OK;
   }
+  const double rad = 1.1 * (double)(R)delta;
   const int grid0 = group_grid(ctx, ngroups, (const void*)group_value_kernel<R, 0>);
   const int grid1 = group_grid(ctx, ngroups, (const void*)group_value_kernel<R, 1>);
-  group_value_kernel<R, 0><<<grid0, kGroupThreads, 0, ctx->stream>>>(
-      xk, sj, y, ngroups, (const long long*)offs, lambda_g, binf, 1.1 * (double)(R)delta, ctx->d_partials);
-  group_value_kernel<R, 1><<<grid1, kGroupThreads, 0, ctx->stream>>>(
-      xk, sj, y, ngroups, (const long long*)offs, lambda_g, binf, 1.1 * (double)(R)delta, ctx->d_partials + grid0);
-  ctx->launches += 2;
+  // the classes (256, 1024] and (1024, 4096]: CTA per group, operands by bulk copies (as in launch_group_l2)
+  constexpr int kMidT = 128;
+  auto big_val = group_value_big_kernel<R, kGroupThreads, (int)kBigMin, kBigE / 2, kBigE, 1>;
+  auto mid_val = group_value_big_kernel<R, kMidT, (int)kMidMin, 4, 8, SPX_L2_MID_STAGES>;
+  const size_t big_bytes = 3 * (size_t)bulk_plane<R>((int)kBigMax) * sizeof(R);
+  const size_t mid_bytes = SPX_L2_MID_STAGES * 3 * (size_t)bulk_plane<R>((int)kBigMin) * sizeof(R);
+  const int grid2 = big_grid(ctx, ngroups, (const void*)big_val, kGroupThreads, big_bytes);
+  const int grid3 = big_grid(ctx, ngroups, (const void*)mid_val, kMidT, mid_bytes);
+  group_value_kernel<R, 0><<<grid0, kGroupThreads, 0, ctx->stream>>>(xk, sj, y, ngroups, (const long long*)offs, lambda_g,
+                                                                    binf, rad, true, ctx->d_partials);
+  group_value_kernel<R, 1><<<grid1, kGroupThreads, 0, ctx->stream>>>(xk, sj, y, ngroups, (const long long*)offs, lambda_g,
+                                                                    binf, rad, true, ctx->d_partials + grid0);
+  big_val<<<grid2, kGroupThreads, big_bytes, ctx->stream>>>(xk, sj, y, ngroups, (const long long*)offs, lambda_g, binf, rad,
+                                                           ctx->d_partials + grid0 + grid1);
+  mid_val<<<grid3, kMidT, mid_bytes, ctx->stream>>>(xk, sj, y, ngroups, (const long long*)offs, lambda_g, binf, rad,
+                                                   ctx->d_partials + grid0 + grid1 + grid2);
+  ctx->launches += 4;
   SPX_CUDA(cudaGetLastError());
-  const int grid = grid0 + grid1;
+  const int grid = grid0 + grid1 + grid2 + grid3;
   int32_t st = finalize_partials(ctx, grid, 1, false);
   if (st != SPX_OK) return st;
   // the reference accumulates sum_c in R; one rounding to R here
