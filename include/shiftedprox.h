@@ -173,7 +173,10 @@ int32_t spx_selftest_topr_pick(spx_ctx* ctx, const uint64_t* hist_host, int64_t 
                                int64_t* above_out);
 /* GroupNormL2's constructor checks (groupNormL2.jl:20-23) for the device layout: offs (device int64, ngroups + 1 entries)
  * must start at 0, never decrease and end at n; SPX_E_INVALID otherwise.  Call once when ψ is built: the prox!/ψ(y)
- * entry points trust the offsets.  Index sets that are not contiguous ranges in order (the reference accepts any
+ * entry points trust the offsets.  The same pass records, per context, which group-size classes the layout holds
+ * (keyed on offs / ngroups / n), so that later calls launch only the kernels that have work; a layout never
+ * validated, or changed afterwards, is still computed correctly -- every class is launched, or the warp kernels take
+ * over the groups of a class that was skipped.  Index sets that are not contiguous ranges in order (the reference accepts any
  * `idx`) cannot be expressed as CSR offsets: the host layer rejects them at construction. */
 int32_t spx_group_validate_offsets(spx_ctx* ctx, int64_t n, int64_t ngroups, const int64_t* offs);
 /* order-independent 64-bit checksum of a buffer's bits (Σ mix(word_i, i) mod 2^64),

@@ -81,6 +81,15 @@ struct spx_ctx {
   int peer_nranks = 0;
   unsigned long long peer_seq = 0;  // all-reduces done so far (the same number on every rank)
   int* d_peer_fail = nullptr;
+  // size classes present in the CSR layouts validated on this context (spx_group_validate_offsets): lets the group
+  // entry points skip the CTA-per-group launches of an absent class.  A hint only: the warp kernels are told which
+  // classes were skipped and take their groups themselves, so a stale entry costs time, never a result.
+  struct GroupCensus {
+    const void* offs = nullptr;
+    long long ngroups = -1, n = -1;
+    unsigned classes = 0;  // bit 0: some group of 257..1024 elements, bit 1: of 1025..4096
+  } census[8];
+  int census_next = 0;
 };
 
 namespace spx {

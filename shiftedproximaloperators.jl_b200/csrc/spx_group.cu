@@ -27,7 +27,11 @@ constexpr long long kBigMin = 1024, kBigMax = 4096;
 constexpr int kBigE = (int)(kBigMax / kGroupThreads);
 // CTA-per-group classes of ShiftedGroupNormL2: (kMidMin, kBigMin] with 128 threads, (kBigMin, kBigMax] with 256
 constexpr long long kMidMin = 256;
-__device__ __forceinline__ bool is_big(long long m) { return m > kMidMin && m <= kBigMax; }
+// `classes`: which of them have their kernel launched in this call (bit 0: the 128-thread class, bit 1: the 256-thread
+// one); the warp kernels take every long group that is in none of the launched classes
+__device__ __forceinline__ bool in_launched_class(long long m, unsigned classes) {
+  return ((classes & 1u) != 0u && m > kMidMin && m <= kBigMin) || ((classes & 2u) != 0u && m > kBigMin && m <= kBigMax);
+}
 
 #ifdef SPX_GROUP_STATS
 __device__ unsigned long long g_stat_evals = 0, g_stat_groups = 0, g_stat_big[3] = {0, 0, 0};  // big: evals, groups, rejected
@@ -253,7 +257,7 @@ __device__ __forceinline__ double l2_long_group(R* y, const R* xk, const R* sj, 
 template <class R, bool PSI, int PART, bool SHIFTED>
 __global__ void __launch_bounds__(kGroupThreads)
     group_l2_kernel(R* y, const R* xk, const R* sj, const R* q, long long ngroups,
-                    const long long* __restrict__ offs, const R* __restrict__ lambda_g, R sigma,
+                    const long long* __restrict__ offs, const R* __restrict__ lambda_g, R sigma, unsigned classes,
                     Partial* __restrict__ partials) {
   const int lane = threadIdx.x & 31;
   const long long warp = ((long long)blockIdx.x * kGroupThreads + threadIdx.x) >> 5;
@@ -272,7 +276,7 @@ __global__ void __launch_bounds__(kGroupThreads)
       if (k < 0) {  // long group: the whole warp (a whole CTA of group_l2_big_kernel for 1024 < m <= 4096)
         if (PART == 1) {
           const long long b = __shfl_sync(0xffffffffu, th.lo, pos), e = __shfl_sync(0xffffffffu, th.hi, pos);
-          if (!is_big(e - b)) {
+          if (!in_launched_class(e - b, classes)) {
             const R lam = __shfl_sync(0xffffffffu, lam_lane, pos);
             const double vv = l2_long_group<R, PSI, SHIFTED>(y, xk, sj, q, b, e, lam, sigma, lane);
             if (PSI && lane == 0) psi += (double)(lam * (R)sqrt(vv));  // λ_g ‖v_g‖  groupNormL2.jl:36
@@ -1714,7 +1718,7 @@ template <class R, int PART>
 __global__ void __launch_bounds__(kGroupThreads)
     group_value_kernel(const R* __restrict__ xk, const R* __restrict__ sj, const R* __restrict__ y, long long ngroups,
                        const long long* __restrict__ offs, const R* __restrict__ lambda_g, bool binf, double rad,
-                       bool skip_classes, Partial* __restrict__ partials) {
+                       unsigned classes, Partial* __restrict__ partials) {
   const int lane = threadIdx.x & 31;
   const long long warp = ((long long)blockIdx.x * kGroupThreads + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * kGroupThreads) >> 5;
@@ -1746,7 +1750,7 @@ __global__ void __launch_bounds__(kGroupThreads)
       const int k = plan_round(th.le, pos);
       if (k < 0) {  // long group: the whole warp
         const long long b = __shfl_sync(0xffffffffu, th.lo, pos), e = __shfl_sync(0xffffffffu, th.hi, pos);
-        if (PART == 1 && !(skip_classes && is_big(e - b))) {
+        if (PART == 1 && !in_launched_class(e - b, classes)) {
           double ss = 0.0;
 #pragma unroll 4
           for (long long i = b + lane; i < e; i += 32) ss += term(xk[i], sj[i], y[i]);
@@ -1966,6 +1970,13 @@ static int group_grid(spx_ctx* ctx, int64_t ngroups, const void* kernel) {
   return (int)(want < cap ? want : cap);
 }
 
+// classes to launch for this layout: what spx_group_validate_offsets recorded, both when the layout is unknown
+static unsigned census_classes(const spx_ctx* ctx, const void* offs, int64_t ngroups, int64_t n) {
+  for (const auto& c : ctx->census)
+    if (c.offs == offs && c.ngroups == (long long)ngroups && c.n == (long long)n) return c.classes;
+  return 3u;
+}
+
 #ifndef SPX_L2_MID_STAGES
 #define SPX_L2_MID_STAGES 2
 #endif
@@ -2018,17 +2029,20 @@ int32_t value_group_binf(spx_ctx* ctx, int64_t n, const R* xk, const R* sj, cons
   auto mid_val = group_value_big_kernel<R, kMidT, (int)kMidMin, 4, 8, SPX_L2_MID_STAGES>;
   const size_t big_bytes = 3 * (size_t)bulk_plane<R>((int)kBigMax) * sizeof(R);
   const size_t mid_bytes = SPX_L2_MID_STAGES * 3 * (size_t)bulk_plane<R>((int)kBigMin) * sizeof(R);
-  const int grid2 = big_grid(ctx, ngroups, (const void*)big_val, kGroupThreads, big_bytes);
-  const int grid3 = big_grid(ctx, ngroups, (const void*)mid_val, kMidT, mid_bytes);
+  const unsigned classes = census_classes(ctx, offs, ngroups, n);
+  const int grid2 = (classes & 2u) ? big_grid(ctx, ngroups, (const void*)big_val, kGroupThreads, big_bytes) : 0;
+  const int grid3 = (classes & 1u) ? big_grid(ctx, ngroups, (const void*)mid_val, kMidT, mid_bytes) : 0;
   group_value_kernel<R, 0><<<grid0, kGroupThreads, 0, ctx->stream>>>(xk, sj, y, ngroups, (const long long*)offs, lambda_g,
-                                                                    binf, rad, true, ctx->d_partials);
+                                                                    binf, rad, classes, ctx->d_partials);
   group_value_kernel<R, 1><<<grid1, kGroupThreads, 0, ctx->stream>>>(xk, sj, y, ngroups, (const long long*)offs, lambda_g,
-                                                                    binf, rad, true, ctx->d_partials + grid0);
-  big_val<<<grid2, kGroupThreads, big_bytes, ctx->stream>>>(xk, sj, y, ngroups, (const long long*)offs, lambda_g, binf, rad,
-                                                           ctx->d_partials + grid0 + grid1);
-  mid_val<<<grid3, kMidT, mid_bytes, ctx->stream>>>(xk, sj, y, ngroups, (const long long*)offs, lambda_g, binf, rad,
-                                                   ctx->d_partials + grid0 + grid1 + grid2);
-  ctx->launches += 4;
+                                                                    binf, rad, classes, ctx->d_partials + grid0);
+  if (grid2 > 0)
+    big_val<<<grid2, kGroupThreads, big_bytes, ctx->stream>>>(xk, sj, y, ngroups, (const long long*)offs, lambda_g, binf,
+                                                             rad, ctx->d_partials + grid0 + grid1);
+  if (grid3 > 0)
+    mid_val<<<grid3, kMidT, mid_bytes, ctx->stream>>>(xk, sj, y, ngroups, (const long long*)offs, lambda_g, binf, rad,
+                                                     ctx->d_partials + grid0 + grid1 + grid2);
+  ctx->launches += 2 + (grid2 > 0) + (grid3 > 0);
   SPX_CUDA(cudaGetLastError());
   const int grid = grid0 + grid1 + grid2 + grid3;
   int32_t st = finalize_partials(ctx, grid, 1, false);
@@ -2045,7 +2059,7 @@ template int32_t value_group_binf<float>(spx_ctx*, int64_t, const float*, const 
 template <class R, bool SHIFTED>
 static int32_t launch_group_l2(spx_ctx* ctx, int64_t n, R* y, const R* xk, const R* sj, const R* q, int64_t ngroups,
                                const int64_t* offs, const R* lambda_g, R sigma, double* psi_out) {
-  (void)n;
+  const unsigned classes = census_classes(ctx, offs, ngroups, n);
   // The CTA-per-group classes stage q | xk | sj in shared memory with bulk copies: (1024, 4096] with 256 threads and one
   // buffer (the copy of the next group runs under the stores of the current one; two CTAs per SM overlap the rest),
   // (256, 1024] with 128 threads and a ring of two buffers (four CTAs per SM; a ring of four with two CTAs measured 3 % slower).
@@ -2059,17 +2073,19 @@ static int32_t launch_group_l2(spx_ctx* ctx, int64_t n, R* y, const R* xk, const
   if (psi_out) {
     const int grid0 = group_grid(ctx, ngroups, (const void*)group_l2_kernel<R, true, 0, SHIFTED>);
     const int grid1 = group_grid(ctx, ngroups, (const void*)group_l2_kernel<R, true, 1, SHIFTED>);
-    const int grid2 = big_grid(ctx, ngroups, (const void*)big_psi, kGroupThreads, big_bytes);
-    const int grid3 = big_grid(ctx, ngroups, (const void*)mid_psi, kMidT, mid_bytes);
+    const int grid2 = (classes & 2u) ? big_grid(ctx, ngroups, (const void*)big_psi, kGroupThreads, big_bytes) : 0;
+    const int grid3 = (classes & 1u) ? big_grid(ctx, ngroups, (const void*)mid_psi, kMidT, mid_bytes) : 0;
     group_l2_kernel<R, true, 0, SHIFTED><<<grid0, kGroupThreads, 0, ctx->stream>>>(
-        y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, sigma, ctx->d_partials);
+        y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, sigma, classes, ctx->d_partials);
     group_l2_kernel<R, true, 1, SHIFTED><<<grid1, kGroupThreads, 0, ctx->stream>>>(
-        y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, sigma, ctx->d_partials + grid0);
-    big_psi<<<grid2, kGroupThreads, big_bytes, ctx->stream>>>(y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, sigma,
-                                                             ctx->d_partials + grid0 + grid1);
-    mid_psi<<<grid3, kMidT, mid_bytes, ctx->stream>>>(y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, sigma,
-                                                     ctx->d_partials + grid0 + grid1 + grid2);
-    ctx->launches += 4;
+        y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, sigma, classes, ctx->d_partials + grid0);
+    if (grid2 > 0)
+      big_psi<<<grid2, kGroupThreads, big_bytes, ctx->stream>>>(y, xk, sj, q, ngroups, (const long long*)offs, lambda_g,
+                                                               sigma, ctx->d_partials + grid0 + grid1);
+    if (grid3 > 0)
+      mid_psi<<<grid3, kMidT, mid_bytes, ctx->stream>>>(y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, sigma,
+                                                       ctx->d_partials + grid0 + grid1 + grid2);
+    ctx->launches += 2 + (grid2 > 0) + (grid3 > 0);
     SPX_CUDA(cudaGetLastError());
     int32_t st = finalize_partials(ctx, grid0 + grid1 + grid2 + grid3, 1, false);
     if (st != SPX_OK) return st;
@@ -2088,25 +2104,40 @@ static int32_t launch_group_l2(spx_ctx* ctx, int64_t n, R* y, const R* xk, const
   const int grid0 = (int)std::max<long long>(1, std::min<long long>((ntasks + warps_per_cta - 1) / warps_per_cta, 1 << 20));
   const int grid2s = (int)std::max<long long>(1, std::min<long long>((ngroups + kGroupThreads - 1) / kGroupThreads, 1 << 20));
   const int grid3s = (int)std::max<long long>(1, std::min<long long>((ngroups + kMidT - 1) / kMidT, 1 << 20));
-  SPX_CUDA(cudaFuncSetAttribute((const void*)big_run, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big_bytes));
-  SPX_CUDA(cudaFuncSetAttribute((const void*)mid_run, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mid_bytes));
+  // A class the layout is known not to hold (census of spx_group_validate_offsets) is not launched: its CTAs would
+  // only scan the offsets, but their shared-memory carve-out keeps the warp kernel off the SMs they pass through
+  // (uniform groups of 64: 2.21 ms with the two empty launches, 1.44 ms without).
   SPX_CUDA(cudaEventRecord(ctx->pipe_events[13], ctx->stream));
-  SPX_CUDA(cudaStreamWaitEvent(ctx->pipe_streams[0], ctx->pipe_events[13], 0));
+  if (classes & 2u) {
+    SPX_CUDA(cudaFuncSetAttribute((const void*)big_run, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big_bytes));
+    big_run<<<grid2s, kGroupThreads, big_bytes, ctx->stream>>>(y, xk, sj, q, ngroups, (const long long*)offs, lambda_g,
+                                                              sigma, ctx->d_partials);
+    ctx->launches++;
+  }
+  if (classes & 1u) {
+    SPX_CUDA(cudaFuncSetAttribute((const void*)mid_run, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mid_bytes));
+    SPX_CUDA(cudaStreamWaitEvent(ctx->pipe_streams[0], ctx->pipe_events[13], 0));
+    mid_run<<<grid3s, kMidT, mid_bytes, ctx->pipe_streams[0]>>>(y, xk, sj, q, ngroups, (const long long*)offs, lambda_g,
+                                                               sigma, ctx->d_partials);
+    SPX_CUDA(cudaEventRecord(ctx->pipe_events[14], ctx->pipe_streams[0]));
+    ctx->launches++;
+  }
+  // groups above 4096 elements (and those of a class not launched): the warp path, whose CTAs exit at once when there
+  // are none -- on the side stream, under the short-group kernel
   SPX_CUDA(cudaStreamWaitEvent(ctx->pipe_streams[1], ctx->pipe_events[13], 0));
-  big_run<<<grid2s, kGroupThreads, big_bytes, ctx->stream>>>(y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, sigma,
-                                                            ctx->d_partials);
-  mid_run<<<grid3s, kMidT, mid_bytes, ctx->pipe_streams[0]>>>(y, xk, sj, q, ngroups, (const long long*)offs, lambda_g,
-                                                             sigma, ctx->d_partials);
-  group_l2_kernel<R, false, 0, SHIFTED><<<grid0, kGroupThreads, 0, ctx->pipe_streams[1]>>>(
-      y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, sigma, ctx->d_partials);
-  // groups above 4096 elements: the warp path (its CTAs exit at once when there are none)
   group_l2_kernel<R, false, 1, SHIFTED><<<grid0, kGroupThreads, 0, ctx->pipe_streams[1]>>>(
-      y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, sigma, ctx->d_partials);
-  ctx->launches += 4;
+      y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, sigma, classes, ctx->d_partials);
+  if (classes == 0u) {
+    group_l2_kernel<R, false, 0, SHIFTED><<<grid0, kGroupThreads, 0, ctx->stream>>>(
+        y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, sigma, classes, ctx->d_partials);
+  } else {
+    group_l2_kernel<R, false, 0, SHIFTED><<<grid0, kGroupThreads, 0, ctx->pipe_streams[1]>>>(
+        y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, sigma, classes, ctx->d_partials);
+  }
+  ctx->launches += 2;
   SPX_CUDA(cudaGetLastError());
-  SPX_CUDA(cudaEventRecord(ctx->pipe_events[14], ctx->pipe_streams[0]));
   SPX_CUDA(cudaEventRecord(ctx->pipe_events[15], ctx->pipe_streams[1]));
-  SPX_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->pipe_events[14], 0));
+  if (classes & 1u) SPX_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->pipe_events[14], 0));
   SPX_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->pipe_events[15], 0));
   return SPX_OK;
 }
@@ -2194,12 +2225,17 @@ static int32_t prox_group(spx_ctx* ctx, bool binf, int64_t n, R* y, const R* xk,
     }
     // Fast kernels first, each marking the groups it has written in `done`: groups of <= 256 elements on the planner's
     // warp rounds, (1024, 4096] with 256 threads per group, (256, 1024] with 128.  The bracketing search (the two warp
-    // kernels) then takes whatever is left.  Not when y aliases an input (the warp path stashes sol in y, so a group a
-    // fast kernel declines must still find its inputs) or σ, Δ are outside the range of the branch-free quotient.
+    // kernels) then takes whatever is left.  prox!(y, ψ, y, σ) (y IS an input vector) takes the same kernels as the
+    // out-of-place call, so both give the same bits: every kernel reads a group's inputs before it writes that group's
+    // y, a group is written by exactly one kernel, and a group a fast kernel declines is left untouched.  Not when y
+    // overlaps an input partially (a group's y would land on another group's inputs) or σ, Δ are outside the range of
+    // the branch-free quotient.
     unsigned char* done = nullptr;
     {
       const char *y0 = (const char*)y, *y1 = y0 + (size_t)n * sizeof(R);
-      auto overlaps = [&](const R* p) { return (const char*)p < y1 && (const char*)p + (size_t)n * sizeof(R) > y0; };
+      auto overlaps = [&](const R* p) {
+        return p != y && (const char*)p < y1 && (const char*)p + (size_t)n * sizeof(R) > y0;
+      };
       if (sigma_ok && !(overlaps(xk) || overlaps(sj) || overlaps(q)) && std::getenv("SPX_BINF_NOBIG") == nullptr) {
         done = (unsigned char*)ctx->d_scratch + done_off;
         SPX_CUDA(cudaMemsetAsync(done, 0, (size_t)ngroups, ctx->stream));
@@ -2223,10 +2259,16 @@ static int32_t prox_group(spx_ctx* ctx, bool binf, int64_t n, R* y, const R* xk,
           ctx->launches++;
           return SPX_OK;
         };
-        int32_t stc = launch_class(group_l2binf_big_kernel<R, kBinfBigThreads, 1024, 8, 16>, kBinfBigThreads,
-                                   3 * (size_t)16 * kBinfBigThreads * sizeof(R));
-        if (stc != SPX_OK) return stc;
-        if (std::getenv("SPX_BINF_NOMID") == nullptr) {
+        // a class the layout is known not to hold is not launched (whatever is not marked done goes to the bracketing
+        // search anyway, so the census is only a hint here as well)
+        const unsigned classes = census_classes(ctx, offs, ngroups, n);
+        int32_t stc = SPX_OK;
+        if (classes & 2u) {
+          stc = launch_class(group_l2binf_big_kernel<R, kBinfBigThreads, 1024, 8, 16>, kBinfBigThreads,
+                             3 * (size_t)16 * kBinfBigThreads * sizeof(R));
+          if (stc != SPX_OK) return stc;
+        }
+        if ((classes & 1u) && std::getenv("SPX_BINF_NOMID") == nullptr) {
           stc = launch_class(group_l2binf_big_kernel<R, kBinfMidThreads, 256, 4, 8>, kBinfMidThreads,
                              3 * (size_t)8 * kBinfMidThreads * sizeof(R));
           if (stc != SPX_OK) return stc;
@@ -2277,11 +2319,18 @@ extern "C" int32_t spx_debug_group_stats(unsigned long long* out2, int reset) {
 // 0, never decrease and end at n -- anything else would make the group kernels read and write out of bounds.
 __global__ void __launch_bounds__(256) group_validate_kernel(const long long* __restrict__ offs, long long ngroups,
                                                              long long n, unsigned* bad) {
-  bool b = false;
-  for (long long g = (long long)blockIdx.x * 256 + threadIdx.x; g < ngroups; g += (long long)gridDim.x * 256)
-    b = b || (offs[g] > offs[g + 1]) || (offs[g] < 0);
+  bool b = false, mid = false, big = false;
+  for (long long g = (long long)blockIdx.x * 256 + threadIdx.x; g < ngroups; g += (long long)gridDim.x * 256) {
+    const long long lo = offs[g], m = offs[g + 1] - lo;
+    b = b || (m < 0) || (lo < 0);
+    mid = mid || (m > kMidMin && m <= kBigMin);
+    big = big || (m > kBigMin && m <= kBigMax);
+  }
   if (blockIdx.x == 0 && threadIdx.x == 0) b = b || (offs[0] != 0) || (offs[ngroups] != n);
-  if (__syncthreads_or(b) && threadIdx.x == 0) *bad = 1u;
+  if (__syncthreads_or(b) && threadIdx.x == 0) bad[0] = 1u;
+  // the size classes present (bad[1] bit 0: 257..1024 elements, bit 1: 1025..4096), for the launch census
+  const int has_mid = __syncthreads_or(mid), has_big = __syncthreads_or(big);
+  if (threadIdx.x == 0 && (has_mid || has_big)) atomicOr(&bad[1], (has_mid ? 1u : 0u) | (has_big ? 2u : 0u));
 }
 extern "C" int32_t spx_group_validate_offsets(spx_ctx* ctx, int64_t n, int64_t ngroups, const int64_t* offs) {
   SPX_REQUIRE(ctx != nullptr, "null context");
@@ -2291,17 +2340,26 @@ extern "C" int32_t spx_group_validate_offsets(spx_ctx* ctx, int64_t n, int64_t n
   int32_t st = ensure_scratch(ctx, 4096);
   if (st != SPX_OK) return st;
   unsigned* flag = (unsigned*)ctx->d_scratch;
-  SPX_CUDA(cudaMemsetAsync(flag, 0, sizeof(unsigned), ctx->stream));
+  SPX_CUDA(cudaMemsetAsync(flag, 0, 2 * sizeof(unsigned), ctx->stream));
   const int grid = (int)std::min<int64_t>((ngroups + 256) / 256, (int64_t)ctx->sm_count * 8);
   group_validate_kernel<<<grid, 256, 0, ctx->stream>>>((const long long*)offs, ngroups, n, flag);
   ctx->launches++;
-  unsigned h = 0;
-  SPX_CUDA(cudaMemcpyAsync(&h, flag, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+  unsigned h[2] = {0, 0};
+  SPX_CUDA(cudaMemcpyAsync(h, flag, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
   SPX_CUDA(cudaStreamSynchronize(ctx->stream));
-  if (h != 0) {
+  // forget whatever was known about this address, then record the layout if it is a valid one
+  for (auto& c : ctx->census)
+    if (c.offs == (const void*)offs) c = spx_ctx::GroupCensus{};
+  if (h[0] != 0) {
     set_error("group offsets must start at 0, be non-decreasing and end at n = %lld", (long long)n);
     return SPX_E_INVALID;
   }
+  auto& slot = ctx->census[ctx->census_next];
+  ctx->census_next = (ctx->census_next + 1) % (int)(sizeof(ctx->census) / sizeof(ctx->census[0]));
+  slot.offs = (const void*)offs;
+  slot.ngroups = (long long)ngroups;
+  slot.n = (long long)n;
+  slot.classes = h[1] & 3u;
   return SPX_OK;
 }
 

@@ -562,12 +562,13 @@ class _GroupBase(ShiftedProximableFunction):
         self.ngroups = self._offs.numel() - 1
         if self._lam_g.numel() != self.ngroups:
             raise ValueError("number of weights and groups should be the same")
-        if h.offsets is not None:  # caller-supplied device offsets: checked once here, trusted by the kernels afterwards
-            try:
-                L.call("spx_group_validate_offsets", context(dev), C.c_int64(xk.numel()), C.c_int64(self.ngroups),
-                       _p(self._offs))
-            except SpxError as e:
-                raise ValueError(str(e)) from None
+        # the device layout is checked once here and trusted by the kernels afterwards; the same pass records which
+        # group-size classes the layout holds, so the entry points launch only the kernels that have work
+        try:
+            L.call("spx_group_validate_offsets", context(dev), C.c_int64(xk.numel()), C.c_int64(self.ngroups),
+                   _p(self._offs))
+        except SpxError as e:
+            raise ValueError(str(e)) from None
         return h
 
     @property

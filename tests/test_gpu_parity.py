@@ -449,6 +449,61 @@ def test_group_l2_prox_and_value(dt, layout):
     assert psi(y) == pytest.approx(val, rel=rtol)
 
 
+@pytest.mark.parametrize("dt", DT)
+def test_group_launch_census_is_only_a_hint(dt):
+    """spx_group_validate_offsets records which group-size classes a layout holds and the entry points skip the
+    CTA-per-group launches of an absent class.  (1) A layout of short groups only (no class launched) and one of short
+    + 257..1024 groups only (one class) agree with the oracle.  (2) The census is a hint: when the offsets are
+    rewritten in place after validation (same address, ngroups and n, now with groups of every class) prox! and ψ(y)
+    of both group types still agree with the oracle."""
+    rng = np.random.default_rng(11)
+    G = 400
+    short = rng.integers(1, 200, G)
+    n = int(short.sum())
+    mixed = np.full(G, 1, np.int64)
+    mixed[rng.choice(G, 10, replace=False)] = [2000, 1500, 1100, 3000, 1025, 500, 700, 300, 1024, 257]
+    mixed[mixed == 1] += np.diff(np.concatenate([[0], np.sort(rng.choice(n - mixed.sum() + 1, G - 11)), [n - mixed.sum()]]))
+    assert int(mixed.sum()) == n and mixed.max() <= 4096
+    midonly = short.copy()
+    midonly[:3] = [600, 900, 300]
+    layouts = {"short": np.concatenate([[0], np.cumsum(short)]), "mid": np.concatenate([[0], np.cumsum(midonly)])}
+    lam_g = (dt(0.5) + orc.uniform(G, 12, dt)).astype(dt)
+    sigma, delta = 0.3, 0.5
+    rtol = 1e-13 if dt == np.float64 else 2e-6
+
+    def check(psi2, psib, offs, xk, sj, q):
+        m = int(offs[-1])
+        tol = 8 * eps(dt) * (np.abs(xk) + np.abs(sj) + np.abs(q) + 1)
+        y = torch.empty(m, dtype=T(q).dtype, device=DEV)
+        for want in (False, True):
+            r = sp.prox_(y, psi2, T(q), sigma, want_value=want)
+            got = N(y)
+            ref = orc.prox_groupl2(xk, sj, q, offs, lam_g, sigma)
+            assert np.all(np.abs(got.astype(np.float64) - ref.astype(np.float64)) <= tol)
+            if want:
+                assert r[1] == pytest.approx(orc.value_groupl2(xk, sj, got, offs, lam_g), rel=rtol)
+        assert psi2(y) == pytest.approx(orc.value_groupl2(xk, sj, N(y), offs, lam_g), rel=rtol)
+        sp.prox_(y, psib, T(q), sigma)
+        refb = orc.prox_groupl2binf(xk, sj, q, offs, lam_g, sigma, delta)
+        scale = np.abs(xk) + np.abs(sj) + np.abs(q) + 1
+        assert np.all(np.abs(N(y).astype(np.float64) - refb.astype(np.float64)) <= (1e-9 if dt == np.float64 else 2e-4) * scale)
+        assert psib(y) == pytest.approx(orc.value_binf("groupl2", xk, sj, N(y), delta, offs=offs, lam_g=lam_g), rel=rtol)
+
+    for name, offs in layouts.items():
+        m = int(offs[-1])
+        xk, sj, q = inputs(m, dt)
+        t_offs = T(offs)
+        h = sp.GroupNormL2(T(lam_g), None, offsets=t_offs)
+        psi2 = sp.shifted(sp.shifted(h, T(xk)), T(sj))
+        psib = sp.shifted(sp.shifted(h, T(xk), delta, sp.NormLinf(1.0)), T(sj))
+        check(psi2, psib, offs, xk, sj, q)
+        if name == "short":  # rewrite the validated layout in place: the recorded census (no class) is now wrong
+            new = np.concatenate([[0], np.cumsum(mixed)])
+            for psi in (psi2, psib):
+                psi._offs.copy_(T(new))
+            check(psi2, psib, new, xk, sj, q)
+
+
 def test_group_l2_from_norml2_differential():
     # runtests.jl:244-251: ShiftedGroupNormL2 from NormL2 == NormL2 prox of (q + x) minus x
     rng = np.random.default_rng(5)

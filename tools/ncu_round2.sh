@@ -16,9 +16,13 @@ tools/ncu_one.sh "uniform_kernel<double, .int.8, .bool.1>" "prox_groupl2binf_g64
 python tools/ncu_summary.py gpurun_out/r02_group_l2binf_uniform_g64_raw.csv > gpurun_out/r02_group_l2binf_uniform_g64_n2p26.ncu_full_summary.txt
 tools/ncu_one.sh "topr_stream_kernel<double, .bool.1" "prox_indballl0binf_batch" r02_topr_stream_batch --log2n 27
 python tools/ncu_summary.py gpurun_out/r02_topr_stream_batch_raw.csv > gpurun_out/r02_topr_stream_batch_n2p27.ncu_full_summary.txt
-tools/ncu_one.sh "group_l2binf_big_kernel<double>" "prox_groupl2binf_ragged" r02_group_l2binf_big_ragged --log2n 26
+tools/ncu_one.sh "group_l2binf_big_kernel<double, .int.256" "prox_groupl2binf_ragged" r02_group_l2binf_big_ragged --log2n 26
 python tools/ncu_summary.py gpurun_out/r02_group_l2binf_big_ragged_raw.csv > gpurun_out/r02_group_l2binf_big_ragged_n2p26.ncu_full_summary.txt
+tools/ncu_one.sh "group_l2_big_kernel<double, .bool.0, .bool.1, .int.256" "^prox_groupl2_ragged" r02_group_l2_big_ragged --log2n 26
+python tools/ncu_summary.py gpurun_out/r02_group_l2_big_ragged_raw.csv > gpurun_out/r02_group_l2_big_ragged_n2p26.ncu_full_summary.txt
 # keep the call's output under gpurun's 64 MiB limit: the reports and per-instruction pages stay on the box
 rm -f gpurun_out/*.ncu-rep gpurun_out/*_src.csv
 python tools/bench_ops.py --json gpurun_out/r02_ops_f64_n2p28.json > gpurun_out/r02_ops_f64_n2p28.txt 2>&1
 python tools/bench_ops.py --dtype f32 --log2n 29 --json gpurun_out/r02_ops_f32_n2p29.json > gpurun_out/r02_ops_f32_n2p29.txt 2>&1
+tools/launch_times.sh "^prox_groupl2_ragged" > gpurun_out/r02_ragged_launch_times.txt 2>&1
+tools/launch_times.sh "^prox_groupl2binf_ragged" >> gpurun_out/r02_ragged_launch_times.txt 2>&1
