@@ -1140,6 +1140,11 @@ template <> struct LoCopy<double> {
   }
 };
 
+// The Float32 Newton search stops once a step is below this fraction of n: Newton converges quadratically, so the
+// iterate that step leads to is already good to ~1e-6 n (Float32 noise level), and phase B cubes whatever is left
+// (measured on the bench layouts: root within 3 ulps of the Float64 bisection either way, one evaluation fewer than
+// with 1e-5).  A root phase B cannot repair fails the acceptance test and goes to the bracketing search.
+constexpr float kBinfSearchTol = 2e-3f;
 // Phases A and B.  Returns false when the round has to go through the bracketing search.  On success: zero_out
 // (`fl*fm > 0`) and the root estimate n (R); fp_out = froot'(n).
 template <class R, int L>
@@ -1216,7 +1221,7 @@ __device__ __forceinline__ bool binf_fast_search(const float (&so)[kEPL], const 
     const float den = fmaf(gap, dfx - fx * rx, fx);
     const float stp = gap * fx * rcp_f(den);
     float xn = x - stp;
-    const bool conv = (fabsf(stp) <= 1e-5f * x) || (fx == 0.f);
+    const bool conv = (fabsf(stp) <= kBinfSearchTol * x) || (fx == 0.f);
     a_ = (fx < 0.f) ? x : a_;
     b_ = (fx < 0.f) ? b_ : x;
     if (!(xn >= a_ && xn <= b_)) xn = 0.5f * (a_ + b_);  // also catches NaN
@@ -1443,14 +1448,16 @@ __global__ void __launch_bounds__(kGroupThreads, sizeof(R) == 8 ? 2 : 3)
 // ---- one CTA per group of 1025..4096 elements (ShiftedGroupNormL2Binf) ----------------------------------------------
 // The warp path above keeps a long group in the output vector and re-reads it from L2 for every evaluation of froot:
 // with groups of thousands of elements nearly all of a ragged vector goes through one warp per group.  Here the group
-// sits in the registers of a 256-thread CTA (8 or 16 elements per thread: sol and xk), every evaluation is a pass over
-// registers plus one block reduction (a single __syncthreads: the reduction slots alternate), and the search is the
-// one of the uniform path in R arithmetic: froot(lmin) skipped when its sign is certain, Newton on
-// h(n) = (n - σλ) froot(n)/n from lmax down to a step of 2^-40 n, then the final pass as the acceptance test
-// (|froot(n)| / froot'(n) within max(2, min(16, 1/κ)) ulps of n).  Groups that fail a guard or the test are left -- unmarked
-// in `done` -- to the bracketing search of the warp path, which runs afterwards.
+// sits in the shared memory of a 256-thread CTA in R (sol | xk | sj, 8 or 16 elements per thread) with Float32 copies
+// of sol and xk in registers; every evaluation of the search is a pass over those registers plus one block reduction
+// (a single __syncthreads: the reduction slots alternate).  The search is the one of the uniform path: froot(lmin)
+// skipped when its sign is certain, Newton on h(n) = (n - σλ) froot(n)/n from lmax in Float32, one evaluation in R with
+// Float64 sums and a Halley step, then the final pass as the acceptance test (|froot(n)| / froot'(n) within
+// max(2, min(16, 1/κ)) ulps of n).  Groups that fail a guard or the test are left -- unmarked in `done` -- to the
+// bracketing search of the warp path, which runs afterwards.  (The all-R search this replaces spent 293 thread
+// instructions per element, most of them Float64, on the ragged layout.)
 constexpr int kBinfBigThreads = 256;  // two CTAs per SM, 16 (or 8) elements per thread; 512 threads x 8 measured slower
-constexpr int kBinfMidThreads = 128;  // groups of 257..1024 elements: four CTAs per SM, 8 (or 4) elements per thread
+constexpr int kBinfMidThreads = 128;  // groups of 257..512 and 513..1024 elements: eight CTAs per SM, 4 and 8 elements per thread
 template <int T> struct BigRed {
   double v[2][T / 32][4];
 };
@@ -1474,18 +1481,59 @@ template <int N, int T> __device__ __forceinline__ void block_sums(double (&a)[N
   parity ^= 1;
 }
 
-// one group, E elements per thread (E * 256 >= m).  Returns true when y_g has been written.
+template <int T> struct BigRedF {
+  float v[2][T / 32][4];
+};
+// Float32 form for the search: sums a[0..N) (N <= 3) and, when mx is given, the maximum of *mx over the CTA
+template <int N, int T>
+__device__ __forceinline__ void block_sums_f(float (&a)[N], BigRedF<T>& red, int& parity, float* mx = nullptr) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) a[k] += __shfl_xor_sync(0xffffffffu, a[k], o);
+    if (mx) *mx = fmaxf(*mx, __shfl_xor_sync(0xffffffffu, *mx, o));
+  }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) red.v[parity][w][k] = a[k];
+    if (mx) red.v[parity][w][3] = *mx;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    float t = 0.f;
+#pragma unroll
+    for (int ww = 0; ww < T / 32; ++ww) t += red.v[parity][ww][k];
+    a[k] = t;
+  }
+  if (mx) {
+    float m = 0.f;
+#pragma unroll
+    for (int ww = 0; ww < T / 32; ++ww) m = fmaxf(m, red.v[parity][ww][3]);
+    *mx = m;
+  }
+  parity ^= 1;
+}
+
+// one group, E elements per thread (E T >= m).  Returns true when y_g has been written.
+// The search runs on Float32 copies of sol and xk held in registers (Float32 sums, one barrier per evaluation); the
+// group itself stays in the staging planes in R -- sol (later w) | xk | sj, every thread reading and writing only its
+// own slots -- for the one evaluation in R with Float64 sums (Halley step) and the final pass, which is the acceptance
+// test.  What the search did therefore cannot reach y except through a root the final pass has accepted.
 template <class R, int E, int T, int PL>
 __device__ __forceinline__ bool binf_big_group(R* y, const R* xk, const R* sj, const R* q, long long b, long long e,
                                                R lam, R sigma, R delta, const UDiv<R>& by_sigma, BigRed<T>& red,
-                                               int& parity, R* stage) {
+                                               BigRedF<T>& redf, int& parity, int& parity_f, R* stage) {
   const int t = threadIdx.x;
   const R epsR = Eps<R>::value;
   const R sl = lam * sigma;
-  R sol[E], xkr[E];
-  // every thread copies ITS elements of q, xk, sj into its slots of the staging planes (no registers tied up by loads
-  // in flight, all of them issued before the first use, nobody else reads the slots: cp.async.wait_group is the only
-  // synchronisation); sj stays there for the write phase
+  float so[E], xg[E];
+  // slots in use: ne per thread (CTA-uniform; the loops below skip the others), element k T + t of the group in slot k
+  const int m = (int)(e - b), ne = (m + T - 1) / T;
+  const R* const gq = q + b;
+  const R* const gx = xk + b;
+  const R* const gs = sj + b;
   R* const st_q = stage + t;
   R* const st_x = stage + PL + t;
   R* const st_s = stage + 2 * PL + t;
@@ -1494,158 +1542,195 @@ __device__ __forceinline__ bool binf_big_group(R* y, const R* xk, const R* sj, c
                    as = (uint32_t)__cvta_generic_to_shared(st_s);
 #pragma unroll
     for (int k = 0; k < E; ++k) {
-      const long long i = b + (long long)k * T + t;
-      if (i < e) {
+      const int i = k * T + t;
+      if (k < ne && i < m) {
         const uint32_t o = (uint32_t)(k * T * (int)sizeof(R));
-        cp_async_elem<R>(aq + o, q + i);
-        cp_async_elem<R>(ax + o, xk + i);
-        cp_async_elem<R>(as + o, sj + i);
+        cp_async_elem<R>(aq + o, gq + i);
+        cp_async_elem<R>(ax + o, gx + i);
+        cp_async_elem<R>(as + o, gs + i);
       }
     }
     cp_async_commit();
     cp_async_wait<0>();
   }
+  // sol over q in the plane; slots beyond the group hold zeros (they add nothing to any sum below)
 #pragma unroll
   for (int k = 0; k < E; ++k) {
-    const long long i = b + (long long)k * T + t;
-    sol[k] = R(0);
-    xkr[k] = R(0);
-    if (i < e) {
-      const R xi = st_x[k * T], si = st_s[k * T], qi = st_q[k * T];
-      sol[k] = (qi + xi) + si;  // :80
-      xkr[k] = xi;
+    const int i = k * T + t;
+    R s = R(0), xi = R(0);
+    if (i < m) {
+      xi = st_x[k * T];
+      s = (st_q[k * T] + xi) + st_s[k * T];  // :80
+    } else {
+      st_x[k * T] = R(0);
     }
+    st_q[k * T] = s;
+    so[k] = (float)s;
+    xg[k] = (float)xi;
   }
-  // ---- the three norms of :97-100 (and max |xk|) at τa = σ c(lmin + 1)
+  // ---- A: the three norms of :97-100 (and max |xk|) at τa = σ c(lmin + 1), in Float32
   const R lmin = sl * (R(1) + epsR);
   const R ansatz = lmin + R(1);
-  const R tau_a = sigma * (ansatz / (sigma * (ansatz - sl)));
-  double nm[3] = {0.0, 0.0, 0.0};
-  R xmax = R(0);
+  const R step_a = ansatz / (sigma * (ansatz - sl));
+  const float slf = (float)sl, delf = (float)delta, lminf = (float)lmin;
+  const float tau_a = (float)sigma * (float)step_a;
+  float nm[3] = {0.f, 0.f, 0.f}, xmax = 0.f;
   {
-    const R sdc = tau_a * delta;
+    const float sdc = tau_a * delf;
 #pragma unroll
     for (int k = 0; k < E; ++k) {
-      const R tt = sol[k] - tau_a * xkr[k];
-      const R a = jl_abs(tt) - sdc;
-      const double z = a > R(0) ? (double)a : 0.0;
-      nm[0] = __fma_rn(z, z, nm[0]);
-      nm[1] = __fma_rn((double)sol[k], (double)sol[k], nm[1]);
-      nm[2] = __fma_rn((double)xkr[k], (double)xkr[k], nm[2]);
-      xmax = jl_abs(xkr[k]) > xmax ? jl_abs(xkr[k]) : xmax;
+      if (k >= ne) break;
+      const float tt = fmaf(-tau_a, xg[k], so[k]);
+      const float a = fmaxf(fabsf(tt) - sdc, 0.f);
+      nm[0] = fmaf(a, a, nm[0]);
+      nm[1] = fmaf(so[k], so[k], nm[1]);
+      nm[2] = fmaf(xg[k], xg[k], nm[2]);
+      xmax = fmaxf(xmax, fabsf(xg[k]));
     }
-    block_sums<3, T>(nm, red, parity);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const R other = __shfl_xor_sync(0xffffffffu, xmax, o);
-      xmax = other > xmax ? other : xmax;
-    }
-    // block-wide max of |xk| through the reduction slots (one more barrier)
-    const int lane = t & 31, w = t >> 5;
-    if (lane == 0) red.v[parity][w][0] = (double)xmax;
-    __syncthreads();
-    double m = 0.0;
-#pragma unroll
-    for (int ww = 0; ww < T / 32; ++ww) m = red.v[parity][ww][0] > m ? red.v[parity][ww][0] : m;
-    xmax = (R)m;
-    parity ^= 1;
+    block_sums_f<3, T>(nm, redf, parity_f, &xmax);
   }
-  const R nsol = (R)sqrt_fast(nm[1]);
-  const R lmax = nsol + sigma * ((R)sqrt_fast(nm[0]) / sigma + R(1) * lam * (R)sqrt_fast(nm[2]));
-  // guards: finite, well-scaled, a proper bracket (everything else: the bracketing search)
-  bool ok = (nm[1] > 1e-280 && nm[1] < 1e280) && (nm[2] < 1e280) && (nm[0] < 1e280) && (sl > R(0)) &&
-            (lmax > lmin * (R)1.001) && (lmax == lmax);
-  auto eval = [&](R tau, double& ssA, double& ssB) {
-    double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
-    const R sdc = tau * delta;
+  const float nsolf = sqrt_approx(nm[1]);
+  const float lmaxf = nsolf + sqrt_approx(nm[0]) + slf * sqrt_approx(nm[2]);
+  // magnitudes the Float32 search is trusted with (see binf_fast_search); everything else: the bracketing search
+  bool ok = (nm[1] > 1e-16f && nm[1] < 1e24f) && (nm[2] < 1e24f) && (nm[0] < 1e30f) && (delf < 1e12f) &&
+            (slf > 1e-12f && slf < 1e12f) && (lmaxf > lminf * 1.001f);
+  auto eval = [&](float tau, float& ssA, float& ssB) {
+    float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+    const float sdc = tau * delf;
 #pragma unroll
     for (int k = 0; k < E; k += 2) {
-      binf_term<R, double>(sol[k], xkr[k], tau, sdc, a0, b0);
-      binf_term<R, double>(sol[k + 1], xkr[k + 1], tau, sdc, a1, b1);
+      if (k >= ne) break;
+      binf_term<float, float>(so[k], xg[k], tau, sdc, a0, b0);
+      binf_term<float, float>(so[k + 1], xg[k + 1], tau, sdc, a1, b1);
     }
-    double ab[2] = {a0 + a1, b0 + b1};
+    float ab[2] = {a0 + a1, b0 + b1};
 #ifdef SPX_GROUP_STATS
     if (threadIdx.x == 0) atomicAdd(&g_stat_big[0], 1ull);
 #endif
-    block_sums<2, T>(ab, red, parity);
+    block_sums_f<2, T>(ab, redf, parity_f);
     ssA = ab[0];
     ssB = ab[1];
   };
   // froot(lmin) < 0 for certain when some |xk_i| is clearly above Δ (see binf_fast_search)
-  const R tau_l = (R(1) + epsR) / epsR;
-  const R excess = xmax - delta;
-  const bool fl_neg = (excess > (R)1e-4 * (xmax + delta)) && (excess * tau_l > (R)1e4 * (lmin + nsol));
-  R fl = R(-1);
-  if (ok && !fl_neg) {  // CTA-uniform
-    double ssA, ssB;
+  const float tau_l = (float)((R(1) + epsR) / epsR);
+  const float excess = xmax - delf;
+  const bool fl_neg = (excess > 1e-4f * (xmax + delf)) && (excess * tau_l > 1e4f * (lminf + nsolf));
+  float fl = -1.f;
+  if (ok && !fl_neg) {  // CTA-uniform: every thread holds the same scalars
+    float ssA, ssB;
     eval(tau_l, ssA, ssB);
-    const R nw = (R)sqrt_fast(ssA + ssB);
-    fl = lmin - nw;
-    ok = ok && (jl_abs(fl) > (R)1e-6 * jl_max(lmin, nw));
+    const float nw = sqrt_approx(ssA + ssB);
+    fl = lminf - nw;
+    ok = ok && (fabsf(fl) > 1e-4f * fmaxf(lminf, nw));
   }
-  // Newton on h(n) = (n - σλ) froot(n)/n from lmax
-  R x = lmax, a_ = lmin, b_ = lmax, dfx_last = R(1);
-  bool zero_out = false, conv = !ok;
+  // froot(lmax), then Newton on h(n) = (n - σλ) froot(n)/n
+  float x = lmaxf, a_ = lminf, b_ = lmaxf;
+  bool zero_out = false, conv = false;
+  if (ok) {
 #pragma unroll 1
-  for (int it = 0; it < 16 && !conv; ++it) {
-    const R gap = x - sl;
-    const R tau = div_fast(x, gap);
-    double ssA, ssB;
-    eval(tau, ssA, ssB);
-    const R nw = (R)sqrt_fast(ssA + ssB);
-    const R fx = x - nw;
-    const R dfx = R(1) + div_fast((R)ssA * sl, x * nw * gap);  // froot' = 1 + (ssA/τ) σλ / (||w|| gap²)
-    dfx_last = dfx;
-    if (it == 0) {
-      ok = ok && (jl_abs(fx) > (R)1e-6 * x);
-      zero_out = (fl > R(0)) == (fx > R(0));  // fl*fm > 0  (:102)
-      if (!ok || zero_out) break;
+    for (int it = 0; it < 8; ++it) {
+      const float gap = x - slf;
+      const float rgap = rcp_f(gap), rx = rcp_f(x);
+      const float tau = x * rgap;
+      float ssA, ssB;
+      eval(tau, ssA, ssB);
+      const float nw = sqrt_approx(ssA + ssB);
+      const float fx = x - nw;
+      const float dfx = fmaf(ssA * slf, rx * rcp_f(nw) * rgap, 1.f);  // froot' = 1 + (ssA/τ) σλ / (||w|| gap²)
+      if (it == 0) {
+        ok = fabsf(fx) > 1e-4f * x;
+        zero_out = (fl > 0.f) == (fx > 0.f);  // fl*fm > 0  (:102)
+        if (!ok || zero_out) break;
+      }
+      const float den = fmaf(gap, dfx - fx * rx, fx);
+      const float stp = gap * fx * rcp_f(den);
+      float xn = x - stp;
+      conv = (fabsf(stp) <= kBinfSearchTol * x) || (fx == 0.f);
+      a_ = (fx < 0.f) ? x : a_;
+      b_ = (fx < 0.f) ? b_ : x;
+      if (!(xn >= a_ && xn <= b_)) xn = 0.5f * (a_ + b_);  // also catches NaN
+      x = xn;
+      if (conv) break;
     }
-    const R den = fx + gap * (dfx - div_fast(fx, x));
-    const R stp = div_fast(gap * fx, den);
-    R xn = x - stp;
-    a_ = (fx < R(0)) ? x : a_;
-    b_ = (fx < R(0)) ? b_ : x;
-    if (!(xn >= a_ && xn <= b_)) xn = a_ + (b_ - a_) / R(2);
-    conv = (jl_abs(stp) <= (R)(sizeof(R) == 8 ? 1.5e-8 : 2e-4) * x) || (fx == R(0));  // the NEXT iterate is then good
-    x = xn;                                                                            // to the square of that
   }
-  ok = ok && (zero_out || (conv && x == x && x > lmin && sl < R(64) * (x - sl)));
-  if (!ok) return false;  // CTA-uniform: every thread holds the same scalars
-  // ---- y_g = l2prox(sol - σ softthres(sol/σ - c xk, Δ c), σλ) - (xk + sj)   (:109-116), and the acceptance test
-  const R nroot = x;
-  const R step = div_fast(nroot, sigma * (nroot - sl));
-  const R dstep2 = delta * step;
-  double vs[1] = {0.0};
-#pragma unroll
-  for (int k = 0; k < E; ++k) {  // w overwrites sol
-    sol[k] = sol[k] - sigma * softthres_sel(quot_uniform(sol[k], by_sigma) - step * xkr[k], dstep2);
-    vs[0] = __fma_rn((double)sol[k], (double)sol[k], vs[0]);
-  }
-  block_sums<1, T>(vs, red, parity);
-  const R nv = (R)sqrt_fast(vs[0]);
+  ok = ok && (zero_out || conv) && (x == x);
+  if (!ok) return false;
+  R nroot = R(0);
+  double fp = 1.0;
   if (!zero_out) {
+    // ---- B: one evaluation in R with Float64 sums at the Float32 root, Halley step (as in binf_fast_search)
+    const double xd = (double)x, sld = (double)sl;
+    const double gapd = xd - sld;
+    const double rg = rcp_d(gapd);
+    const double taud = xd * rg;
+    double ab[2];
+    {
+      const R tau = (R)taud, sdc = (R)((double)delta * taud);
+      double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+#pragma unroll
+      for (int k = 0; k < E; k += 2) {
+        if (k >= ne) break;
+        binf_term<R, double>(st_q[k * T], st_x[k * T], tau, sdc, a0, b0);
+        binf_term<R, double>(st_q[(k + 1) * T], st_x[(k + 1) * T], tau, sdc, a1, b1);
+      }
+      ab[0] = a0 + a1;
+      ab[1] = b0 + b1;
+#ifdef SPX_GROUP_STATS
+      if (threadIdx.x == 0) atomicAdd(&g_stat_big[0], 1ull);
+#endif
+      block_sums<2, T>(ab, red, parity);
+    }
+    const double ssA = ab[0], ssB = ab[1];
+    const double phi = sqrt_fast(ssA + ssB);
+    const double f = xd - phi;
+    const double rD = rcp_d(xd * phi * gapd);
+    const double p1 = ssA * sld * rD;
+    fp = 1.0 + p1;
+    const double fpp = -(p1 * (ssB * sld * rD) * (rD * xd * gapd) + 2.0 * p1 * rg);
+    const double n1 = xd - 2.0 * f * fp * rcp_d(__fma_rn(2.0 * fp, fp, -f * fpp));
+    nroot = (R)n1;
+    const double kap = sld * rcp_d(n1 - sld);
+    if (!(n1 > (double)lmin && kap < 64.0 && n1 == n1)) return false;  // next to the pole of c, or not finite
+  }
+  // ---- y_g = l2prox(sol - σ softthres(sol/σ - c xk, Δ c), σλ) - (xk + sj)   (:109-116), and the acceptance test
+  R alpha = R(0);
+  if (!zero_out) {
+    const R step = div_fast(nroot, sigma * (nroot - sl));
+    const R dstep2 = delta * step;
+    double vs[1] = {0.0};
+#pragma unroll
+    for (int k = 0; k < E; ++k) {  // w overwrites sol
+      if (k >= ne) break;
+      const R s = st_q[k * T];
+      const R w = s - sigma * softthres_sel(quot_uniform(s, by_sigma) - step * st_x[k * T], dstep2);
+      st_q[k * T] = w;
+      vs[0] = __fma_rn((double)w, (double)w, vs[0]);
+    }
+    block_sums<1, T>(vs, red, parity);
+    const R nv = (R)sqrt_fast(vs[0]);
     const R res = nroot - nv;
     const R gap = nroot - sl;
     // within max(2, min(16, 1/κ)) ulps of the root: |res| / froot' (see group_l2binf_uniform_kernel)
     const R ulps = jl_max(R(2), jl_min(R(16), gap * (R)(1.0 / (double)sl)));
-    if (!(jl_abs(res) <= ulps * epsR * nroot * dfx_last)) return false;  // not accepted: the bracketing search takes it
+    if (!(jl_abs(res) <= ulps * epsR * nroot * (R)fp)) return false;  // not accepted: the bracketing search takes it
+    alpha = jl_max(R(0), R(1) - div_fast(sl, nv));
   }
-  const R alpha = zero_out ? R(0) : jl_max(R(0), R(1) - div_fast(sl, nv));
+  R* const gy = y + b;
 #pragma unroll
   for (int k = 0; k < E; ++k) {
-    const long long i = b + (long long)k * T + t;
-    if (i < e) {
-      const R o = zero_out ? R(0) : alpha * sol[k];
-      stv(y + i, o - (xkr[k] + st_s[k * T]));
+    const int i = k * T + t;
+    if (k < ne && i < m) {
+      const R o = zero_out ? R(0) : alpha * st_q[k * T];
+      stv(gy + i, o - (st_x[k * T] + st_s[k * T]));
     }
   }
   return true;
 }
 
 // T threads per group; groups of LO < m <= EA T elements with EA elements per thread, up to EB T with EB
-template <class R, int T, int LO, int EA, int EB>
-__global__ void __launch_bounds__(T, 512 / T)
+// TPS: threads per SM the register budget is set for (512: 128 registers, 1024: 64)
+template <class R, int T, int LO, int EA, int EB, int TPS>
+__global__ void __launch_bounds__(T, TPS / T)
     group_l2binf_big_kernel(R* y, const R* xk, const R* sj, const R* q, long long ngroups,
                             const long long* __restrict__ offs, const R* __restrict__ lambda_g, R sigma, R delta,
                             UDiv<R> by_sigma, const unsigned* __restrict__ uniform_flag, unsigned char* __restrict__ done) {
@@ -1654,10 +1739,11 @@ __global__ void __launch_bounds__(T, 512 / T)
   __shared__ int list[T];
   __shared__ int wcount[T / 32];
   __shared__ BigRed<T> red;
+  __shared__ BigRedF<T> redf;
   extern __shared__ __align__(16) unsigned char big_stage_raw[];
   R* const stage = reinterpret_cast<R*>(big_stage_raw);  // three planes of PL elements: q | xk | sj
   const int t = threadIdx.x;
-  int parity = 0;
+  int parity = 0, parity_f = 0;
   for (long long g0 = (long long)blockIdx.x * T; g0 < ngroups; g0 += (long long)gridDim.x * T) {
     // index-ordered list of this chunk's groups of LO+1 .. EB T elements
     int nbig;
@@ -1690,9 +1776,9 @@ __global__ void __launch_bounds__(T, 512 / T)
       }
       bool wrote;
       if (e - b <= EA * T)
-        wrote = binf_big_group<R, EA, T, PL>(y, xk, sj, q, b, e, lam, sigma, delta, by_sigma, red, parity, stage);
+        wrote = binf_big_group<R, EA, T, PL>(y, xk, sj, q, b, e, lam, sigma, delta, by_sigma, red, redf, parity, parity_f, stage);
       else
-        wrote = binf_big_group<R, EB, T, PL>(y, xk, sj, q, b, e, lam, sigma, delta, by_sigma, red, parity, stage);
+        wrote = binf_big_group<R, EB, T, PL>(y, xk, sj, q, b, e, lam, sigma, delta, by_sigma, red, redf, parity, parity_f, stage);
       if (wrote && t == 0) done[g] = 1;
 #ifdef SPX_GROUP_STATS
       if (t == 0) atomicAdd(&g_stat_big[wrote ? 1 : 2], 1ull);
@@ -2263,14 +2349,21 @@ static int32_t prox_group(spx_ctx* ctx, bool binf, int64_t n, R* y, const R* xk,
         // search anyway, so the census is only a hint here as well)
         const unsigned classes = census_classes(ctx, offs, ngroups, n);
         int32_t stc = SPX_OK;
+        // (1024, 4096]: 256 threads x 8 or 16 elements, two CTAs per SM in 128 registers (measured at 2^28 Float64,
+        // ragged layout: 2.8 ms; split into 512 x 8 and 256 x 8 at 64 registers and 1024 threads per SM: 3.4 ms).
+        // (256, 1024]: two shapes of 128 threads, 8 and 4 elements, 64 registers (0.77 ms; one shape of 4 or 8
+        // elements at 128 registers: 0.94 ms).
         if (classes & 2u) {
-          stc = launch_class(group_l2binf_big_kernel<R, kBinfBigThreads, 1024, 8, 16>, kBinfBigThreads,
+          stc = launch_class(group_l2binf_big_kernel<R, kBinfBigThreads, 1024, 8, 16, 512>, kBinfBigThreads,
                              3 * (size_t)16 * kBinfBigThreads * sizeof(R));
           if (stc != SPX_OK) return stc;
         }
         if ((classes & 1u) && std::getenv("SPX_BINF_NOMID") == nullptr) {
-          stc = launch_class(group_l2binf_big_kernel<R, kBinfMidThreads, 256, 4, 8>, kBinfMidThreads,
+          stc = launch_class(group_l2binf_big_kernel<R, kBinfMidThreads, 512, 8, 8, 1024>, kBinfMidThreads,
                              3 * (size_t)8 * kBinfMidThreads * sizeof(R));
+          if (stc != SPX_OK) return stc;
+          stc = launch_class(group_l2binf_big_kernel<R, kBinfMidThreads, 256, 4, 4, 1024>, kBinfMidThreads,
+                             3 * (size_t)4 * kBinfMidThreads * sizeof(R));
           if (stc != SPX_OK) return stc;
         }
       }

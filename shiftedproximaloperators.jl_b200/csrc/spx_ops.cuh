@@ -752,8 +752,92 @@ template <class R, bool PSI> struct ProxLhalfBox {
   float lamf;  // λ
   float c4f;   // σλ/4
   double a2;   // σλ/2 (= 2 c4), the constant term of the cubic
+  float a2f;   // the same in Float32 (exact when R = Float32: c4 is σλ/4 evaluated in R)
+  __device__ __forceinline__ const LhalfBoxExact<float>& kexact_f32() const {
+    return reinterpret_cast<const LhalfBoxExact<float>&>(k);  // only called when R = Float32
+  }
   bool fast;   // σ, λ, σλ/4 inside the Float32-friendly range (host-checked)
+  // R = Float32.  The reference evaluates candidate 4 in Float64 (`val - xs`, the range test `l <= val - xk <= u`) and
+  // rounds once when it stores into y.  Here val is carried as an unevaluated sum of two Float32 numbers (error
+  // ~1e-11 |val|, that of the one-step Float64 form this replaces): s0² = p + e exactly (one FMA), p - |z| is exact
+  // (Sterbenz: s² ∈ [0.52 |z|, |z|] for t <= 0.9), so the residual of the cubic loses nothing to cancellation; one
+  // Newton step with the Float32 reciprocal slope, s² = p + (e + 2 s0 δ + δ²).  `val - xs` is a TwoSum.
+  // No Float64 instruction and no Float32 <-> Float64 conversion on this path (they share the 16-lane XU pipe with the
+  // square roots: 12 conversions + 6 SFU operations per element made the Float32 kernel slower per byte than the
+  // Float64 one).  t32 in (0.9, 1.002) -- slope of the cubic shrinking, 0.5 % of the bench's elements -- takes the
+  // three-step Float64 Newton; a range test within 4 ulps of a bound goes to lhalfbox_exact.
+  __device__ __forceinline__ float apply_f32(const float (&x)[NIN], long long i, Partial& acc) const {
+    const float xi = x[0], si = x[1], qi = x[2], li = x[3], ui = x[4];
+    const bool s = (sel.kind == SPX_SEL_ALL) || sel.has(i);
+    const float xs = xi + si;  // ψ.sol[i]  (:94)
+    const float xsq = xs + qi;
+    const float zf = fabsf(xsq);
+    const float left = li - si, right = ui - si, mxs = -xs;
+    const LhalfStart st = lhalf_start(zf, c4f);
+    const bool real_branch = st.t32 <= 0.998f;
+    bool hard = !(fast && lhalf_f32_range(zf)) || !(st.t32 <= 0.998f || st.t32 >= 1.002f);
+    float mh, ml;  // |val| = mh + ml
+    if (st.t32 > 0.9f && st.t32 < 1.002f) {
+      const double mag = lhalf_newton<true, true>((double)zf, a2, st);
+      mh = (float)mag;
+      ml = (float)(mag - (double)mh);
+    } else {
+      const float s0 = st.s0;
+      const float p = s0 * s0;
+      const float e = fmaf(s0, s0, -p);
+      const float uh = p - zf;
+      const float t1 = s0 * uh;
+      const float t1e = fmaf(s0, uh, -t1);
+      const float f = (t1 + a2f) + fmaf(s0, e, t1e);
+      const float d = -f * st.inv;
+      const float m1 = fmaf(d, d, fmaf(s0 + s0, d, e));
+      mh = p + m1;
+      ml = (p - mh) + m1;  // Fast2Sum: |p| >= |m1|
+    }
+    // val = sign(xsq) (mh + ml); cand4 = val - xs and vmx = val - xk as two-term sums
+    const float vh = copysignf(mh, xsq), vl = (xsq < 0.f) ? -ml : ml;
+    const float th = vh - xs, tb = th - vh;
+    const float cl = ((vh - (th - tb)) + (-xs - tb)) + vl;
+    const float cand4 = th + cl;  // `val - xs` rounded to R once
+    // li <= val - xk <= ui in Float64: val - xk = (val - xs) + sj; decided by the Float32 value of that (off by at
+    // most half an ulp of each of the two terms) unless it sits within 4 ulps of a bound
+    const float vmx = cand4 + si;
+    const float guard = 2.4e-7f * (fabsf(vmx) + fabsf(cand4));
+    hard = hard || (fabsf(vmx - li) <= guard) || (fabsf(vmx - ui) <= guard);
+    const bool in4 = real_branch && (li <= vmx) && (vmx <= ui);
+    const bool zero_in = (li <= -xi) && (-xi <= ui);
+    // Float32 objectives (as in the generic form below)
+    const float inff = __int_as_float(0x7f800000);
+    const float dlf = left - qi, drf = right - qi;
+    const float alf = fabsf(left + xs), arf = fabsf(right + xs);
+    const float dq4f = (th - qi) + cl;
+    const float c0 = fmaf(dlf * dlf, kf, lamf * sqrt_approx(alf));
+    const float c1 = fmaf(drf * drf, kf, lamf * sqrt_approx(arf));
+    const float c2 = zero_in ? (zf * zf) * kf : inff;
+    const float c3 = in4 ? fmaf(dq4f * dq4f, kf, lamf * sqrt_approx(mh)) : inff;
+    int a = 0;
+    float m = c0;
+    if (c1 < m) { m = c1; a = 1; }
+    if (c2 < m) { m = c2; a = 2; }
+    if (c3 < m) { m = c3; a = 3; }
+    const float lo01 = fminf(c0, c1), hi01 = fmaxf(c0, c1);
+    const float lo23 = fminf(c2, c3), hi23 = fmaxf(c2, c3);
+    const float m2 = fminf(fmaxf(lo01, lo23), fminf(hi01, hi23));  // second smallest
+    const bool clear = (m2 > m * 1.000004f) && (m > 1e-30f);
+    // the objectives are >= +0, +Inf or NaN: their sum is NaN exactly when one of them is
+    const float csum = (c0 + c1) + (c2 + c3);
+    hard = hard || !clear || (csum != csum);
+    float o = left;
+    o = (a == 1) ? right : o;
+    o = (a == 2) ? mxs : o;
+    o = (a == 3) ? cand4 : o;
+    if (hard) o = lhalfbox_exact<float>(xi, si, qi, li, ui, kexact_f32());
+    if (!s) o = prox_zero(qi, left, right);
+    if (PSI) BoxPsi<float>{SPX_H_LHALF}.add(acc, s, xi, si, o, li, ui);
+    return o;
+  }
   __device__ __forceinline__ R apply(const R (&x)[NIN], long long i, Partial& acc) const {
+    if constexpr (sizeof(R) == 4) return apply_f32(x, i, acc);
     const R xi = x[0], si = x[1], qi = x[2], li = x[3], ui = x[4];
     const bool s = (sel.kind == SPX_SEL_ALL) || sel.has(i);
     const R xs = xi + si;  // ψ.sol[i]  (:94)

@@ -67,6 +67,7 @@ template <class R, bool PSI> static inline void configure(ProxLhalfBox<R, PSI>& 
   op.lamf = (float)lam;
   op.c4f = (float)op.k.c4;
   op.a2 = op.k.c4 + op.k.c4;
+  op.a2f = (float)op.a2;
   op.fast = lhalf_f32_range_host(op.k.c4) && lhalf_f32_range_host((double)sig) && lhalf_f32_range_host((double)lam);
 }
 
