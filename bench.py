@@ -404,7 +404,9 @@ def run_configs(args, sp, L, shd, dev, dist, world, rank, peak, c2):
                C.c_uint64(SEED), C.c_uint64(stream), ct(scale), ct(shift))
         return t
 
-    def timed(fn):
+    def timed(fn, burst=1):
+        # burst > 1: that many calls between one pair of events (time per call): the host's launch path, which a single
+        # call of a 5 us kernel mostly measures, overlaps with the kernels already queued
         for _ in range(3):
             fn()
         if dist is not None:
@@ -413,10 +415,11 @@ def run_configs(args, sp, L, shd, dev, dist, world, rank, peak, c2):
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
         for a, b in ev:
             a.record()
-            fn()
+            for _ in range(burst):
+                fn()
             b.record()
         torch.cuda.synchronize()
-        ts = sorted(a.elapsed_time(b) for a, b in ev)
+        ts = sorted(a.elapsed_time(b) / burst for a, b in ev)
         ms = ts[len(ts) // 2]
         if dist is not None:
             tt = torch.tensor([ms], dtype=f64, device=dev)
@@ -442,6 +445,9 @@ def run_configs(args, sp, L, shd, dev, dist, world, rank, peak, c2):
         c1[name] = entry(timed(lambda: sp.prox_(y, psi, q, SIGMA)), world * n, 32)
         c1[name + "+psi"] = entry(timed(lambda: sp.prox_(y, psi, q, SIGMA, want_value=True)), world * n, 32,
                                   note="psi(y) fused" + (", scalar all-reduced (NCCL)" if world > 1 else ""))
+        if n == 1_000_000:  # launch-bound: the same call 32 times back to back (the four vectors, 32 MB, stay in L2)
+            c1[name + "_x32_back_to_back"] = entry(timed(lambda: sp.prox_(y, psi, q, SIGMA), burst=32), world * n, 32,
+                                                   note="time per call of 32 queued calls; operands L2-resident (32 MB)")
         del xk, sj, q, y, psi
     out["C1"] = c1
     torch.cuda.empty_cache()

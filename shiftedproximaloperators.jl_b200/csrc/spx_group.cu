@@ -1521,7 +1521,9 @@ __device__ __forceinline__ void block_sums_f(float (&a)[N], BigRedF<T>& red, int
 // group itself stays in the staging planes in R -- sol (later w) | xk | sj, every thread reading and writing only its
 // own slots -- for the one evaluation in R with Float64 sums (Halley step) and the final pass, which is the acceptance
 // test.  What the search did therefore cannot reach y except through a root the final pass has accepted.
-template <class R, int E, int T, int PL>
+// SJP: sj has a staging plane of its own; !SJP: it is read straight from global memory for sol and once more (an L2
+// hit) for the store -- two planes per CTA instead of three, so a third CTA fits on the SM
+template <class R, int E, int T, int PL, bool SJP>
 __device__ __forceinline__ bool binf_big_group(R* y, const R* xk, const R* sj, const R* q, long long b, long long e,
                                                R lam, R sigma, R delta, const UDiv<R>& by_sigma, BigRed<T>& red,
                                                BigRedF<T>& redf, int& parity, int& parity_f, R* stage) {
@@ -1536,7 +1538,8 @@ __device__ __forceinline__ bool binf_big_group(R* y, const R* xk, const R* sj, c
   const R* const gs = sj + b;
   R* const st_q = stage + t;
   R* const st_x = stage + PL + t;
-  R* const st_s = stage + 2 * PL + t;
+  R* const st_s = stage + (SJP ? 2 : 0) * PL + t;  // !SJP: never dereferenced
+  R sjr[SJP ? 1 : E];
   {
     const uint32_t aq = (uint32_t)__cvta_generic_to_shared(st_q), ax = (uint32_t)__cvta_generic_to_shared(st_x),
                    as = (uint32_t)__cvta_generic_to_shared(st_s);
@@ -1547,10 +1550,17 @@ __device__ __forceinline__ bool binf_big_group(R* y, const R* xk, const R* sj, c
         const uint32_t o = (uint32_t)(k * T * (int)sizeof(R));
         cp_async_elem<R>(aq + o, gq + i);
         cp_async_elem<R>(ax + o, gx + i);
-        cp_async_elem<R>(as + o, gs + i);
+        if (SJP) cp_async_elem<R>(as + o, gs + i);
       }
     }
     cp_async_commit();
+    if (!SJP) {  // in flight together with the copies
+#pragma unroll
+      for (int k = 0; k < E; ++k) {
+        const int i = k * T + t;
+        sjr[k] = (k < ne && i < m) ? ldv(gs + i) : R(0);
+      }
+    }
     cp_async_wait<0>();
   }
   // sol over q in the plane; slots beyond the group hold zeros (they add nothing to any sum below)
@@ -1560,7 +1570,7 @@ __device__ __forceinline__ bool binf_big_group(R* y, const R* xk, const R* sj, c
     R s = R(0), xi = R(0);
     if (i < m) {
       xi = st_x[k * T];
-      s = (st_q[k * T] + xi) + st_s[k * T];  // :80
+      s = (st_q[k * T] + xi) + (SJP ? st_s[k * T] : sjr[SJP ? 0 : k]);  // :80
     } else {
       st_x[k * T] = R(0);
     }
@@ -1721,7 +1731,7 @@ __device__ __forceinline__ bool binf_big_group(R* y, const R* xk, const R* sj, c
     const int i = k * T + t;
     if (k < ne && i < m) {
       const R o = zero_out ? R(0) : alpha * st_q[k * T];
-      stv(gy + i, o - (st_x[k * T] + st_s[k * T]));
+      stv(gy + i, o - (st_x[k * T] + (SJP ? st_s[k * T] : gs[i])));
     }
   }
   return true;
@@ -1729,7 +1739,7 @@ __device__ __forceinline__ bool binf_big_group(R* y, const R* xk, const R* sj, c
 
 // T threads per group; groups of LO < m <= EA T elements with EA elements per thread, up to EB T with EB
 // TPS: threads per SM the register budget is set for (512: 128 registers, 1024: 64)
-template <class R, int T, int LO, int EA, int EB, int TPS>
+template <class R, int T, int LO, int EA, int EB, int TPS, bool SJP = true>
 __global__ void __launch_bounds__(T, TPS / T)
     group_l2binf_big_kernel(R* y, const R* xk, const R* sj, const R* q, long long ngroups,
                             const long long* __restrict__ offs, const R* __restrict__ lambda_g, R sigma, R delta,
@@ -1776,9 +1786,9 @@ __global__ void __launch_bounds__(T, TPS / T)
       }
       bool wrote;
       if (e - b <= EA * T)
-        wrote = binf_big_group<R, EA, T, PL>(y, xk, sj, q, b, e, lam, sigma, delta, by_sigma, red, redf, parity, parity_f, stage);
+        wrote = binf_big_group<R, EA, T, PL, SJP>(y, xk, sj, q, b, e, lam, sigma, delta, by_sigma, red, redf, parity, parity_f, stage);
       else
-        wrote = binf_big_group<R, EB, T, PL>(y, xk, sj, q, b, e, lam, sigma, delta, by_sigma, red, redf, parity, parity_f, stage);
+        wrote = binf_big_group<R, EB, T, PL, SJP>(y, xk, sj, q, b, e, lam, sigma, delta, by_sigma, red, redf, parity, parity_f, stage);
       if (wrote && t == 0) done[g] = 1;
 #ifdef SPX_GROUP_STATS
       if (t == 0) atomicAdd(&g_stat_big[wrote ? 1 : 2], 1ull);
@@ -2350,7 +2360,9 @@ static int32_t prox_group(spx_ctx* ctx, bool binf, int64_t n, R* y, const R* xk,
         const unsigned classes = census_classes(ctx, offs, ngroups, n);
         int32_t stc = SPX_OK;
         // (1024, 4096]: 256 threads x 8 or 16 elements, two CTAs per SM in 128 registers (measured at 2^28 Float64,
-        // ragged layout: 2.8 ms; split into 512 x 8 and 256 x 8 at 64 registers and 1024 threads per SM: 3.4 ms).
+        // ragged layout: 2.8 ms; split into 512 x 8 and 256 x 8 at 64 registers and 1024 threads per SM: 3.4 ms;
+        // three CTAs per SM in 80 registers with sj read from global memory instead of staged -- the SJP = false
+        // form of the kernel -- 3.3 ms: more resident CTAs do not help this class).
         // (256, 1024]: two shapes of 128 threads, 8 and 4 elements, 64 registers (0.77 ms; one shape of 4 or 8
         // elements at 128 registers: 0.94 ms).
         if (classes & 2u) {
