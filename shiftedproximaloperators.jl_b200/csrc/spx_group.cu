@@ -1448,7 +1448,8 @@ __global__ void __launch_bounds__(kGroupThreads, sizeof(R) == 8 ? 2 : 3)
 // ---- one CTA per group of 1025..4096 elements (ShiftedGroupNormL2Binf) ----------------------------------------------
 // The warp path above keeps a long group in the output vector and re-reads it from L2 for every evaluation of froot:
 // with groups of thousands of elements nearly all of a ragged vector goes through one warp per group.  Here the group
-// sits in the shared memory of a 256-thread CTA in R (sol | xk | sj, 8 or 16 elements per thread) with Float32 copies
+// sits in the shared memory of a 256-thread CTA in R (sol | xk | sj, 8 or 16 elements per thread; q | xk | sj arrive by
+// three bulk copies of one elected thread, as in group_l2_big_kernel: no per-element copy instructions) with Float32 copies
 // of sol and xk in registers; every evaluation of the search is a pass over those registers plus one block reduction
 // (a single __syncthreads: the reduction slots alternate).  The search is the one of the uniform path: froot(lmin)
 // skipped when its sign is certain, Newton on h(n) = (n - σλ) froot(n)/n from lmax in Float32, one evaluation in R with
@@ -1521,48 +1522,31 @@ __device__ __forceinline__ void block_sums_f(float (&a)[N], BigRedF<T>& red, int
 // group itself stays in the staging planes in R -- sol (later w) | xk | sj, every thread reading and writing only its
 // own slots -- for the one evaluation in R with Float64 sums (Halley step) and the final pass, which is the acceptance
 // test.  What the search did therefore cannot reach y except through a root the final pass has accepted.
-// SJP: sj has a staging plane of its own; !SJP: it is read straight from global memory for sol and once more (an L2
-// hit) for the store -- two planes per CTA instead of three, so a third CTA fits on the SM
-template <class R, int E, int T, int PL, bool SJP>
+// q | xk | sj of the group arrive in the planes (PLS elements each: bulk_plane) by three bulk copies issued by thread 0
+// once every thread is done with the previous group (the barrier below), completion on `bar`.
+template <class R, int E, int T, int PLS>
 __device__ __forceinline__ bool binf_big_group(R* y, const R* xk, const R* sj, const R* q, long long b, long long e,
                                                R lam, R sigma, R delta, const UDiv<R>& by_sigma, BigRed<T>& red,
-                                               BigRedF<T>& redf, int& parity, int& parity_f, R* stage) {
+                                               BigRedF<T>& redf, int& parity, int& parity_f, R* stage, uint64_t* bar,
+                                               uint32_t& phase) {
   const int t = threadIdx.x;
   const R epsR = Eps<R>::value;
   const R sl = lam * sigma;
   float so[E], xg[E];
   // slots in use: ne per thread (CTA-uniform; the loops below skip the others), element k T + t of the group in slot k
   const int m = (int)(e - b), ne = (m + T - 1) / T;
-  const R* const gq = q + b;
-  const R* const gx = xk + b;
-  const R* const gs = sj + b;
-  R* const st_q = stage + t;
-  R* const st_x = stage + PL + t;
-  R* const st_s = stage + (SJP ? 2 : 0) * PL + t;  // !SJP: never dereferenced
-  R sjr[SJP ? 1 : E];
-  {
-    const uint32_t aq = (uint32_t)__cvta_generic_to_shared(st_q), ax = (uint32_t)__cvta_generic_to_shared(st_x),
-                   as = (uint32_t)__cvta_generic_to_shared(st_s);
-#pragma unroll
-    for (int k = 0; k < E; ++k) {
-      const int i = k * T + t;
-      if (k < ne && i < m) {
-        const uint32_t o = (uint32_t)(k * T * (int)sizeof(R));
-        cp_async_elem<R>(aq + o, gq + i);
-        cp_async_elem<R>(ax + o, gx + i);
-        if (SJP) cp_async_elem<R>(as + o, gs + i);
-      }
-    }
-    cp_async_commit();
-    if (!SJP) {  // in flight together with the copies
-#pragma unroll
-      for (int k = 0; k < E; ++k) {
-        const int i = k * T + t;
-        sjr[k] = (k < ne && i < m) ? ldv(gs + i) : R(0);
-      }
-    }
-    cp_async_wait<0>();
+  __syncthreads();  // the planes are free: every thread has finished the previous group
+  if (t == 0) {
+    fence_proxy_async();
+    stage_group_bulk<R, 3, PLS>(stage, bar, q, xk, sj, b, e);
   }
+  // each thread works on its own slots from here on (element k T + t of the group; the planes carry the padding of
+  // the 16-byte granule the group starts in)
+  R* const st_q = stage + bulk_skip(q + b) + t;
+  R* const st_x = stage + PLS + bulk_skip(xk + b) + t;
+  R* const st_s = stage + 2 * PLS + bulk_skip(sj + b) + t;
+  mbar_wait(bar, phase);
+  phase ^= 1u;
   // sol over q in the plane; slots beyond the group hold zeros (they add nothing to any sum below)
 #pragma unroll
   for (int k = 0; k < E; ++k) {
@@ -1570,7 +1554,7 @@ __device__ __forceinline__ bool binf_big_group(R* y, const R* xk, const R* sj, c
     R s = R(0), xi = R(0);
     if (i < m) {
       xi = st_x[k * T];
-      s = (st_q[k * T] + xi) + (SJP ? st_s[k * T] : sjr[SJP ? 0 : k]);  // :80
+      s = (st_q[k * T] + xi) + st_s[k * T];  // :80
     } else {
       st_x[k * T] = R(0);
     }
@@ -1731,7 +1715,7 @@ __device__ __forceinline__ bool binf_big_group(R* y, const R* xk, const R* sj, c
     const int i = k * T + t;
     if (k < ne && i < m) {
       const R o = zero_out ? R(0) : alpha * st_q[k * T];
-      stv(gy + i, o - (st_x[k * T] + (SJP ? st_s[k * T] : gs[i])));
+      stv(gy + i, o - (st_x[k * T] + st_s[k * T]));
     }
   }
   return true;
@@ -1739,20 +1723,25 @@ __device__ __forceinline__ bool binf_big_group(R* y, const R* xk, const R* sj, c
 
 // T threads per group; groups of LO < m <= EA T elements with EA elements per thread, up to EB T with EB
 // TPS: threads per SM the register budget is set for (512: 128 registers, 1024: 64)
-template <class R, int T, int LO, int EA, int EB, int TPS, bool SJP = true>
+template <class R, int T, int LO, int EA, int EB, int TPS>
 __global__ void __launch_bounds__(T, TPS / T)
     group_l2binf_big_kernel(R* y, const R* xk, const R* sj, const R* q, long long ngroups,
                             const long long* __restrict__ offs, const R* __restrict__ lambda_g, R sigma, R delta,
                             UDiv<R> by_sigma, const unsigned* __restrict__ uniform_flag, unsigned char* __restrict__ done) {
   if (uniform_flag != nullptr && *uniform_flag != 0u) return;
-  constexpr int PL = EB * T;  // elements per staging plane
+  constexpr int PL = EB * T;                 // longest group of the class
+  constexpr int PLS = bulk_plane<R>(PL);     // elements per staging plane
   __shared__ int list[T];
   __shared__ int wcount[T / 32];
   __shared__ BigRed<T> red;
   __shared__ BigRedF<T> redf;
-  extern __shared__ __align__(16) unsigned char big_stage_raw[];
-  R* const stage = reinterpret_cast<R*>(big_stage_raw);  // three planes of PL elements: q | xk | sj
+  __shared__ __align__(8) uint64_t bar;
+  extern __shared__ __align__(128) unsigned char big_stage_raw[];
+  R* const stage = reinterpret_cast<R*>(big_stage_raw);  // three planes of PLS elements: q | xk | sj
   const int t = threadIdx.x;
+  if (t == 0) mbar_init(&bar, 1);
+  __syncthreads();
+  uint32_t phase = 0;
   int parity = 0, parity_f = 0;
   for (long long g0 = (long long)blockIdx.x * T; g0 < ngroups; g0 += (long long)gridDim.x * T) {
     // index-ordered list of this chunk's groups of LO+1 .. EB T elements
@@ -1786,9 +1775,9 @@ __global__ void __launch_bounds__(T, TPS / T)
       }
       bool wrote;
       if (e - b <= EA * T)
-        wrote = binf_big_group<R, EA, T, PL, SJP>(y, xk, sj, q, b, e, lam, sigma, delta, by_sigma, red, redf, parity, parity_f, stage);
+        wrote = binf_big_group<R, EA, T, PLS>(y, xk, sj, q, b, e, lam, sigma, delta, by_sigma, red, redf, parity, parity_f, stage, &bar, phase);
       else
-        wrote = binf_big_group<R, EB, T, PL, SJP>(y, xk, sj, q, b, e, lam, sigma, delta, by_sigma, red, redf, parity, parity_f, stage);
+        wrote = binf_big_group<R, EB, T, PLS>(y, xk, sj, q, b, e, lam, sigma, delta, by_sigma, red, redf, parity, parity_f, stage, &bar, phase);
       if (wrote && t == 0) done[g] = 1;
 #ifdef SPX_GROUP_STATS
       if (t == 0) atomicAdd(&g_stat_big[wrote ? 1 : 2], 1ull);
@@ -2335,48 +2324,75 @@ static int32_t prox_group(spx_ctx* ctx, bool binf, int64_t n, R* y, const R* xk,
       if (sigma_ok && !(overlaps(xk) || overlaps(sj) || overlaps(q)) && std::getenv("SPX_BINF_NOBIG") == nullptr) {
         done = (unsigned char*)ctx->d_scratch + done_off;
         SPX_CUDA(cudaMemsetAsync(done, 0, (size_t)ngroups, ctx->stream));
-        if (std::getenv("SPX_BINF_NOSMALL") == nullptr) {
-          const int grids = group_grid(ctx, ngroups, (const void*)group_l2binf_small_fast_kernel<R>);
-          group_l2binf_small_fast_kernel<R><<<grids, kGroupThreads, 0, ctx->stream>>>(
-              y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, (R)sigma, (R)delta, by_sigma,
-              uni ? uniform_flag : nullptr, done);
-          ctx->launches++;
+        // a class the layout is known not to hold is not launched (whatever is not marked done goes to the bracketing
+        // search anyway, so the census is only a hint here as well)
+        const unsigned classes = census_classes(ctx, offs, ngroups, n);
+        // With CTA-per-group classes present the fast kernels run CONCURRENTLY (short groups and the 128-thread classes on
+        // the context's side streams, fork / join by events as in launch_group_l2), each with one short-lived CTA per
+        // chunk of groups instead of a persistent grid: the block scheduler then mixes CTAs of the kernels on an SM, and
+        // the barrier-separated phases of one kernel leave their idle issue slots to the others.
+        const bool fork = classes != 0u && std::getenv("SPX_BINF_SERIAL") == nullptr;
+        cudaStream_t s_small = ctx->stream, s_mid = ctx->stream;
+        if (fork) {
+          for (int i = 0; i < 2; ++i)
+            if (!ctx->pipe_streams[i]) SPX_CUDA(cudaStreamCreateWithFlags(&ctx->pipe_streams[i], cudaStreamNonBlocking));
+          for (int i = 13; i < 16; ++i)
+            if (!ctx->pipe_events[i]) SPX_CUDA(cudaEventCreateWithFlags(&ctx->pipe_events[i], cudaEventDisableTiming));
+          s_mid = ctx->pipe_streams[0];
+          s_small = ctx->pipe_streams[1];
+          SPX_CUDA(cudaEventRecord(ctx->pipe_events[13], ctx->stream));
+          SPX_CUDA(cudaStreamWaitEvent(s_mid, ctx->pipe_events[13], 0));
+          SPX_CUDA(cudaStreamWaitEvent(s_small, ctx->pipe_events[13], 0));
         }
-        auto launch_class = [&](auto kern, int threads, size_t stage_bytes) -> int32_t {
+        auto launch_class = [&](auto kern, int threads, size_t stage_bytes, cudaStream_t stream) -> int32_t {
           int per_sm = 1;
           SPX_CUDA(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes));
           if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)kern, threads, stage_bytes) != cudaSuccess ||
               per_sm < 1)
             per_sm = 1;
+          const int64_t chunks = (ngroups + threads - 1) / threads;
           const int grid = (int)std::max<int64_t>(
-              1, std::min<int64_t>((ngroups + threads - 1) / threads, (int64_t)ctx->sm_count * per_sm));
-          kern<<<grid, threads, stage_bytes, ctx->stream>>>(y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, (R)sigma,
-                                                           (R)delta, by_sigma, uni ? uniform_flag : nullptr, done);
+              1, std::min<int64_t>(chunks, fork ? (int64_t)(1 << 20) : (int64_t)ctx->sm_count * per_sm));
+          kern<<<grid, threads, stage_bytes, stream>>>(y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, (R)sigma,
+                                                      (R)delta, by_sigma, uni ? uniform_flag : nullptr, done);
           ctx->launches++;
           return SPX_OK;
         };
-        // a class the layout is known not to hold is not launched (whatever is not marked done goes to the bracketing
-        // search anyway, so the census is only a hint here as well)
-        const unsigned classes = census_classes(ctx, offs, ngroups, n);
         int32_t stc = SPX_OK;
         // (1024, 4096]: 256 threads x 8 or 16 elements, two CTAs per SM in 128 registers (measured at 2^28 Float64,
         // ragged layout: 2.8 ms; split into 512 x 8 and 256 x 8 at 64 registers and 1024 threads per SM: 3.4 ms;
-        // three CTAs per SM in 80 registers with sj read from global memory instead of staged -- the SJP = false
-        // form of the kernel -- 3.3 ms: more resident CTAs do not help this class).
+        // three CTAs per SM in 80 registers with sj read from global memory instead of staged: 3.3 ms -- more
+        // resident CTAs do not help this class).
         // (256, 1024]: two shapes of 128 threads, 8 and 4 elements, 64 registers (0.77 ms; one shape of 4 or 8
         // elements at 128 registers: 0.94 ms).
         if (classes & 2u) {
           stc = launch_class(group_l2binf_big_kernel<R, kBinfBigThreads, 1024, 8, 16, 512>, kBinfBigThreads,
-                             3 * (size_t)16 * kBinfBigThreads * sizeof(R));
+                             3 * (size_t)bulk_plane<R>(16 * kBinfBigThreads) * sizeof(R), ctx->stream);
           if (stc != SPX_OK) return stc;
         }
         if ((classes & 1u) && std::getenv("SPX_BINF_NOMID") == nullptr) {
           stc = launch_class(group_l2binf_big_kernel<R, kBinfMidThreads, 512, 8, 8, 1024>, kBinfMidThreads,
-                             3 * (size_t)8 * kBinfMidThreads * sizeof(R));
+                             3 * (size_t)bulk_plane<R>(8 * kBinfMidThreads) * sizeof(R), s_mid);
           if (stc != SPX_OK) return stc;
           stc = launch_class(group_l2binf_big_kernel<R, kBinfMidThreads, 256, 4, 4, 1024>, kBinfMidThreads,
-                             3 * (size_t)4 * kBinfMidThreads * sizeof(R));
+                             3 * (size_t)bulk_plane<R>(4 * kBinfMidThreads) * sizeof(R), s_mid);
           if (stc != SPX_OK) return stc;
+        }
+        // the short groups last: the class (1024, 4096] is the long pole and should get the SMs first
+        if (std::getenv("SPX_BINF_NOSMALL") == nullptr) {
+          const long long ntasks = (ngroups + kTask - 1) / kTask;
+          const int grids = fork ? (int)std::max<long long>(1, std::min<long long>((ntasks + 7) / 8, 1 << 20))
+                                 : group_grid(ctx, ngroups, (const void*)group_l2binf_small_fast_kernel<R>);
+          group_l2binf_small_fast_kernel<R><<<grids, kGroupThreads, 0, s_small>>>(
+              y, xk, sj, q, ngroups, (const long long*)offs, lambda_g, (R)sigma, (R)delta, by_sigma,
+              uni ? uniform_flag : nullptr, done);
+          ctx->launches++;
+        }
+        if (fork) {
+          SPX_CUDA(cudaEventRecord(ctx->pipe_events[14], s_mid));
+          SPX_CUDA(cudaEventRecord(ctx->pipe_events[15], s_small));
+          SPX_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->pipe_events[14], 0));
+          SPX_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->pipe_events[15], 0));
         }
       }
     }
