@@ -892,7 +892,8 @@ __global__ void __launch_bounds__(THREADS, MINB)
 
 // ------------------------------------------------- global multi-pass path ---
 // For one long vector: z is stashed in y (3R + 1W), every further digit costs
-// one read of y, the last pass reads y, xk, sj and writes y.
+// one read of y (until the selected bin is down to the elements it keeps: two such passes on random Float64 data), the
+// last pass reads y, xk, sj and writes y; the tie ranks of the last pass come from per-warp slices (no block barrier).
 struct GlobalSel {
   unsigned long long hist[kTrBins];  // 64-bit: the sharded form sums the histograms of every GPU
   unsigned long long prefix;
@@ -976,42 +977,47 @@ __global__ void __launch_bounds__(kPickThreads) topr_g_pick(int pass, GlobalSel*
   }
 }
 
-// per-block count of threshold-equal elements (block-contiguous slices, index order)
+// Tie ranks (lowest index first among the threshold-equal entries) need the number of such entries in front of every
+// element.  The vector is cut into one contiguous slice per WARP of the final pass (per_slice elements, a multiple of
+// 128): this kernel counts the threshold-equal entries of each slice, topr_g_scan turns the counts into exclusive
+// prefixes, and the final pass ranks inside a slice with ballots only -- no block barrier anywhere in it.
 template <class R>
-__global__ void __launch_bounds__(256) topr_g_eqcount(const R* y, long long n, long long per_block,
-                                                      const GlobalSel* st, long long* block_eq) {
+__global__ void __launch_bounds__(256) topr_g_eqcount(const R* y, long long n, long long per_slice,
+                                                      const GlobalSel* st, long long* slice_eq) {
   using KT = KeyTraits<R>;
   using K = typename KT::K;
+  const int lane = threadIdx.x & 31;
+  const long long slice = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (st->done) {
-    if (threadIdx.x == 0) block_eq[blockIdx.x] = 0;
+    if (lane == 0) slice_eq[slice] = 0;
     return;
   }
-  const long long b = (long long)blockIdx.x * per_block;
-  const long long e = b + per_block < n ? b + per_block : n;
+  const long long b = slice * per_slice;
+  const long long e = b + per_slice < n ? b + per_slice : n;
   const K prefix = (K)st->prefix;
+  const int shift = st->shift;
   long long c = 0;
-  for (long long i = b + threadIdx.x; i < e; i += 256) c += (KT::key(y[i]) >> st->shift) == prefix;
-  __shared__ long long shc[8];
+#pragma unroll 4
+  for (long long i = b + lane; i < e; i += 32) c += (KT::key(y[i]) >> shift) == prefix;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-  if ((threadIdx.x & 31) == 0) shc[threadIdx.x >> 5] = c;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    long long s = 0;
-    for (int w = 0; w < 8; ++w) s += shc[w];
-    block_eq[blockIdx.x] = s;
-  }
+  if (lane == 0) slice_eq[slice] = c;
 }
-__global__ void topr_g_scan(long long* block_eq, int nblocks, GlobalSel* st) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    long long run = 0;
-    for (int i = 0; i < nblocks; ++i) {
-      long long c = block_eq[i];
-      block_eq[i] = run;
-      run += c;
-    }
-    st->eq_total = run;
+// exclusive prefix sums of the slice counts (one block of 1024 threads, consecutive runs of slices per thread)
+__global__ void __launch_bounds__(1024) topr_g_scan(long long* slice_eq, int nslices, GlobalSel* st) {
+  __shared__ long long ws[40];
+  const int per = (nslices + 1023) / 1024;
+  const int b = threadIdx.x * per, e = min(b + per, nslices);
+  long long local = 0;
+  for (int i = b; i < e; ++i) local += slice_eq[i];
+  long long total;
+  long long run = block_excl_scan64<1024>(local, ws, &total);
+  for (int i = b; i < e; ++i) {
+    const long long c = slice_eq[i];
+    slice_eq[i] = run;
+    run += c;
   }
+  if (threadIdx.x == 0) st->eq_total = total;
 }
 
 // phase 0: slots[rr] = (rr == rank) ? this shard's threshold-equal count : 0;  phase 1 (after the sum over ranks):
@@ -1027,57 +1033,55 @@ __global__ void topr_g_rank_slot(long long* slots, int world, int rank, GlobalSe
 }
 
 template <class R, bool BINF>
-__global__ void __launch_bounds__(256) topr_g_final(R* y, const R* xk, const R* sj, long long n, long long per_block,
-                                                    const GlobalSel* st, const long long* block_eq, R delta,
+__global__ void __launch_bounds__(256) topr_g_final(R* y, const R* xk, const R* sj, long long n, long long per_slice,
+                                                    const GlobalSel* st, const long long* slice_eq, R delta,
                                                     int mode /*0 select, 1 keep all, 2 keep none*/) {
   using KT = KeyTraits<R>;
   using K = typename KT::K;
-  __shared__ int wsum[8];
-  const long long b = (long long)blockIdx.x * per_block;
-  const long long e = b + per_block < n ? b + per_block : n;
+  constexpr int U = 4;  // 32-element chunks per trip: 3 U independent loads per lane in flight
+  const int lane = threadIdx.x & 31;
+  const long long slice = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const long long b = slice * per_slice;
+  const long long e = b + per_slice < n ? b + per_slice : n;
   const K prefix = (K)st->prefix;
   const int shift = st->shift;
   const bool all_bin = st->done != 0;
   const long long need = st->need;
-  long long run = mode == 0 ? st->eq_base + block_eq[blockIdx.x] : 0;
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  for (long long base = b; base < e; base += 256) {
-    const long long i = base + threadIdx.x;
-    R z = R(0), xs = R(0);
-    bool eq = false, keep = false;
-    if (i < e) {
-      z = y[i];
-      xs = xk[i] + sj[i];
-      if (mode == 1) keep = true;
-      else if (mode == 0) {
-        const K kp = KT::key(z) >> shift;
+  long long run = (mode == 0 && !all_bin) ? st->eq_base + slice_eq[slice] : 0;  // threshold-equal entries in front
+  for (long long base = b; base < e; base += 32 * U) {
+    R z[U], xs[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long i = base + u * 32 + lane;
+      z[u] = R(0);
+      xs[u] = R(0);
+      if (i < e) {
+        z[u] = y[i];
+        xs[u] = xk[i] + sj[i];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long i = base + u * 32 + lane;
+      bool keep = mode == 1;
+      if (mode == 0) {
+        const K kp = KT::key(z[u]) >> shift;
+        const bool eq = i < e && kp == prefix;
         keep = kp > prefix;
-        eq = kp == prefix;
-      }
-    }
-    if (mode == 0) {
-      if (all_bin) {
-        keep = keep || eq;
-      } else {
-        const unsigned bal = __ballot_sync(0xffffffffu, eq);
-        if (lane == 0) wsum[w] = __popc(bal);
-        __syncthreads();
-        long long off = run;
-        int tot = 0;
-        for (int ww = 0; ww < 8; ++ww) {
-          if (ww < w) off += wsum[ww];
-          tot += wsum[ww];
+        if (all_bin) {
+          keep = keep || eq;
+        } else {  // lowest index first: rank among the threshold-equal entries of the shard(s)
+          const unsigned bal = __ballot_sync(0xffffffffu, eq);
+          const long long rank = run + __popc(bal & ((1u << lane) - 1u));
+          keep = keep || (eq && rank < need);
+          run += __popc(bal);
         }
-        const long long rank = off + __popc(bal & ((1u << lane) - 1u));
-        if (eq && rank < need) keep = true;
-        run += tot;
-        __syncthreads();
       }
-    }
-    if (i < e) {
-      R v = (keep ? z : R(0)) - xs;
-      if (BINF) v = jl_min(jl_max(v, -delta), delta);
-      y[i] = v;
+      if (i < e) {
+        R v = (keep ? z[u] : R(0)) - xs[u];
+        if (BINF) v = jl_min(jl_max(v, -delta), delta);
+        y[i] = v;
+      }
     }
   }
 }
@@ -1094,7 +1098,8 @@ static int32_t topr_global(spx_ctx* ctx, int64_t n, R* y, const R* xk, const R* 
   using KT = KeyTraits<R>;
   if (n_global < 0) n_global = n;
   const int nblk = ctx->sm_count * 8;
-  int32_t stt = ensure_scratch(ctx, sizeof(GlobalSel) + sizeof(long long) * (size_t)(nblk + 1 + 64));
+  const int nslices = nblk * 8;  // one contiguous slice of the vector per warp of the counting / final passes
+  int32_t stt = ensure_scratch(ctx, sizeof(GlobalSel) + sizeof(long long) * (size_t)(nslices + 1 + 64));
   if (stt != SPX_OK) return stt;
   GlobalSel* st = (GlobalSel*)ctx->d_scratch;
   long long* block_eq = (long long*)((char*)ctx->d_scratch + sizeof(GlobalSel));
@@ -1131,7 +1136,7 @@ static int32_t topr_global(spx_ctx* ctx, int64_t n, R* y, const R* xk, const R* 
     topr_g_stash<R><<<nblk, 256, 0, ctx->stream>>>(y, xk, sj, q, n, st);
     ctx->launches++;
   }
-  const long long per_block = (n + nblk - 1) / nblk;
+  const long long per_slice = ((n + nslices - 1) / nslices + 127) / 128 * 128;
   if (mode == 0) {
     for (int pass = 0; pass < KT::NPASS; ++pass) {
       if (pass > 0 && n > 0) {
@@ -1143,12 +1148,12 @@ static int32_t topr_global(spx_ctx* ctx, int64_t n, R* y, const R* xk, const R* 
       topr_g_pick<R><<<1, kPickThreads, 0, ctx->stream>>>(pass, st);
       ctx->launches++;
     }
-    topr_g_eqcount<R><<<nblk, 256, 0, ctx->stream>>>(y, n, per_block, st, block_eq);
-    topr_g_scan<<<1, 32, 0, ctx->stream>>>(block_eq, nblk, st);
+    topr_g_eqcount<R><<<nblk, 256, 0, ctx->stream>>>(y, n, per_slice, st, block_eq);
+    topr_g_scan<<<1, 1024, 0, ctx->stream>>>(block_eq, nslices, st);
     ctx->launches += 2;
     if (lib_comm) {
       // exclusive prefix over ranks of the threshold-equal counts, on the device: one slot per rank, summed
-      long long* slots = block_eq + nblk + 1;
+      long long* slots = block_eq + nslices + 1;
       topr_g_rank_slot<<<1, 64, 0, ctx->stream>>>(slots, world, rank, st, 0);
       int32_t st2 = comm_allreduce_raw(ctx, slots, (size_t)world, kNcclInt64, kNcclSum);
       if (st2 != SPX_OK) return st2;
@@ -1174,9 +1179,9 @@ static int32_t topr_global(spx_ctx* ctx, int64_t n, R* y, const R* xk, const R* 
   }
   if (n > 0) {
     if (binf)
-      topr_g_final<R, true><<<nblk, 256, 0, ctx->stream>>>(y, xk, sj, n, per_block, st, block_eq, delta, mode);
+      topr_g_final<R, true><<<nblk, 256, 0, ctx->stream>>>(y, xk, sj, n, per_slice, st, block_eq, delta, mode);
     else
-      topr_g_final<R, false><<<nblk, 256, 0, ctx->stream>>>(y, xk, sj, n, per_block, st, block_eq, delta, mode);
+      topr_g_final<R, false><<<nblk, 256, 0, ctx->stream>>>(y, xk, sj, n, per_slice, st, block_eq, delta, mode);
     ctx->launches++;
   }
   SPX_CUDA(cudaGetLastError());
