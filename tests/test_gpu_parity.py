@@ -573,9 +573,11 @@ def test_indballl0_bit_exact(dt, n, r, binf):
 
 
 @pytest.mark.parametrize("dt", DT)
-@pytest.mark.parametrize("n,r", [(4096, 300), (70_001, 1024), (200_000, 4321)])
+@pytest.mark.parametrize("n,r", [(4096, 300), (70_001, 1024), (200_000, 4321), (3_000_017, 1_234_567)])
 def test_indballl0_ties_keep_lowest_index(dt, n, r):
     # magnitudes quantised to 1/64: massive ties at the threshold (SURVEY.md §8d tie-stress)
+    # (the last case: the multi-pass global path with thousands of threshold-equal entries spread over every
+    # per-warp slice of its final pass)
     xk = np.zeros(n, dt); sj = np.zeros(n, dt)
     q = (np.round(orc.uniform(n, 2, dt, 4.0, -2.0) * 64) / 64).astype(dt)
     psi = sp.shifted(sp.IndBallL0(r), T(xk))
