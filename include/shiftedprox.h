@@ -352,6 +352,16 @@ typedef struct spx_box_job_f32 {
   int32_t spx_step_box_##SUF(spx_ctx* ctx, int32_t op, int64_t n, R* s, R* xsy, const R* xk,     \
                              const R* sj, const R* grad, const spx_bound* l, const spx_bound* u, \
                              const spx_sel* sel, double lambda, double nu, double* out3_host);   \
+  /* The step around a prox! that is not one streaming pass (groups, top-r, ShiftedNormL1B2): the    */ \
+  /* caller's sweeps as two passes around the operator's own entry point --                          */ \
+  /*   spx_step_pre:   q = (-nu) .* grad (rounded to R), written where s will be;                    */ \
+  /*   the type's spx_prox_* IN PLACE (y = q = s, sigma = nu, its psi_out / value entry gives ψ(s)); */ \
+  /*   spx_step_post:  xsy = (xk + sj) + s (xsy may be NULL), out2_host = {Σ s², Σ grad·s} (Float64; */ \
+  /*   all-reduced like every folded reduction when the context reduces scalars).  sj == NULL: zeros. */ \
+  /* s must not alias grad.  spx_step_post synchronises.                                             */ \
+  int32_t spx_step_pre_##SUF(spx_ctx* ctx, int64_t n, R* q, const R* grad, double nu);               \
+  int32_t spx_step_post_##SUF(spx_ctx* ctx, int64_t n, R* xsy, const R* xk, const R* sj, const R* s, \
+                              const R* grad, double* out2_host);                                     \
   /* ------------------------------ host-buffer entry points (end-to-end path) */              \
   /* Box prox!/iprox! with every vector in HOST memory (pinned for full speed): chunked, */     \
   /* H2D / kernel / D2H overlapped on three streams.  op: 0 L1Box, 1 L0Box, 2 LhalfBox; */      \

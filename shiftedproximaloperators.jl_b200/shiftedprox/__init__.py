@@ -266,7 +266,22 @@ class ShiftedProximableFunction:
         raise NotImplementedError(f"iprox! is not defined for {type(self).__name__}")
 
     def step_(self, s, grad, nu, xsy=None):
-        raise NotImplementedError(f"the fused solver step is not defined for {type(self).__name__}")
+        """The solver step for the types whose prox! is not one streaming pass (groups, top-r, ShiftedNormL1B2): the
+        caller's sweeps as two passes around the type's own prox! -- spx_step_pre_* writes q = -ν∇f where s will be,
+        prox!(s, ψ, s, ν) runs in place with ψ(s) out of its own pass (or the type's ψ(y) entry), spx_step_post_* gives
+        xsy = xk + sj + s, Σs² and Σ∇f·s in one pass.  Same results as the separate sweeps, bit for bit for s and xsy.
+        The separable and Box types override this with the single-pass form."""
+        self._check(s, grad, ("s", "grad"))
+        if xsy is not None:
+            _vec(xsy, self.xk, "xsy")
+        if s.data_ptr() == grad.data_ptr():
+            raise ValueError("step_: s must not alias grad")
+        self._call("step_pre", C.c_int64(self.n), _p(s), _p(grad), C.c_double(nu))
+        _, val = self.prox_(s, s, nu, want_value=True)
+        out = (C.c_double * 2)()
+        sj = self.sj if self.shifted_twice else None
+        self._call("step_post", C.c_int64(self.n), _p(xsy), _p(self.xk), _p(sj), _p(s), _p(grad), out)
+        return s, StepResult(val, math.sqrt(out[0]), out[1])
 
     def _step_sep(self, s, grad, nu, xsy):
         # spx_step_sep_*: q = -ν∇f, prox!, ψ(s), xk+sj+s, Σs², Σ∇f·s in the one pass of the prox!
@@ -770,8 +785,9 @@ def step_(s, psi, grad, nu, xsy=None):
 
         q = -ν .* ∇f;  prox!(s, ψ, q, ν);  xsy .= xk .+ sj .+ s (if given);  ψ(s);  ‖s‖₂;  ∇f's
 
-    Returns (s, StepResult(psi, snorm, gdots)).  `s` is bit-identical to prox_(s, ψ, -ν*grad, ν).  Defined for
-    ShiftedNormL1 / L0 / RootNormLhalf and their Box / BInf forms."""
+    Returns (s, StepResult(psi, snorm, gdots)).  `s` is bit-identical to prox_(s, ψ, -ν*grad, ν).  One pass for
+    ShiftedNormL1 / L0 / RootNormLhalf and their Box / BInf forms; for the group, top-r and L1B2 types the sweeps are
+    two passes around the type's own prox! (ShiftedProximableFunction.step_)."""
     return psi.step_(s, grad, nu, xsy)
 
 

@@ -140,3 +140,62 @@ def test_step_in_place(dt):
     _, res = sp.step_(tg, psi, tg, 0.25, xsy=txk)
     assert np.array_equal(N(tg), rs) and np.array_equal(N(txk), rxsy)
     assert res.psi == pytest.approx(rpsi, rel=1e-5) and res.snorm == pytest.approx(rsn) and res.gdots == pytest.approx(rgd)
+
+
+# ---- the step around a prox! that is not one streaming pass (spx_step_pre_*, the type's prox! in place, spx_step_post_*)
+def _composed_cases(dt, n):
+    from test_gpu_parity import ragged_offsets
+
+    xk, sj, grad = inputs(n, dt)
+    offs = ragged_offsets(120, 1500)
+    offs = offs[offs <= n]
+    if offs[-1] != n:
+        offs = np.concatenate([offs, [n]])
+    lam_g = (dt(0.5) + orc.uniform(len(offs) - 1, 12, dt)).astype(dt)
+    hg = sp.GroupNormL2(T(lam_g), None, offsets=T(offs))
+    y0 = orc.prox_l1b2(xk, sj, (dt(-0.3) * grad).astype(dt), 1.0, 0.3, 1e30)
+    full = float(np.linalg.norm((y0 + sj).astype(np.float64)))
+    return xk, sj, grad, offs, lam_g, {
+        "groupl2": (sp.shifted(sp.shifted(hg, T(xk)), T(sj)),
+                    lambda s: orc.value_groupl2(xk, sj, s, offs, lam_g)),
+        "groupl2binf": (sp.shifted(sp.shifted(hg, T(xk), 0.5, sp.NormLinf(1.0)), T(sj)),
+                        lambda s: orc.value_binf("groupl2", xk, sj, s, 0.5, offs=offs, lam_g=lam_g)),
+        "l1b2": (sp.shifted(sp.shifted(sp.NormL1(1.0), T(xk), 0.5 * full, sp.NormL2(1.0)), T(sj)),
+                 lambda s: orc.value_l1b2(xk, sj, s, 1.0, 0.5 * full)),
+        "indballl0": (sp.shifted(sp.shifted(sp.IndBallL0(777), T(xk)), T(sj)),
+                      lambda s: orc.value_plain("indballl0", xk, sj, s, r=777)),
+        "indballl0binf": (sp.shifted(sp.shifted(sp.IndBallL0(777), T(xk), 1.0, sp.NormLinf(1.0)), T(sj)),
+                          lambda s: orc.value_binf("indballl0", xk, sj, s, 1.0, r=777)),
+    }
+
+
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("kind", ["groupl2", "groupl2binf", "l1b2", "indballl0", "indballl0binf"])
+def test_step_composed_types(dt, kind):
+    """step_ of the group, top-r and L1B2 types: s bit-identical to the stand-alone prox! of q = -ν∇f, xsy bit-identical
+    to (xk + sj) + s, ψ(s) equal to the type's own ψ(s) and to the oracle's value at that s, ‖s‖ and ∇f's against
+    Float64 sums of the result."""
+    n, nu = 60_013, 0.3
+    xk, sj, grad, offs, lam_g, cases = _composed_cases(dt, n)
+    psi, oracle_value = cases[kind]
+    s = torch.empty(n, dtype=T(grad).dtype, device=DEV)
+    xsy = torch.empty_like(s)
+    out, res = sp.step_(s, psi, T(grad), nu, xsy=xsy)
+    assert out is s
+    q = (dt(-dt(nu)) * grad).astype(dt)
+    y = torch.empty_like(s)
+    sp.prox_(y, psi, T(q), nu)
+    assert np.array_equal(N(s), N(y), equal_nan=True)
+    assert np.array_equal(N(xsy), ((xk + sj) + N(s)).astype(dt))
+    gs = N(s)
+    g64, s64 = grad.astype(np.float64), gs.astype(np.float64)
+    ref_psi = oracle_value(gs)
+    scalars_close(res, ref_psi, float(np.sqrt(np.sum(s64 * s64))), float(np.sum(g64 * s64)), grad, gs, dt)
+    assert res.psi == pytest.approx(psi(s), rel=1e-12 if dt == np.float64 else 1e-6, abs=1e-300)
+    # xsy is optional; s must not be the gradient itself
+    s2 = torch.empty_like(s)
+    _, res2 = sp.step_(s2, psi, T(grad), nu)
+    assert torch.equal(s2, s) and tuple(res2) == tuple(res)
+    tg = T(grad)
+    with pytest.raises(ValueError):
+        sp.step_(tg, psi, tg, nu)

@@ -166,6 +166,11 @@ def main():
         psi = sp.shifted(sp.shifted(h, xk), sj)
         timeit(f"prox_groupl2_{gname}", lambda psi=psi: sp.prox_(y, psi, q, 0.3), 4 * R, note=f"{ng} groups")
         timeit(f"value_groupl2_{gname}", lambda psi=psi: psi(y), 3 * R)
+        if gname == "g64" and re.search(args.only, "step_groupl2_g64"):
+            xsy_g = torch.empty_like(y)
+            timeit("step_groupl2_g64", lambda psi=psi: sp.step_(y, psi, q, 0.3, xsy=xsy_g), 5 * R,
+                   note="pre (1R+1W) + prox! in place with fused psi + post (4R+1W); alg. bytes = 3 reads + 2 writes")
+            del xsy_g
         psib = sp.shifted(sp.shifted(h, xk, 0.5, sp.NormLinf(1.0)), sj)
         timeit(f"prox_groupl2binf_{gname}", lambda psi=psib: sp.prox_(y, psi, q, 0.3), 4 * R, note=f"{ng} groups")
         if gname == "g64":  # σλ_g >> ||sol_g||: the regime of a sparse solution (root next to the pole of c(n) at σλ)
