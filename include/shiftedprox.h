@@ -360,6 +360,13 @@ typedef struct spx_box_job_f32 {
   /*   all-reduced like every folded reduction when the context reduces scalars).  sj == NULL: zeros. */ \
   /* s must not alias grad.  spx_step_post synchronises.                                             */ \
   int32_t spx_step_pre_##SUF(spx_ctx* ctx, int64_t n, R* q, const R* grad, double nu);               \
+  /* The whole step of ShiftedGroupNormL2 (shiftedGroupNormL2.jl:52-79) in one call: ONE pass when   */ \
+  /* every group of a validated layout holds <= 256 elements (spx_group_validate_offsets), the three */ \
+  /* calls above otherwise.  out3_host as for spx_step_sep.  sj must be given (zeros when ψ is       */ \
+  /* shifted once); s must not alias grad.                                                            */ \
+  int32_t spx_step_groupl2_##SUF(spx_ctx* ctx, int64_t n, R* s, R* xsy, const R* xk, const R* sj,    \
+                                 const R* grad, int64_t ngroups, const int64_t* offs,                \
+                                 const R* lambda_g, double nu, double* out3_host);                   \
   int32_t spx_step_post_##SUF(spx_ctx* ctx, int64_t n, R* xsy, const R* xk, const R* sj, const R* s, \
                               const R* grad, double* out2_host);                                     \
   /* ------------------------------ host-buffer entry points (end-to-end path) */              \

@@ -87,7 +87,7 @@ struct spx_ctx {
   struct GroupCensus {
     const void* offs = nullptr;
     long long ngroups = -1, n = -1;
-    unsigned classes = 0;  // bit 0: some group of 257..1024 elements, bit 1: of 1025..4096
+    unsigned classes = 0;  // bit 0: some group of 257..1024 elements, bit 1: of 1025..4096, bit 2: longer ones
   } census[8];
   int census_next = 0;
 };
@@ -275,6 +275,10 @@ int32_t make_sel(const spx_sel* s, int64_t n, DevSel* out);
 // fold `nblocks` partials (slot stride `stride`, `nslot` independent slots) into
 // ctx->d_result[slot], copy to the pinned mirror, synchronise
 int32_t finalize_partials(spx_ctx* ctx, int nblocks, int nslot, bool bad_is_min);
+// the two passes of the solver step around a prox! that is not one streaming pass (spx_step.cu)
+template <class R> int32_t step_pre(spx_ctx* ctx, int64_t n, R* q, const R* grad, double nu);
+template <class R>
+int32_t step_post(spx_ctx* ctx, int64_t n, R* xsy, const R* xk, const R* sj, const R* s, const R* grad, double* out2);
 // spx_comm.cu: is the context in "scalars are global" mode; all-reduce ctx->d_result[0..nslot) on ctx->stream
 bool comm_active(const spx_ctx* ctx);
 int32_t comm_neutral_result(spx_ctx* ctx, int nslot);

@@ -2058,8 +2058,14 @@ static int group_grid(spx_ctx* ctx, int64_t ngroups, const void* kernel) {
 // classes to launch for this layout: what spx_group_validate_offsets recorded, both when the layout is unknown
 static unsigned census_classes(const spx_ctx* ctx, const void* offs, int64_t ngroups, int64_t n) {
   for (const auto& c : ctx->census)
-    if (c.offs == offs && c.ngroups == (long long)ngroups && c.n == (long long)n) return c.classes;
+    if (c.offs == offs && c.ngroups == (long long)ngroups && c.n == (long long)n) return c.classes & 3u;
   return 3u;
+}
+// a validated layout whose groups all have <= 256 elements (the packed warp rounds hold every group)
+static bool census_short_only(const spx_ctx* ctx, const void* offs, int64_t ngroups, int64_t n) {
+  for (const auto& c : ctx->census)
+    if (c.offs == offs && c.ngroups == (long long)ngroups && c.n == (long long)n) return c.classes == 0u;
+  return false;
 }
 
 #ifndef SPX_L2_MID_STAGES
@@ -2416,6 +2422,140 @@ static int32_t prox_group(spx_ctx* ctx, bool binf, int64_t n, R* y, const R* xk,
   return SPX_OK;
 }
 
+// ---- the solver step of ShiftedGroupNormL2 (spx_step.cu for the separable types) ---------------
+//     q = (-ν) ∇f;  prox!(s, ψ, q, ν);  xsy = (xk + sj) + s;  ψ(s);  Σ s²;  Σ ∇f·s
+// Layouts whose groups all hold <= 256 elements (the C4 shape: the census of spx_group_validate_offsets says so) run it
+// in the ONE pass of the packed warp rounds: ∇f takes the place of q on the load (q = (-ν)∇f rounded to R, as the
+// caller's broadcast would), the store loop also writes xsy and folds the two sums next to the ψ term.  s is bit for
+// bit what prox! writes.  A group longer than that (a stale census) raises the flag and the call is redone in the
+// composed form; every other layout takes the composed form at once: spx_step_pre, prox! in place, spx_step_post.
+// two CTAs per SM (125 registers in Float64: sol, ∇f and xk + sj of 8 elements per lane); three spill and measure the
+// same (2.60 vs 2.54 ms at 2^28 Float64)
+#ifndef SPX_GSTEP_MINB
+#define SPX_GSTEP_MINB 2
+#endif
+template <class R>
+__global__ void __launch_bounds__(kGroupThreads, SPX_GSTEP_MINB)
+    group_l2_step_kernel(R* s, R* xsy, const R* xk, const R* sj, const R* grad, long long ngroups,
+                         const long long* __restrict__ offs, const R* __restrict__ lambda_g, R sigma, R mnu,
+                         Partial* __restrict__ partials) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * kGroupThreads + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * kGroupThreads) >> 5;
+  const long long ntasks = (ngroups + kTask - 1) / kTask;
+  double psi = 0.0, ss2 = 0.0, dot = 0.0;
+  long long bad = -1;
+  for (long long task = warp; task < ntasks; task += nwarps) {
+    const long long g0 = task * kTask;
+    const TaskHead th = load_task(offs, g0, ngroups, lane);
+    const R lam_lane = lane < th.cnt ? lambda_g[g0 + lane] : R(0);
+    int pos = 0;
+    while (pos < th.cnt) {
+      const int k = plan_round(th.le, pos);
+      if (k < 0) {  // a group of more than 256 elements: not this kernel's (the host redoes the call)
+        bad = 1;
+        pos += 1;
+        continue;
+      }
+      const int L = 1 << k, sub = lane & (L - 1), gi = pos + (lane >> k);
+      const long long lo = __shfl_sync(0xffffffffu, th.lo, gi & 31), hi = __shfl_sync(0xffffffffu, th.hi, gi & 31);
+      const R lam = __shfl_sync(0xffffffffu, lam_lane, gi & 31);
+      const bool valid = gi < th.cnt;
+      const long long b = valid ? lo : 0, e = valid ? hi : 0;
+      R sol[kEPL], g[kEPL], xs[kEPL];
+#pragma unroll
+      for (int j = 0; j < kEPL; ++j) {
+        const long long i = b + (long long)j * L + sub;
+        sol[j] = R(0);
+        g[j] = R(0);
+        xs[j] = R(0);
+        if (i < e) {
+          const R xi = ldv(xk + i), si = ldv(sj + i), gj = ldv(grad + i);
+          const R qi = mnu * gj;     // q = -ν ∇f
+          sol[j] = (qi + xi) + si;   // shiftedGroupNormL2.jl:65
+          xs[j] = xi + si;
+          g[j] = gj;
+        }
+      }
+      double ss = 0.0;
+#pragma unroll
+      for (int j = 0; j < kEPL; ++j) ss += (double)sol[j] * (double)sol[j];
+      ss = sub_sum(ss, L);
+      const R snorm = (R)sqrt_fast(ss);
+      const R alpha = jl_max(R(1) - sigma * lam / snorm, R(0));
+      double vv = 0.0;
+#pragma unroll
+      for (int j = 0; j < kEPL; ++j) {
+        const long long i = b + (long long)j * L + sub;
+        if (i < e) {
+          const R o = (snorm == R(0) ? R(0) : alpha * sol[j]) - xs[j];  // :70-77
+          stv(s + i, o);
+          const R v = xs[j] + o;  // ψ's own argument (ShiftedProximalOperators.jl:52)
+          if (xsy != nullptr) stv(xsy + i, v);
+          vv += (double)v * (double)v;
+          ss2 = __fma_rn((double)o, (double)o, ss2);
+          dot = __fma_rn((double)g[j], (double)o, dot);
+        }
+      }
+      vv = sub_sum(vv, L);
+      if (valid && sub == 0) psi += (double)(lam * (R)sqrt_fast(vv));  // λ_g ‖v_g‖  groupNormL2.jl:36
+      pos += 32 >> k;
+    }
+  }
+  Partial p;
+  p.s = psi;
+  p.s2 = ss2;
+  p.bad = bad;
+  p = block_fold<kGroupThreads>(p);
+  Partial p2;
+  p2.s = dot;
+  p2.s2 = 0.0;
+  p2.bad = -1;
+  p2 = block_fold<kGroupThreads>(p2);
+  if (threadIdx.x == 0) {
+    partials[blockIdx.x] = p;
+    partials[gridDim.x + blockIdx.x] = p2;
+  }
+}
+
+template <class R>
+static int32_t step_groupl2(spx_ctx* ctx, int64_t n, R* s, R* xsy, const R* xk, const R* sj, const R* grad,
+                            int64_t ngroups, const int64_t* offs, const R* lambda_g, double nu, double* out3) {
+  SPX_REQUIRE(ctx != nullptr, "null context");
+  SPX_REQUIRE(n >= 0 && ngroups >= 0, "negative size");
+  SPX_REQUIRE(out3 != nullptr, "null result array");
+  SPX_REQUIRE(ngroups == 0 || (s && xk && sj && grad && offs && lambda_g), "null device vector");
+  SPX_REQUIRE(s != grad || n == 0, "s must not alias grad");
+  DeviceGuard g(ctx->device);
+  out3[0] = out3[1] = out3[2] = 0.0;
+  if (ngroups == 0 || n == 0) return SPX_OK;
+  if (ngroups > 1 && census_short_only(ctx, offs, ngroups, n) && std::getenv("SPX_STEP_COMPOSED") == nullptr) {
+    const int grid = std::min(group_grid(ctx, ngroups, (const void*)group_l2_step_kernel<R>), kMaxPartials / 2);
+    group_l2_step_kernel<R><<<grid, kGroupThreads, 0, ctx->stream>>>(s, xsy, xk, sj, grad, ngroups, (const long long*)offs,
+                                                                    lambda_g, (R)nu, -(R)nu, ctx->d_partials);
+    ctx->launches++;
+    SPX_CUDA(cudaGetLastError());
+    int32_t st = finalize_partials(ctx, grid, 2, false);
+    if (st != SPX_OK) return st;
+    if (ctx->h_result[0].bad <= 0) {
+      out3[0] = (double)(R)ctx->h_result[0].s;
+      out3[1] = ctx->h_result[0].s2;
+      out3[2] = ctx->h_result[1].s;
+      return SPX_OK;
+    }  // else: the layout is not what the census recorded -- redo the call the long way
+  }
+  int32_t st = step_pre<R>(ctx, n, s, grad, nu);
+  if (st != SPX_OK) return st;
+  st = prox_group<R>(ctx, false, n, s, xk, sj, s, ngroups, offs, lambda_g, nu, 0.0, &out3[0]);
+  if (st != SPX_OK) return st;
+  double out2[2] = {0.0, 0.0};
+  st = step_post<R>(ctx, n, xsy, xk, sj, s, grad, out2);
+  if (st != SPX_OK) return st;
+  out3[1] = out2[0];
+  out3[2] = out2[1];
+  return SPX_OK;
+}
+
 }  // namespace spx
 
 using namespace spx;
@@ -2440,18 +2580,20 @@ extern "C" int32_t spx_debug_group_stats(unsigned long long* out2, int reset) {
 // 0, never decrease and end at n -- anything else would make the group kernels read and write out of bounds.
 __global__ void __launch_bounds__(256) group_validate_kernel(const long long* __restrict__ offs, long long ngroups,
                                                              long long n, unsigned* bad) {
-  bool b = false, mid = false, big = false;
+  bool b = false, mid = false, big = false, lng = false;
   for (long long g = (long long)blockIdx.x * 256 + threadIdx.x; g < ngroups; g += (long long)gridDim.x * 256) {
     const long long lo = offs[g], m = offs[g + 1] - lo;
     b = b || (m < 0) || (lo < 0);
     mid = mid || (m > kMidMin && m <= kBigMin);
     big = big || (m > kBigMin && m <= kBigMax);
+    lng = lng || (m > kBigMax);
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) b = b || (offs[0] != 0) || (offs[ngroups] != n);
   if (__syncthreads_or(b) && threadIdx.x == 0) bad[0] = 1u;
-  // the size classes present (bad[1] bit 0: 257..1024 elements, bit 1: 1025..4096), for the launch census
-  const int has_mid = __syncthreads_or(mid), has_big = __syncthreads_or(big);
-  if (threadIdx.x == 0 && (has_mid || has_big)) atomicOr(&bad[1], (has_mid ? 1u : 0u) | (has_big ? 2u : 0u));
+  // the size classes present (bad[1] bit 0: 257..1024 elements, bit 1: 1025..4096, bit 2: longer), for the census
+  const int has_mid = __syncthreads_or(mid), has_big = __syncthreads_or(big), has_lng = __syncthreads_or(lng);
+  if (threadIdx.x == 0 && (has_mid || has_big || has_lng))
+    atomicOr(&bad[1], (has_mid ? 1u : 0u) | (has_big ? 2u : 0u) | (has_lng ? 4u : 0u));
 }
 extern "C" int32_t spx_group_validate_offsets(spx_ctx* ctx, int64_t n, int64_t ngroups, const int64_t* offs) {
   SPX_REQUIRE(ctx != nullptr, "null context");
@@ -2480,7 +2622,7 @@ extern "C" int32_t spx_group_validate_offsets(spx_ctx* ctx, int64_t n, int64_t n
   slot.offs = (const void*)offs;
   slot.ngroups = (long long)ngroups;
   slot.n = (long long)n;
-  slot.classes = h[1] & 3u;
+  slot.classes = h[1] & 7u;
   return SPX_OK;
 }
 
@@ -2500,6 +2642,11 @@ extern "C" int32_t spx_group_validate_offsets(spx_ctx* ctx, int64_t n, int64_t n
                                              int64_t ngroups, const int64_t* offs, const R* lambda_g,            \
                                              double* out) {                                                      \
     return value_group_binf<R>(ctx, n, xk, sj, y, false, 0.0, ngroups, offs, lambda_g, out);                     \
+  }                                                                                                              \
+  extern "C" int32_t spx_step_groupl2_##SUF(spx_ctx* ctx, int64_t n, R* s, R* xsy, const R* xk, const R* sj,     \
+                                            const R* grad, int64_t ngroups, const int64_t* offs,                 \
+                                            const R* lambda_g, double nu, double* out3) {                        \
+    return step_groupl2<R>(ctx, n, s, xsy, xk, sj, grad, ngroups, offs, lambda_g, nu, out3);                     \
   }
 
 SPX_DEFINE_GROUP(f64, double)

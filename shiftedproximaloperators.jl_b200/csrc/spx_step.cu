@@ -227,7 +227,7 @@ template <class R, bool WRITE> struct StepPost {
   }
 };
 
-template <class R> static int32_t step_pre(spx_ctx* ctx, int64_t n, R* q, const R* grad, double nu) {
+template <class R> int32_t step_pre(spx_ctx* ctx, int64_t n, R* q, const R* grad, double nu) {
   SPX_REQUIRE(ctx != nullptr, "null context");
   SPX_REQUIRE(n >= 0, "n < 0");
   SPX_REQUIRE(n == 0 || (q && grad), "null device vector");
@@ -241,8 +241,7 @@ template <class R> static int32_t step_pre(spx_ctx* ctx, int64_t n, R* q, const 
   return ew_launch(ctx, ctx->stream, op, n, 0, ctx->d_partials, &nb);
 }
 template <class R>
-static int32_t step_post(spx_ctx* ctx, int64_t n, R* xsy, const R* xk, const R* sj, const R* s, const R* grad,
-                         double* out2) {
+int32_t step_post(spx_ctx* ctx, int64_t n, R* xsy, const R* xk, const R* sj, const R* s, const R* grad, double* out2) {
   SPX_REQUIRE(ctx != nullptr, "null context");
   SPX_REQUIRE(n >= 0, "n < 0");
   SPX_REQUIRE(out2 != nullptr, "null result array");
@@ -263,6 +262,13 @@ static int32_t step_post(spx_ctx* ctx, int64_t n, R* xsy, const R* xk, const R* 
   out2[1] = ctx->h_result[0].s;
   return SPX_OK;
 }
+
+template int32_t step_pre<double>(spx_ctx*, int64_t, double*, const double*, double);
+template int32_t step_pre<float>(spx_ctx*, int64_t, float*, const float*, double);
+template int32_t step_post<double>(spx_ctx*, int64_t, double*, const double*, const double*, const double*, const double*,
+                                   double*);
+template int32_t step_post<float>(spx_ctx*, int64_t, float*, const float*, const float*, const float*, const float*,
+                                  double*);
 
 }  // namespace spx
 

@@ -612,6 +612,19 @@ class ShiftedGroupNormL2(_GroupBase):
                    _p(self._offs), _p(self._lam_g), C.byref(out))
         return out.value
 
+    def step_(self, s, grad, nu, xsy=None):
+        """spx_step_groupl2_*: the whole step in one pass when every group holds <= 256 elements (the C4 shape), the
+        two passes around prox! otherwise (decided in the library from the census of the validated layout)."""
+        self._check(s, grad, ("s", "grad"))
+        if xsy is not None:
+            _vec(xsy, self.xk, "xsy")
+        if s.data_ptr() == grad.data_ptr():
+            raise ValueError("step_: s must not alias grad")
+        out = (C.c_double * 3)()
+        self._call("step_groupl2", C.c_int64(self.n), _p(s), _p(xsy), _p(self.xk), _p(self.sj), _p(grad),
+                   C.c_int64(self.ngroups), _p(self._offs), _p(self._lam_g), C.c_double(nu), out)
+        return s, StepResult(out[0], math.sqrt(out[1]), out[2])
+
 
 class ShiftedGroupNormL2Binf(_GroupBase):
     """ShiftedGroupNormL2Binf  (src/shiftedGroupNormL2Binf.jl:3-60)."""

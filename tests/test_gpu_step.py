@@ -199,3 +199,60 @@ def test_step_composed_types(dt, kind):
     tg = T(grad)
     with pytest.raises(ValueError):
         sp.step_(tg, psi, tg, nu)
+
+
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("layout", ["g64", "short_ragged"])
+def test_step_groupl2_single_pass_on_short_group_layouts(dt, layout):
+    """ShiftedGroupNormL2 with every group <= 256 elements (the C4 shape): spx_step_groupl2_* runs the whole step in the
+    one pass of the packed warp rounds.  Same bars as above, the composed form of the same call (SPX_STEP_COMPOSED)
+    gives the same s bit for bit, and a layout rewritten after validation so that it holds a long group (stale census)
+    is still computed correctly (the kernel flags it and the call is redone the long way)."""
+    import os
+
+    rng = np.random.default_rng(7)
+    sizes = np.full(1500, 64) if layout == "g64" else rng.integers(1, 257, 1500)
+    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    n, nu = int(offs[-1]), 0.3
+    xk, sj, grad = inputs(n, dt)
+    lam_g = (dt(0.5) + orc.uniform(len(sizes), 12, dt)).astype(dt)
+    psi = sp.shifted(sp.shifted(sp.GroupNormL2(T(lam_g), None, offsets=T(offs)), T(xk)), T(sj))
+    s = torch.empty(n, dtype=T(grad).dtype, device=DEV)
+    xsy = torch.empty_like(s)
+
+    def check(offsets):
+        launches0 = sp.launch_count(DEV) if hasattr(sp, "launch_count") else None
+        _, res = sp.step_(s, psi, T(grad), nu, xsy=xsy)
+        q = (dt(-dt(nu)) * grad).astype(dt)
+        y = torch.empty_like(s)
+        sp.prox_(y, psi, T(q), nu)
+        assert np.array_equal(N(s), N(y))
+        assert np.array_equal(N(xsy), ((xk + sj) + N(s)).astype(dt))
+        gs = N(s)
+        g64, s64 = grad.astype(np.float64), gs.astype(np.float64)
+        scalars_close(res, orc.value_groupl2(xk, sj, gs, offsets, lam_g), float(np.sqrt(np.sum(s64 * s64))),
+                      float(np.sum(g64 * s64)), grad, gs, dt)
+        return res, launches0
+
+    res, _ = check(offs)
+    s_fused = s.clone()
+    os.environ["SPX_STEP_COMPOSED"] = "1"
+    try:
+        res_c, _ = check(offs)
+    finally:
+        del os.environ["SPX_STEP_COMPOSED"]
+    assert torch.equal(s, s_fused)
+    assert res_c.psi == pytest.approx(res.psi, rel=1e-12 if dt == np.float64 else 1e-6)
+    assert res_c.snorm == pytest.approx(res.snorm, rel=1e-12) and res_c.gdots == pytest.approx(res.gdots, rel=1e-9, abs=1e-9)
+    # stale census: same address, ngroups and n, but two neighbours merged into one long group and one group split
+    new = sizes.copy()
+    big = int(np.argmax(np.cumsum(new) > n // 2))
+    take = 0
+    j = big + 1
+    while new[big] + take <= 300:
+        take += new[j]; new[j] = 0; j += 1
+    new[big] += take
+    offs2 = np.concatenate([[0], np.cumsum(new)]).astype(np.int64)
+    assert offs2[-1] == n and np.max(new) > 256
+    psi._offs.copy_(T(offs2))
+    check(offs2)

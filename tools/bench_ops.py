@@ -146,7 +146,7 @@ def main():
     # groups of 64 (and ragged)
     for gname in ("g64", "ragged"):
         names = [f"prox_groupl2_{gname}", f"value_groupl2_{gname}", f"prox_groupl2binf_{gname}",
-                 "prox_groupl2binf_g64_biglambda"]
+                 "prox_groupl2binf_g64_biglambda", "step_groupl2_g64"]
         if not any(re.search(args.only, nm) for nm in names):
             continue
         if gname == "g64":
@@ -169,7 +169,7 @@ def main():
         if gname == "g64" and re.search(args.only, "step_groupl2_g64"):
             xsy_g = torch.empty_like(y)
             timeit("step_groupl2_g64", lambda psi=psi: sp.step_(y, psi, q, 0.3, xsy=xsy_g), 5 * R,
-                   note="pre (1R+1W) + prox! in place with fused psi + post (4R+1W); alg. bytes = 3 reads + 2 writes")
+                   note="spx_step_groupl2: one pass on this layout (groups <= 256); alg. bytes = 3 reads + 2 writes")
             del xsy_g
         psib = sp.shifted(sp.shifted(h, xk, 0.5, sp.NormLinf(1.0)), sj)
         timeit(f"prox_groupl2binf_{gname}", lambda psi=psib: sp.prox_(y, psi, q, 0.3), 4 * R, note=f"{ng} groups")
