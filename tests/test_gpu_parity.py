@@ -556,6 +556,27 @@ def test_group_l2binf_against_oracle(dt, layout):
     check_groupl2binf(N(y), xk, sj, q, offs, lam_g, sigma, delta, label=f"{dt.__name__} {layout}")
 
 
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("delta_frac", [0.5, 1e9])
+def test_l1b2_nan_in_xk_matches_the_oracle(dt, delta_frac):
+    """A NaN in xk makes every norm of the search NaN (the Float32 passes clamp with min/max instructions, which would
+    drop it: the packet's NaN flag puts it back): whatever the reference does with it -- the oracle restates it -- is
+    what comes out, NaN positions included."""
+    n = 50_001
+    xk, sj, q = inputs(n, dt)
+    y0 = orc.prox_l1b2(xk, sj, q, 1.0, 0.1, 1e30)
+    full = float(np.linalg.norm((y0 + sj).astype(np.float64)))
+    xk = xk.copy()
+    xk[12345] = np.nan
+    delta = delta_frac * full if delta_frac < 1e6 else 1e30
+    psi = sp.shifted(sp.shifted(sp.NormL1(1.0), T(xk), delta, sp.NormL2(1.0)), T(sj))
+    y = N(sp.prox(psi, T(q), 0.1))
+    ref = orc.prox_l1b2(xk, sj, q, 1.0, 0.1, delta)
+    assert np.array_equal(np.isnan(y), np.isnan(ref))
+    ok = ~np.isnan(ref)
+    assert np.all(np.abs(y[ok].astype(np.float64) - ref[ok].astype(np.float64)) <= 64 * eps(dt) * (np.abs(ref[ok]) + 1))
+
+
 # --------------------------------------------------------------------------- top-r ---
 @pytest.mark.parametrize("dt", DT)
 @pytest.mark.parametrize("n,r", [(6, 2), (1000, 1), (1000, 999), (1000, 1000), (1000, 2000), (16_384, 100),
