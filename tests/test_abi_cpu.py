@@ -105,3 +105,25 @@ def test_group_index_sets_must_be_contiguous_ranges():
         sp.GroupNormL2([1.0, 2.0], [range(3, 6), range(0, 3)])  # out of order
     with pytest.raises(ValueError, match="same"):
         sp.GroupNormL2([1.0], [range(0, 3), range(3, 6)])
+
+
+def test_library_holds_only_sm_100a_code_and_the_bulk_copy_kernels_use_tma():
+    """The shipped library is sm_100a-only (no PTX fallback, no other architecture), and the CTA-per-group kernels of
+    spx_group.cu stage their groups with bulk copies (UBLKCP in the SASS: cp.async.bulk completing on an mbarrier) --
+    checked on the built artefacts with cuobjdump (skipped when the toolkit is not on PATH)."""
+    import shutil
+    import subprocess
+
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    pkg = os.path.join(ROOT, "shiftedproximaloperators.jl_b200")
+    elfs = subprocess.run([cuobjdump, "-lelf", os.path.join(pkg, "libshiftedprox.so")], capture_output=True, text=True).stdout
+    names = [ln.split(":")[-1].strip() for ln in elfs.splitlines() if "ELF file" in ln]
+    assert names and all(n.endswith(".sm_100a.cubin") for n in names), names
+    ptx = subprocess.run([cuobjdump, "-lptx", os.path.join(pkg, "libshiftedprox.so")], capture_output=True, text=True).stdout
+    assert "PTX file" not in ptx
+    obj = os.path.join(pkg, "csrc", "build", "spx_group.o")
+    if os.path.exists(obj):
+        sass = subprocess.run([cuobjdump, "-sass", obj], capture_output=True, text=True).stdout
+        assert sass.count("UBLKCP") > 0 and "SYNCS" in sass  # bulk copy + mbarrier
