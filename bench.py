@@ -495,6 +495,12 @@ def run_configs(args, sp, L, shd, dev, dist, world, rank, peak, c2):
         c1[name] = entry(timed(lambda: sp.prox_(y, psi, q, SIGMA)), world * n, 32)
         c1[name + "+psi"] = entry(timed(lambda: sp.prox_(y, psi, q, SIGMA, want_value=True)), world * n, 32,
                                   note="psi(y) fused" + (", scalar all-reduced (NCCL)" if world > 1 else ""))
+        if n != 1_000_000:  # the solver step around this prox! in one pass (psi shifted once: 2 reads + 2 writes)
+            psi1 = sp.shifted(sp.NormL1(1.0), xk)
+            xsy = torch.empty_like(q)
+            c1[name + " step"] = entry(timed(lambda: sp.step_(y, psi1, q, SIGMA, xsy=xsy)), world * n, 32,
+                                       note="fused solver step (spx_step_sep): q = -nu grad, prox!, psi(s), xk + s, |s|, grad's")
+            del psi1, xsy
         if n == 1_000_000:  # launch-bound: the same call 32 times back to back (the four vectors, 32 MB, stay in L2)
             c1[name + "_x32_back_to_back"] = entry(timed(lambda: sp.prox_(y, psi, q, SIGMA), burst=32), world * n, 32,
                                                    note="time per call of 32 queued calls; operands L2-resident (32 MB)")
@@ -556,6 +562,13 @@ def run_configs(args, sp, L, shd, dev, dist, world, rank, peak, c2):
     c4["prox_groupl2_g64"] = entry(timed(lambda: sp.prox_(y, psi, q, 0.3)), world * n4, bpe)
     c4["prox_groupl2_g64+psi"] = entry(timed(lambda: sp.prox_(y, psi, q, 0.3, want_value=True)), world * n4, bpe,
                                        note="psi(y) fused" + (", scalar all-reduced (NCCL)" if world > 1 else ""))
+    # the solver step around this prox!: q = -nu grad, prox!, psi(s), xk + sj + s, |s|, grad's in
+    # ONE pass on this layout (spx_step_groupl2); q stands in for the gradient
+    xsy = torch.empty_like(q)
+    c4["step_groupl2_g64"] = entry(timed(lambda: sp.step_(y, psi, q, 0.3, xsy=xsy)), world * n4, 40 + 16.0 / 64,
+                                   note="fused solver step: 3 reads + 2 writes, three scalars"
+                                        + (" all-reduced on the device" if world > 1 else ""))
+    del xsy
     psib = sp.shifted(sp.shifted(h, xk, 0.5, sp.NormLinf(1.0)), sj)
     c4["prox_groupl2binf_g64"] = entry(timed(lambda: sp.prox_(y, psib, q, 0.3)), world * n4, bpe)
     import numpy as np
