@@ -363,7 +363,7 @@ typedef struct spx_box_job_f32 {
   /* The whole step of ShiftedGroupNormL2 (shiftedGroupNormL2.jl:52-79) in one call: ONE pass when   */ \
   /* every group of a validated layout holds <= 256 elements (spx_group_validate_offsets), the three */ \
   /* calls above otherwise.  out3_host as for spx_step_sep.  sj must be given (zeros when ψ is       */ \
-  /* shifted once); s must not alias grad.                                                            */ \
+  /* shifted once); s must not alias grad, xsy must not alias an input of the call.                   */ \
   int32_t spx_step_groupl2_##SUF(spx_ctx* ctx, int64_t n, R* s, R* xsy, const R* xk, const R* sj,    \
                                  const R* grad, int64_t ngroups, const int64_t* offs,                \
                                  const R* lambda_g, double nu, double* out3_host);                   \
